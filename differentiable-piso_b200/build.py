@@ -1,0 +1,54 @@
+"""Build libdpiso.so (hand-written CUDA kernels for sm_100a behind the C ABI of include/dpiso.h).
+
+    python differentiable-piso_b200/build.py [--force] [--verbose]
+
+nvcc cross-compiles without a GPU.  The library is written next to the Python package
+(differentiable-piso_b200/diffpiso_b200/libdpiso.so) so that it travels with the repo snapshot.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "diffpiso_b200", "libdpiso.so")
+SOURCES = ["piso_ops.cu", "pressure_cg.cu", "bicgstab.cu", "piso_adjoint.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "--threads", "4"]
+
+
+def _deps():
+    files = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    files.append(os.path.join(HERE, "..", "include", "dpiso.h"))
+    return files
+
+
+def build(force=False, verbose=False):
+    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    if not force and os.path.exists(OUT):
+        t = os.path.getmtime(OUT)
+        if all(os.path.getmtime(f) <= t for f in _deps()):
+            return OUT
+    objs = []
+    procs = []
+    for s in srcs:
+        o = os.path.join(CSRC, os.path.basename(s)[:-3] + ".o")
+        cmd = ["nvcc"] + NVCC_FLAGS + ["-c", s, "-o", o]
+        if verbose:
+            print(" ".join(cmd))
+        procs.append((subprocess.Popen(cmd), cmd))
+        objs.append(o)
+    for p, cmd in procs:
+        if p.wait() != 0:
+            raise RuntimeError("nvcc failed: " + " ".join(cmd))
+    cmd = ["nvcc", "-shared", "--cudart", "shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT] + objs
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    for o in objs:
+        os.remove(o)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -1,0 +1,405 @@
+// bicgstab.cu -- batched ILU(0)-preconditioned BiCGStab for the velocity predictor and its adjoint.
+//
+// Re-design of BicgstabIluLinearSolveLauncher (CUDAsrc/multi_bicgstab_ilu_linear_solve_op.cu.cc:85-453), which drives
+// cuSPARSE csrilu02 / csrsv2 / CsrmvEx and cuBLAS level-1 calls from the host (19 library launches and 6 blocking
+// reductions per iteration, one host thread per velocity component).  Here ONE persistent CTA owns one
+// (sample, component) system for the whole solve:
+//   * the matrix is re-packed once into a level-major ELL layout (rows ordered by the lx+ly wavefront, <= 6 entries
+//     per row, column order = ascending original column so that every sum is accumulated in CSR order);
+//   * ILU(0) and the four triangular solves per iteration sweep the wavefront levels inside the kernel; the vector
+//     being solved for lives in shared memory, so the dependent chain of a level is smem -> FMA -> smem, and the
+//     next level's coefficients are prefetched into registers before the level barrier (a named barrier over the
+//     participating warps only);
+//   * SpMVs read the preconditioned vector straight from shared memory; dot products / norms are accumulated in
+//     fp64 per thread, reduced with warp shuffles and a shared-memory stage, and consumed on the device -- no scalar
+//     ever returns to the host; convergence tests, the restart rule and the NaN warning follow the reference.
+// The transposed solve of the adjoint uses tables built for A^T (the reference transposes with csr2csc and
+// factorises again, ":113-134"); the kernels are identical.
+#include "rows.cuh"
+
+namespace dpiso {
+
+constexpr int kBicgThreads = 1024;
+constexpr int kMaxWa = 6;
+
+struct BicgTab {
+    int n, n_levels, wa, max_level;
+    const int *level_ptr, *perm, *a_col, *a_src, *a_rev;
+};
+
+struct BicgParams {
+    BicgTab tab[2];
+    int nnz[2];            // CSR entries of component 0, 1
+    int n_face;            // n_u + n_v
+    int nnz_total;
+    int n_max;             // max(n_u, n_v): plane stride inside the workspace
+    int zs_in_smem;
+    size_t ws_floats;      // per system
+    const float *values, *rhs, *x0;
+    float *x;
+    int *stats;
+    uint8_t *warn;
+    float *workspace;
+    float tol;
+    int max_it;
+};
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block-wide sum of two doubles, result broadcast to every thread (2 barriers)
+__device__ __forceinline__ void block_sum2(double &a, double &b, double *scratch /* [64] */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    a = warp_sum_d(a); b = warp_sum_d(b);
+    __syncthreads();                      // scratch free (previous result consumed)
+    if (lane == 0) { scratch[warp] = a; scratch[32 + warp] = b; }
+    __syncthreads();
+    double va = lane < nw ? scratch[lane] : 0.0, vb = lane < nw ? scratch[32 + lane] : 0.0;
+    a = warp_sum_d(va); b = warp_sum_d(vb);
+}
+
+__device__ __forceinline__ void named_bar(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+struct RowRegs {
+    int q;                 // row (level-major position) handled by this thread in this level, -1 = none
+    int col[kMaxWa];
+    float val[kMaxWa];
+    float aux[kMaxWa];     // MODE 0: upper entry u(col, q) paired with the k-th entry (0 when absent)
+    float rhs;
+};
+
+// One wavefront sweep over the level-major rows.
+//   MODE 0: ILU(0) factorisation  (in: a_val planes, out: lu planes, zs = pivots)
+//   MODE 1: L solve   zs[q] = in[q] - sum_{col<q} lu*zs[col]
+//   MODE 2: U solve   zs[q] = (zs[q] - sum_{col>q} lu*zs[col]) / lu_diag
+template <int MODE>
+__device__ void wavefront(const BicgTab &T, int n_max, const float *__restrict__ values_c, const float *a_val,
+                          float *lu, const float *in, float *zs) {
+    const int wa = T.wa, n = T.n;
+    const int P = min((int)blockDim.x, (T.max_level + 31) & ~31);
+    const int t = threadIdx.x;
+    __syncthreads();
+    if (t < P) {
+        const int nl = T.n_levels;
+        for (int s = 0; s < nl; s++) {
+            const int d = MODE == 2 ? nl - 1 - s : s;
+            const int q0 = T.level_ptr[d], q1 = T.level_ptr[d + 1];
+            for (int q = q0 + t; q < q1; q += P) {
+                if (MODE == 0) {
+                    float diag = 0.0f;
+                    int dslot = 0;
+                    // pivot of this row first (needed as the fma accumulator), then the L entries in column order
+                    for (int k = 0; k < wa; k++)
+                        if (T.a_col[k * n + q] == q && T.a_src[k * n + q] >= 0) { dslot = k; diag = a_val[k * n_max + q]; }
+                    for (int k = 0; k < wa; k++) {
+                        const int col = T.a_col[k * n + q];
+                        const float a = a_val[k * n_max + q];
+                        if (col < q) {
+                            const float lik = __fdiv_rn(a, zs[col]);
+                            lu[k * n_max + q] = lik;
+                            const int rev = T.a_rev[k * n + q];
+                            if (rev >= 0) diag = fmaf(-lik, values_c[rev], diag);
+                        } else if (k != dslot) {
+                            lu[k * n_max + q] = a;                    // U entries are unchanged by ILU(0) on this pattern
+                        }
+                    }
+                    lu[dslot * n_max + q] = diag;
+                    zs[q] = diag;
+                } else if (MODE == 1) {
+                    float acc = in[q];
+                    for (int k = 0; k < wa; k++) {
+                        const int col = T.a_col[k * n + q];
+                        if (col < q) acc = fmaf(-lu[k * n_max + q], zs[col], acc);
+                    }
+                    zs[q] = acc;
+                } else {
+                    float acc = zs[q], dg = 1.0f;
+                    for (int k = 0; k < wa; k++) {
+                        const int col = T.a_col[k * n + q];
+                        const float l = lu[k * n_max + q];
+                        if (col > q) acc = fmaf(-l, zs[col], acc);
+                        else if (col == q && T.a_src[k * n + q] >= 0) dg = l;
+                    }
+                    zs[q] = __fdiv_rn(acc, dg);
+                }
+            }
+            named_bar(1, P);
+        }
+    }
+    __syncthreads();
+}
+
+// fast path: at most one row per participating thread and level; the next level's row is prefetched before the
+// barrier so that the critical path of a level is  smem load -> fma chain -> smem store -> bar.sync
+template <int MODE>
+__device__ void wavefront_prefetch(const BicgTab &T, int n_max, const float *__restrict__ values_c, const float *a_val,
+                                   float *lu, const float *in, float *zs) {
+    const int wa = T.wa, n = T.n;
+    const int P = (T.max_level + 31) & ~31;
+    const int t = threadIdx.x;
+    __syncthreads();
+    if (t < P) {
+        const int nl = T.n_levels;
+        RowRegs cur, nxt;
+        auto load = [&](RowRegs &R, int s) {
+            int q = -1;
+            if (s < nl) {
+                const int d = MODE == 2 ? nl - 1 - s : s;
+                q = T.level_ptr[d] + t;
+                if (q >= T.level_ptr[d + 1]) q = -1;
+            }
+            R.q = q;
+            const float *src_val = MODE == 0 ? a_val : lu;
+#pragma unroll
+            for (int k = 0; k < kMaxWa; k++) {
+                const bool on = q >= 0 && k < wa;
+                R.col[k] = on ? T.a_col[k * n + q] : -1;
+                R.val[k] = on ? src_val[k * n_max + q] : 0.0f;
+                if (MODE == 0) {
+                    const int rev = on ? T.a_rev[k * n + q] : -1;
+                    R.aux[k] = rev >= 0 ? values_c[rev] : 0.0f;
+                }
+            }
+            R.rhs = (q >= 0 && MODE == 1) ? in[q] : 0.0f;
+        };
+        load(cur, 0);
+        for (int s = 0; s < nl; s++) {
+            load(nxt, s + 1);
+            const int q = cur.q;
+            if (q >= 0) {
+                if (MODE == 0) {
+                    // pivot = first self entry in column order (padding, also col == q, sits behind the real entries)
+                    float diag = 0.0f;
+                    int dslot = -1;
+#pragma unroll
+                    for (int k = 0; k < kMaxWa; k++)
+                        if (cur.col[k] == q && dslot < 0) { dslot = k; diag = cur.val[k]; }
+#pragma unroll
+                    for (int k = 0; k < kMaxWa; k++) {
+                        if (k < wa) {
+                            if (cur.col[k] >= 0 && cur.col[k] < q) {
+                                const float lik = __fdiv_rn(cur.val[k], zs[cur.col[k]]);
+                                lu[k * n_max + q] = lik;
+                                diag = fmaf(-lik, cur.aux[k], diag);
+                            } else if (k != dslot) {
+                                lu[k * n_max + q] = cur.val[k];
+                            }
+                        }
+                    }
+                    lu[dslot * n_max + q] = diag;
+                    zs[q] = diag;
+                } else if (MODE == 1) {
+                    float acc = cur.rhs;
+#pragma unroll
+                    for (int k = 0; k < kMaxWa; k++)
+                        if (cur.col[k] >= 0 && cur.col[k] < q) acc = fmaf(-cur.val[k], zs[cur.col[k]], acc);
+                    zs[q] = acc;
+                } else {
+                    float acc = zs[q], dg = 1.0f;
+                    bool seen_diag = false;
+#pragma unroll
+                    for (int k = 0; k < kMaxWa; k++) {
+                        if (cur.col[k] > q) acc = fmaf(-cur.val[k], zs[cur.col[k]], acc);
+                        else if (cur.col[k] == q && !seen_diag) { dg = cur.val[k]; seen_diag = true; }
+                    }
+                    zs[q] = __fdiv_rn(acc, dg);
+                }
+            }
+            named_bar(1, P);
+            cur = nxt;
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_kernel(const BicgParams prm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double red[64];
+    const int sys = blockIdx.x;
+    const int sample = sys >> 1, comp = sys & 1;
+    const BicgTab &T = prm.tab[comp];
+    const int n = T.n, wa = T.wa, n_max = prm.n_max;
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const int face_off = comp ? prm.tab[0].n : 0;
+    const float *values_c = prm.values + (size_t)sample * prm.nnz_total + (comp ? prm.nnz[0] : 0);
+    const int nnz_c = prm.nnz[comp];
+    const float *rhs_g = prm.rhs + (size_t)sample * prm.n_face + face_off;
+    const float *x0_g = prm.x0 + (size_t)sample * prm.n_face + face_off;
+    float *x_g = prm.x + (size_t)sample * prm.n_face + face_off;
+
+    float *ws = prm.workspace + (size_t)sys * prm.ws_floats;
+    float *a_val = ws;                       // [kMaxWa][n_max]
+    float *lu = a_val + (size_t)kMaxWa * n_max;
+    float *b = lu + (size_t)kMaxWa * n_max;
+    float *x = b + n_max, *r = x + n_max, *rh = r + n_max, *p = rh + n_max, *v = p + n_max, *tt = v + n_max;
+    float *zs = prm.zs_in_smem ? (float *)smem_raw : tt + n_max;
+
+    // ---- setup: permuted copies, NaN guard (":245-256") ------------------------------------------------------
+    double nv = 0.0, nb = 0.0;
+    for (int i = tid; i < nnz_c; i += NT) { const double a = values_c[i]; nv += a * a; }
+    for (int q = tid; q < n; q += NT) {
+        const int orig = T.perm[q];
+        const float bq = rhs_g[orig];
+        b[q] = bq; nb += (double)bq * bq;
+        x[q] = x0_g[orig];                                           // cublasScopy(x_old -> x) (":261")
+        for (int k = 0; k < wa; k++) {
+            const int src = T.a_src[k * n + q];
+            a_val[k * n_max + q] = src >= 0 ? values_c[src] : 0.0f;
+        }
+    }
+    block_sum2(nv, nb, red);
+    int warn = (isnan((float)sqrt(nv)) || isnan((float)sqrt(nb))) ? 1 : 0;
+
+    // ---- ILU(0) (csrilu02, ":181-218") ---------------------------------------------------------------------
+    const bool fast = ((T.max_level + 31) & ~31) <= NT;
+    if (fast) wavefront_prefetch<0>(T, n_max, values_c, a_val, lu, nullptr, zs);
+    else wavefront<0>(T, n_max, values_c, a_val, lu, nullptr, zs);
+
+    auto precondition = [&](const float *src) {                      // zs = U^-1 L^-1 src   (csrsv2 x2, ":321-327")
+        if (fast) {
+            wavefront_prefetch<1>(T, n_max, nullptr, nullptr, lu, src, zs);
+            wavefront_prefetch<2>(T, n_max, nullptr, nullptr, lu, nullptr, zs);
+        } else {
+            wavefront<1>(T, n_max, nullptr, nullptr, lu, src, zs);
+            wavefront<2>(T, n_max, nullptr, nullptr, lu, nullptr, zs);
+        }
+    };
+    auto spmv_row = [&](const float *vec, int q) {                   // CsrmvEx row: fma in ascending column order
+        float acc = 0.0f;
+        for (int k = 0; k < wa; k++) acc = fmaf(a_val[k * n_max + q], vec[T.a_col[k * n + q]], acc);
+        return acc;
+    };
+
+    float alpha = 1.f, rho = 1.f, rhop = 1.f, omega = 1.f, beta, nrm_r = 0.f;
+    int it_count = 0, restarts = 0, exit_kind = 3;
+    const float tol = prm.tol;
+
+    for (int restart = 0; restart < 2; restart++) {
+        restarts = restart;
+        // r = b - A x  (":275-282"); x is in global memory -> stage it through zs for the gather
+        for (int q = tid; q < n; q += NT) zs[q] = x[q];
+        __syncthreads();
+        double s0 = 0.0, s1 = 0.0;
+        for (int q = tid; q < n; q += NT) {
+            const float rq = __fsub_rn(b[q], spmv_row(zs, q));
+            r[q] = rq; s0 += (double)rq * rq;
+        }
+        block_sum2(s0, s1, red);
+        nrm_r = (float)sqrt(s0);
+        if (nrm_r < tol) { exit_kind = 0; break; }                   // lucky guess (":287-289")
+        for (int q = tid; q < n; q += NT) { rh[q] = r[q]; p[q] = 0.0f; v[q] = 0.0f; }
+        exit_kind = 3;
+        float rho_next = (float)s0;                                  // r.rh with rh = r
+        for (int it = 0; it < prm.max_it; it++) {
+            it_count++;
+            rhop = rho;
+            rho = rho_next;
+            beta = __fmul_rn(__fdiv_rn(rho, rhop), __fdiv_rn(alpha, omega));
+            __syncthreads();
+            for (int q = tid; q < n; q += NT) {                      // p = r + beta (p - omega v)  (":315-317")
+                float pq = fmaf(-omega, v[q], p[q]);
+                pq = __fmul_rn(beta, pq);
+                p[q] = __fadd_rn(pq, r[q]);
+            }
+            precondition(p);                                         // zs = p_hat
+            s0 = 0.0; s1 = 0.0;
+            for (int q = tid; q < n; q += NT) {                      // v = A p_hat ; rh.v
+                const float vq = spmv_row(zs, q);
+                v[q] = vq; s0 += (double)rh[q] * vq;
+            }
+            block_sum2(s0, s1, red);
+            alpha = __fdiv_rn(rho, (float)s0);
+            s0 = 0.0; s1 = 0.0;
+            for (int q = tid; q < n; q += NT) {                      // x += alpha p_hat ; r -= alpha v ; |r|
+                x[q] = fmaf(alpha, zs[q], x[q]);
+                const float rq = fmaf(-alpha, v[q], r[q]);
+                r[q] = rq; s0 += (double)rq * rq;
+            }
+            block_sum2(s0, s1, red);
+            nrm_r = (float)sqrt(s0);
+            if (nrm_r < tol) { exit_kind = 1; break; }
+            precondition(r);                                         // zs = s_hat
+            s0 = 0.0; s1 = 0.0;
+            for (int q = tid; q < n; q += NT) {                      // t = A s_hat ; t.r ; t.t
+                const float tq = spmv_row(zs, q);
+                tt[q] = tq; s0 += (double)tq * r[q]; s1 += (double)tq * tq;
+            }
+            block_sum2(s0, s1, red);
+            omega = __fdiv_rn((float)s0, (float)s1);
+            s0 = 0.0; s1 = 0.0;
+            for (int q = tid; q < n; q += NT) {                      // x += omega s_hat ; r -= omega t ; |r| ; r.rh
+                x[q] = fmaf(omega, zs[q], x[q]);
+                const float rq = fmaf(-omega, tt[q], r[q]);
+                r[q] = rq; s0 += (double)rq * rq; s1 += (double)rq * rh[q];
+            }
+            block_sum2(s0, s1, red);
+            nrm_r = (float)sqrt(s0);
+            rho_next = (float)s1;
+            if (nrm_r < tol) { exit_kind = 2; break; }
+        }
+        if (nrm_r > __fmul_rn(tol, 100.0f) || isnan(nrm_r)) {        // ":392-404"
+            __syncthreads();
+            for (int q = tid; q < n; q += NT) x[q] = 0.0f;
+            if (restart == 1) restarts = 2;
+        } else break;
+    }
+    __syncthreads();
+    for (int q = tid; q < n; q += NT) x_g[T.perm[q]] = x[q];
+    if (tid == 0) {
+        int *st = prm.stats + (size_t)sys * 4;
+        st[0] = it_count; st[1] = restarts; st[2] = warn; st[3] = exit_kind;
+        if (warn) *prm.warn = 1;
+    }
+}
+
+}  // namespace dpiso
+
+using namespace dpiso;
+
+static void to_tab(const dpiso_bicg_tables *h, BicgTab &t) {
+    t.n = h->n; t.n_levels = h->n_levels; t.wa = h->wa; t.max_level = h->max_level;
+    t.level_ptr = h->level_ptr; t.perm = h->perm; t.a_col = h->a_col; t.a_src = h->a_src; t.a_rev = h->a_rev;
+}
+
+extern "C" {
+
+size_t dpiso_bicgstab_workspace_floats(const dpiso_bicg_tables *h_tab_u, const dpiso_bicg_tables *h_tab_v) {
+    const size_t n_max = (size_t)(h_tab_u->n > h_tab_v->n ? h_tab_u->n : h_tab_v->n);
+    return (2 * (size_t)kMaxWa + 8) * n_max;
+}
+
+int dpiso_bicgstab_ilu(int batch, const dpiso_bicg_tables *h_tab_u, const dpiso_bicg_tables *h_tab_v, int nnz_u,
+                       int nnz_v, const float *values, const float *rhs, const float *x0, float tol, int max_it,
+                       float *x, int *stats, uint8_t *warn, float *workspace, void *stream) {
+    DPISO_REQUIRE(batch >= 1 && h_tab_u && h_tab_v, "bad arguments");
+    DPISO_REQUIRE(values && rhs && x0 && x && stats && warn && workspace, "null pointer");
+    DPISO_REQUIRE(h_tab_u->wa >= 1 && h_tab_u->wa <= kMaxWa && h_tab_v->wa >= 1 && h_tab_v->wa <= kMaxWa,
+                  "ELL width out of range");
+    BicgParams prm;
+    to_tab(h_tab_u, prm.tab[0]);
+    to_tab(h_tab_v, prm.tab[1]);
+    prm.nnz[0] = nnz_u; prm.nnz[1] = nnz_v; prm.nnz_total = nnz_u + nnz_v;
+    prm.n_face = h_tab_u->n + h_tab_v->n;
+    prm.n_max = h_tab_u->n > h_tab_v->n ? h_tab_u->n : h_tab_v->n;
+    prm.ws_floats = dpiso_bicgstab_workspace_floats(h_tab_u, h_tab_v);
+    prm.values = values; prm.rhs = rhs; prm.x0 = x0; prm.x = x; prm.stats = stats; prm.warn = warn;
+    prm.workspace = workspace; prm.tol = tol; prm.max_it = max_it;
+    const size_t smem_need = (size_t)prm.n_max * sizeof(float);
+    prm.zs_in_smem = smem_need <= 200 * 1024 ? 1 : 0;
+    const size_t smem = prm.zs_in_smem ? smem_need : 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+        DPISO_CUDA_TRY(cudaFuncSetAttribute(bicgstab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    bicgstab_kernel<<<batch * 2, kBicgThreads, smem, (cudaStream_t)stream>>>(prm);
+    DPISO_CHECK_LAUNCH();
+    return DPISO_OK;
+}
+
+}  // extern "C"

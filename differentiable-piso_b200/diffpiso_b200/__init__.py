@@ -1,0 +1,14 @@
+"""diffpiso_b200 -- B200-native PISO step (hot path of tum-pbs/differentiable-piso) behind the reference's operator
+surface.  Importing this package loads libdpiso.so (sm_100a kernels); there is no CPU or library fallback."""
+from . import _native
+from .grids import (CenteredGrid, StaggeredGrid, flatten_staggered_data, stack_staggered_components,
+                    stagger_flattened_data, unstack_staggered_tensor)
+from .linear_solver import LinearSolver, LinearSolverCudaBicgstabILU, LinearSolverCudaMultiBicgstabILU
+from .ops import Geometry
+from .piso import SimulationParameters, advection_matrix_cuda, piso_step, pressure_extrapolation
+from .pressure_solver import PisoPressureSolverCudaCustom, PoissonSolver
+
+__all__ = ["CenteredGrid", "StaggeredGrid", "flatten_staggered_data", "stagger_flattened_data",
+           "stack_staggered_components", "unstack_staggered_tensor", "LinearSolver", "LinearSolverCudaBicgstabILU",
+           "LinearSolverCudaMultiBicgstabILU", "PisoPressureSolverCudaCustom", "PoissonSolver", "SimulationParameters",
+           "piso_step", "advection_matrix_cuda", "pressure_extrapolation", "Geometry"]

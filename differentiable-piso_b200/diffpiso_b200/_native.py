@@ -1,0 +1,95 @@
+"""ctypes binding of libdpiso.so (the C ABI declared in include/dpiso.h).
+
+The product path has NO fallback: if the library cannot be loaded (or built with nvcc) importing this module raises,
+and every call raises `DpisoError` on a non-zero status.  Tensors are passed as raw device pointers together with the
+current torch CUDA stream; PyTorch is only the allocator / stream owner here.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libdpiso.so")
+
+
+class DpisoError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(_LIB_PATH):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("dpiso_build", os.path.join(_HERE, "..", "build.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mod.build()
+    return C.CDLL(_LIB_PATH)
+
+
+lib = _load()
+
+
+class BicgTables(C.Structure):
+    _fields_ = [("n", C.c_int), ("n_levels", C.c_int), ("wa", C.c_int), ("max_level", C.c_int),
+                ("level_ptr", C.c_void_p), ("perm", C.c_void_p), ("a_col", C.c_void_p), ("a_src", C.c_void_p),
+                ("a_rev", C.c_void_p)]
+
+
+_I, _F, _P, _SZ = C.c_int, C.c_float, C.c_void_p, C.c_size_t
+_SIGS = {
+    "dpiso_version": ([], _I),
+    "dpiso_last_error": ([], C.c_char_p),
+    "dpiso_sizes": ([_I, _I, _I, _I, _P, _P], _I),
+    "dpiso_csr_structure": ([_I, _I, _I, _I, _P, _P, _P], _I),
+    "dpiso_assemble": ([_I, _I, _I, _I, _I, _F, _F, _F, _P, _P, _P, _P, _P, _I, _P, _P, _P], _I),
+    "dpiso_predictor_rhs": ([_I, _I, _I, _F, _F, _F, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P], _I),
+    "dpiso_fv_gradient": ([_I, _I, _I, _F, _F, _P, _P, _P, _P, _P], _I),
+    "dpiso_fv_divergence": ([_I, _I, _I, _F, _F, _P, _P, _F, _P, _P], _I),
+    "dpiso_corrector1": ([_I, _I, _I, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P], _I),
+    "dpiso_h_apply": ([_I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P], _I),
+    "dpiso_corrector2": ([_I, _I, _I, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P], _I),
+    "dpiso_fv_gradient_adj": ([_I, _I, _I, _F, _F, _P, _P, _P, _P, _F, _F, _I, _P, _P, _P], _I),
+    "dpiso_fv_divergence_adj": ([_I, _I, _I, _I, _I, _F, _F, _P, _P, _P, _F, _P, _P], _I),
+    "dpiso_h_apply_adj": ([_I, _P, _P, _I, _I, _F, _P, _P, _P, _P, _P], _I),
+    "dpiso_predictor_rhs_adj": ([_I, _I, _I, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P], _I),
+    "dpiso_bicgstab_workspace_floats": ([_P, _P], _SZ),
+    "dpiso_bicgstab_ilu": ([_I, _P, _P, _I, _I, _P, _P, _P, _F, _I, _P, _P, _P, _P, _P], _I),
+    "dpiso_laplace_f64": ([_I, _I, _I, _P, _P, _P, _I, _F, _F, _P, _P], _I),
+    "dpiso_laplace_f32": ([_I, _I, _I, _P, _P, _P, _I, _F, _F, _P, _P], _I),
+    "dpiso_pressure_cg_f64": ([_I, _I, _I, _I, _I, _P, _P, _F, _I, _I, _I, _P, _P, _P, _P], _I),
+    "dpiso_pressure_cg_f32": ([_I, _I, _I, _I, _I, _P, _P, _F, _I, _I, _I, _P, _P, _P, _P], _I),
+    "dpiso_pressure_cg_mixed": ([_I, _I, _I, _I, _I, _P, _P, _F, _I, _I, _I, _P, _P, _P], _I),
+    "dpiso_pressure_cg_last_config": ([_P], _I),
+    "dpiso_pressure_cg_set_tuning": ([_I, _I], _I),
+}
+for _name, (_args, _res) in _SIGS.items():
+    _fn = getattr(lib, _name)
+    _fn.argtypes = _args
+    _fn.restype = _res
+
+EXPORTS = tuple(_SIGS)
+
+
+def ptr(t):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise DpisoError("libdpiso needs CUDA tensors (got a %s tensor): there is no CPU path" % t.device)
+    if not t.is_contiguous():
+        raise DpisoError("libdpiso needs contiguous tensors")
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def check(rc, what):
+    if rc != 0:
+        raise DpisoError("%s failed (%d): %s" % (what, rc, lib.dpiso_last_error().decode()))
+
+
+def int4(values):
+    return (C.c_int * 4)(*[int(v) for v in values])

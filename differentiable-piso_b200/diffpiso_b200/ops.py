@@ -1,0 +1,269 @@
+"""Thin torch-tensor front-ends of the C ABI (one function per entry point) plus the cached per-grid state.
+
+Everything here allocates outputs with torch and enqueues the native kernel on the current torch stream.  No
+arithmetic happens in Python and there is no fallback path.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native as N
+from . import structure as S
+
+
+class Geometry(object):
+    """Static per-grid state on one device: sizes, periodic flags, device copies of the BiCGStab tables."""
+
+    _cache = {}
+
+    def __init__(self, ny, nx, per_y, per_x, device):
+        self.ny, self.nx, self.per_y, self.per_x = int(ny), int(nx), bool(per_y), bool(per_x)
+        self.device = torch.device(device)
+        self.n_u, self.n_v, self.nnz_u, self.nnz_v = S.sizes(self.ny, self.nx, self.per_x, self.per_y)
+        self.nf, self.nc, self.nnz = self.n_u + self.n_v, self.ny * self.nx, self.nnz_u + self.nnz_v
+        self._tables = {}
+        self._csr = None
+
+    @classmethod
+    def get(cls, ny, nx, per_y, per_x, device):
+        key = (int(ny), int(nx), bool(per_y), bool(per_x), str(torch.device(device)))
+        g = cls._cache.get(key)
+        if g is None:
+            g = cls._cache[key] = cls(ny, nx, per_y, per_x, device)
+        return g
+
+    def tables(self, transpose):
+        """(BicgTables_u, BicgTables_v) ctypes structs whose pointers reference cached device tensors."""
+        t = self._tables.get(bool(transpose))
+        if t is None:
+            structs, keep = [], []
+            for comp in (0, 1):
+                h = S.bicg_tables(self.ny, self.nx, self.per_x, self.per_y, comp, bool(transpose))
+                dev = {k: torch.from_numpy(h[k]).to(self.device) for k in ("level_ptr", "perm", "a_col", "a_src", "a_rev")}
+                st = N.BicgTables(h["n"], h["n_levels"], h["wa"], h["max_level"], dev["level_ptr"].data_ptr(),
+                                  dev["perm"].data_ptr(), dev["a_col"].data_ptr(), dev["a_src"].data_ptr(),
+                                  dev["a_rev"].data_ptr())
+                structs.append(st)
+                keep.append(dev)
+            t = self._tables[bool(transpose)] = (structs[0], structs[1], keep)
+        return t[0], t[1]
+
+    def csr_structure(self):
+        """(row_ptr, col_ind) int32 device tensors in the reference layout, from the device kernel."""
+        if self._csr is None:
+            rp = torch.empty(self.nf + 2, dtype=torch.int32, device=self.device)
+            ci = torch.empty(self.nnz, dtype=torch.int32, device=self.device)
+            N.check(N.lib.dpiso_csr_structure(self.ny, self.nx, int(self.per_x), int(self.per_y), N.ptr(rp), N.ptr(ci),
+                                              N.stream()), "dpiso_csr_structure")
+            self._csr = (rp, ci)
+        return self._csr
+
+
+def _f32(t):
+    return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.to(torch.float32).contiguous()
+
+
+def assemble(g, vel, dirichlet_u8, active, noslip_u8, visc, dy, dx, beta):
+    """-> values [B, nnz], a_diag [B, nf]   (advection_matrix_cuda, diffpiso/piso_tf.py:85-137)"""
+    vel = _f32(vel)
+    b = vel.shape[0]
+    visc = _f32(visc).reshape(-1) if visc.dim() < 2 else _f32(visc)
+    if visc.numel() == 1:
+        mode = 0
+    elif visc.dim() == 1 and visc.numel() == g.nf:
+        mode = 1
+    elif visc.dim() == 2 and tuple(visc.shape) == (b, g.nf):
+        mode = 2
+    elif visc.dim() == 2 and tuple(visc.shape) == (1, g.nf):
+        mode, visc = 1, visc.reshape(-1)
+    else:
+        raise ValueError("viscosity must be a scalar or a flat [u, v] face field")
+    values = torch.empty((b, g.nnz), dtype=torch.float32, device=vel.device)
+    a_diag = torch.empty((b, g.nf), dtype=torch.float32, device=vel.device)
+    N.check(N.lib.dpiso_assemble(b, g.ny, g.nx, int(g.per_x), int(g.per_y), dy, dx, beta, N.ptr(vel), N.ptr(dirichlet_u8),
+                                 N.ptr(active), N.ptr(noslip_u8), N.ptr(visc), mode, N.ptr(values), N.ptr(a_diag),
+                                 N.stream()), "dpiso_assemble")
+    return values, a_diag
+
+
+def predictor_rhs(g, vel, pres, access, dirichlet_u8, dvals, forcing, dy, dx, beta, pbc):
+    vel, pres, dvals = _f32(vel), _f32(pres), _f32(dvals)
+    b = vel.shape[0]
+    forcing = None if forcing is None else _f32(forcing)
+    if dvals.dim() != 2 or dvals.shape[0] not in (1, b) or dvals.shape[1] != g.nf:
+        raise ValueError("dirichlet values must be [1 or B, n_u+n_v]")
+    rhs = torch.empty_like(vel)
+    N.check(N.lib.dpiso_predictor_rhs(b, g.ny, g.nx, dy, dx, beta, N.int4(pbc), N.ptr(vel), N.ptr(pres), N.ptr(access),
+                                      N.ptr(dirichlet_u8), N.ptr(dvals), int(dvals.shape[0] == b), N.ptr(forcing),
+                                      N.ptr(rhs), N.stream()), "dpiso_predictor_rhs")
+    return rhs
+
+
+def fv_gradient(g, p, access, dy, dx, pbc):
+    p = _f32(p)
+    b = p.shape[0]
+    out = torch.empty((b, g.nf), dtype=torch.float32, device=p.device)
+    N.check(N.lib.dpiso_fv_gradient(b, g.ny, g.nx, dy, dx, N.int4(pbc), N.ptr(access), N.ptr(p), N.ptr(out), N.stream()),
+            "dpiso_fv_gradient")
+    return out
+
+
+def fv_divergence(g, vel, dy, dx, a_diag=None, beta=0.0):
+    vel = _f32(vel)
+    b = vel.shape[0]
+    out = torch.empty((b, g.nc), dtype=torch.float32, device=vel.device)
+    N.check(N.lib.dpiso_fv_divergence(b, g.ny, g.nx, dy, dx, N.ptr(vel), N.ptr(a_diag), beta, N.ptr(out), N.stream()),
+            "dpiso_fv_divergence")
+    return out
+
+
+def corrector1(g, u_star, p1, a_diag, access, dy, dx, beta, pbc):
+    out = torch.empty_like(u_star)
+    N.check(N.lib.dpiso_corrector1(u_star.shape[0], g.ny, g.nx, dy, dx, beta, N.int4(pbc), N.ptr(access), N.ptr(u_star),
+                                   N.ptr(_f32(p1)), N.ptr(a_diag), N.ptr(out), N.stream()), "dpiso_corrector1")
+    return out
+
+
+def h_apply(g, values, a_diag, u_star, u_s2, beta):
+    out = torch.empty_like(u_star)
+    N.check(N.lib.dpiso_h_apply(u_star.shape[0], g.ny, g.nx, int(g.per_x), int(g.per_y), beta, N.ptr(values),
+                                N.ptr(a_diag), N.ptr(u_star), N.ptr(u_s2), N.ptr(out), N.stream()), "dpiso_h_apply")
+    return out
+
+
+def corrector2(g, u_s2, h, p2, a_diag, p, p1, access, dy, dx, beta, pbc):
+    u_next = torch.empty_like(u_s2)
+    p_next = torch.empty_like(p)
+    N.check(N.lib.dpiso_corrector2(u_s2.shape[0], g.ny, g.nx, dy, dx, beta, N.int4(pbc), N.ptr(access), N.ptr(u_s2),
+                                   N.ptr(h), N.ptr(_f32(p2)), N.ptr(a_diag), N.ptr(_f32(p)), N.ptr(_f32(p1)),
+                                   N.ptr(u_next), N.ptr(p_next), N.stream()), "dpiso_corrector2")
+    return u_next, p_next
+
+
+def fv_gradient_adj(g, gs, access, dy, dx, pbc, a_diag=None, beta=0.0, divisor=1.0, negate=False, base=None):
+    gs = _f32(gs)
+    b = gs.shape[0]
+    out = torch.empty((b, g.nc), dtype=torch.float32, device=gs.device)
+    N.check(N.lib.dpiso_fv_gradient_adj(b, g.ny, g.nx, dy, dx, N.int4(pbc), N.ptr(access), N.ptr(gs), N.ptr(a_diag), beta,
+                                        divisor, int(negate), N.ptr(None if base is None else _f32(base)), N.ptr(out),
+                                        N.stream()), "dpiso_fv_gradient_adj")
+    return out
+
+
+def fv_divergence_adj(g, gc, dy, dx, base=None, a_diag=None, beta=0.0):
+    gc = _f32(gc)
+    b = gc.shape[0]
+    out = torch.empty((b, g.nf), dtype=torch.float32, device=gc.device)
+    N.check(N.lib.dpiso_fv_divergence_adj(b, g.ny, g.nx, int(g.per_x), int(g.per_y), dy, dx, N.ptr(gc),
+                                          N.ptr(None if base is None else _f32(base)), N.ptr(a_diag), beta, N.ptr(out),
+                                          N.stream()), "dpiso_fv_divergence_adj")
+    return out
+
+
+def h_apply_adj(g, values, a_diag, gh, beta):
+    gh = _f32(gh)
+    tu, tv = g.tables(True)
+    out = torch.empty_like(gh)
+    N.check(N.lib.dpiso_h_apply_adj(gh.shape[0], C.byref(tu), C.byref(tv), g.nnz_u, g.nnz_v, beta, N.ptr(values),
+                                    N.ptr(a_diag), N.ptr(gh), N.ptr(out), N.stream()), "dpiso_h_apply_adj")
+    return out
+
+
+def predictor_rhs_adj(g, grhs, dirichlet_u8, dy, dx, beta, want_force, want_dvals):
+    grhs = _f32(grhs)
+    b = grhs.shape[0]
+    gvel = torch.empty_like(grhs)
+    gfree = torch.empty_like(grhs)
+    gforce = torch.empty_like(grhs) if want_force else None
+    gdvals = torch.empty_like(grhs) if want_dvals else None
+    N.check(N.lib.dpiso_predictor_rhs_adj(b, g.ny, g.nx, dy, dx, beta, N.ptr(dirichlet_u8), N.ptr(grhs), N.ptr(gvel),
+                                          N.ptr(gforce), N.ptr(gdvals), N.ptr(gfree), N.stream()),
+            "dpiso_predictor_rhs_adj")
+    return gvel, gforce, gdvals, gfree
+
+
+def bicgstab_ilu(g, values, rhs, x0, tol, max_it, transpose=False, warn=None):
+    """-> x [B, nf], stats int32 [B, 2, 4] (iterations, restarts, warn, exit kind), warn uint8 [1]"""
+    values, rhs, x0 = _f32(values), _f32(rhs), _f32(x0)
+    b = rhs.shape[0]
+    tu, tv = g.tables(transpose)
+    ws_floats = N.lib.dpiso_bicgstab_workspace_floats(C.byref(tu), C.byref(tv))
+    ws = torch.empty(b * 2 * ws_floats, dtype=torch.float32, device=rhs.device)
+    x = torch.empty_like(rhs)
+    stats = torch.zeros((b, 2, 4), dtype=torch.int32, device=rhs.device)
+    if warn is None:
+        warn = torch.zeros(1, dtype=torch.uint8, device=rhs.device)
+    N.check(N.lib.dpiso_bicgstab_ilu(b, C.byref(tu), C.byref(tv), g.nnz_u, g.nnz_v, N.ptr(values), N.ptr(rhs), N.ptr(x0),
+                                     float(tol), int(max_it), N.ptr(x), N.ptr(stats), N.ptr(warn), N.ptr(ws), N.stream()),
+            "dpiso_bicgstab_ilu")
+    return x, stats, warn
+
+
+def laplace(g, active, fluid, k_faces, mode, beta, dx_factor, fp64=True):
+    """-> lap [B, nc, 5]; mode 0: k_faces = scaling field flattened [v, u]; mode 1: k_faces = a_diag [u, v]."""
+    k_faces = _f32(k_faces)
+    b = k_faces.shape[0]
+    lap = torch.empty((b, g.nc, 5), dtype=torch.float64 if fp64 else torch.float32, device=k_faces.device)
+    fn = N.lib.dpiso_laplace_f64 if fp64 else N.lib.dpiso_laplace_f32
+    N.check(fn(b, g.ny, g.nx, N.ptr(active), N.ptr(fluid), N.ptr(k_faces), int(mode), beta, dx_factor, N.ptr(lap),
+               N.stream()), "dpiso_laplace")
+    return lap
+
+
+def pressure_cg(g, lap, div, accuracy, max_it, residual_reset, rank_deficient):
+    """-> pressure float32 [B, nc], iterations int32 [B].  lap fp64: fp32 divergence in, fp64 solve, fp32 out
+    (cast_to_double path); lap fp32: everything fp32."""
+    b = div.shape[0]
+    div = _f32(div).reshape(b, g.nc)
+    x32 = torch.empty((b, g.nc), dtype=torch.float32, device=div.device)
+    its = torch.zeros(b, dtype=torch.int32, device=div.device)
+    if lap.dtype == torch.float64:
+        rc = N.lib.dpiso_pressure_cg_mixed(b, g.ny, g.nx, int(g.per_x), int(g.per_y), N.ptr(lap), N.ptr(div),
+                                           float(accuracy), int(max_it), int(residual_reset), int(rank_deficient),
+                                           N.ptr(x32), N.ptr(its), N.stream())
+    else:
+        rc = N.lib.dpiso_pressure_cg_f32(b, g.ny, g.nx, int(g.per_x), int(g.per_y), N.ptr(lap), N.ptr(div),
+                                         float(accuracy), int(max_it), int(residual_reset), int(rank_deficient),
+                                         N.ptr(x32), None, N.ptr(its), N.stream())
+    N.check(rc, "dpiso_pressure_cg")
+    return x32, its
+
+
+def pressure_cg_config():
+    out = (C.c_int * 5)()
+    N.lib.dpiso_pressure_cg_last_config(out)
+    return dict(cluster=out[0], threads=out[1], cells_per_thread=out[2], smem_bytes=out[3], variant=out[4])
+
+
+def to_device_masks(sim, g):
+    """Device copies of the SimulationParameters masks in the layouts the kernels read (cached on `sim`)."""
+    key = ("_dpiso_masks", str(g.device))
+    cached = getattr(sim, "_dpiso_cache", None)
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    from .grids import as_tensor, flatten_staggered_data
+    dm = as_tensor(sim.dirichlet_mask, dtype=None)
+    dm = flatten_staggered_data(dm.to(torch.float32), coord_flip=True)[0]
+    if dm.numel() != g.nf:
+        raise ValueError("dirichlet_mask does not match the grid")
+    active = as_tensor(sim.active_mask).reshape(-1)
+    access = as_tensor(sim.accessible_mask).reshape(-1)
+    nm = (g.ny + 2) * (g.nx + 2)
+    if active.numel() != nm or access.numel() != nm:
+        raise ValueError("active/accessible masks must be [1, ny+2, nx+2, 1]")
+    if sim.no_slip_mask is None:
+        noslip = torch.zeros(nm, dtype=torch.uint8)
+    else:
+        noslip = as_tensor(sim.no_slip_mask, dtype=None).reshape(-1)
+        if noslip.numel() != nm:
+            raise ValueError("no_slip_mask must be indexable as the padded centred grid (ny+2)*(nx+2) "
+                             "(CUDAsrc/central_difference_csr_op.cu.cc:251-253)")
+        noslip = (noslip != 0).to(torch.uint8)
+    acc_np, act_np = access.cpu().numpy().reshape(g.ny + 2, g.nx + 2), active.cpu().numpy().reshape(g.ny + 2, g.nx + 2)
+    prod = acc_np * act_np + (1 - acc_np) * (1 - act_np)        # piso_cuda_pressure_solver.py:84-87
+    rank_def = bool(np.prod(prod[0, 1:-1]) * np.prod(prod[-1, 1:-1]) * np.prod(prod[1:-1, 0]) * np.prod(prod[1:-1, -1]))
+    m = dict(dirichlet=(dm != 0).to(torch.uint8).contiguous().to(g.device), active=active.contiguous().to(g.device),
+             access=access.contiguous().to(g.device), noslip=noslip.contiguous().to(g.device), rank_deficient=rank_def)
+    sim._dpiso_cache = (key, m)
+    return m

@@ -1,0 +1,228 @@
+"""The PISO step with the reference's call surface (diffpiso/piso_tf.py:11-81, 85-137, 165-182).
+
+`piso_step(velocity, pressure, pressure_inc1, pressure_inc2, dt, simulation_physics, dirichlet_values, ...)` returns
+`(StaggeredGrid velocity, CenteredGrid pressure, warn)` (or the 17 intermediates with `full_output`).  Forward and
+backward of one step are ONE `torch.autograd.Function` that enqueues the fused native kernels; the two solver plug-ins
+of `SimulationParameters` (`linear_solver.solve`, `pressure_solver.solve`) are called exactly where the reference calls
+them -- in forward and, for the adjoint, in backward (transposed predictor solve, two more pressure solves).
+
+Backward follows the reference's gradient registrations: the advection matrices, 1/(beta-A), the
+pressure matrix, masks and initial guesses are constants; gradients flow to velocity, pressure, the forcing term and the
+Dirichlet values.
+"""
+import numpy as np
+import torch
+
+from . import ops
+from .grids import (CenteredGrid, StaggeredGrid, as_tensor, extrapolation_codes, flatten_staggered_data,
+                    stagger_flattened_data)
+from .pressure_solver import ScalingFromDiagonal, _periodic_flags
+
+
+class SimulationParameters(object):
+    """diffpiso/piso_tf.py:165-182.  Masks as in the reference: dirichlet_mask / dirichlet_values in staggered shape
+    [1, ny+1, nx+1, 2]; active_mask / accessible_mask [1, ny+2, nx+2, 1]; no_slip_mask indexable as the flattened padded
+    centred grid; bool_periodic = (periodic_y, periodic_x)."""
+
+    def __init__(self, dirichlet_mask, dirichlet_values, active_mask, accessible_mask, bool_periodic=None,
+                 no_slip_mask=None, viscosity=0., linear_solver=None, pressure_solver=None):
+        self.pressure_solver = pressure_solver
+        self.linear_solver = linear_solver
+        self.dirichlet_mask = dirichlet_mask
+        self.dirichlet_values = dirichlet_values
+        self.active_mask = active_mask
+        self.accessible_mask = accessible_mask
+        self.no_slip_mask = no_slip_mask
+        self.bool_periodic = bool_periodic
+        self.viscosity = viscosity
+
+
+def pressure_extrapolation(boundaries):
+    """diffpiso/piso_tf.py:140-162: nested tuple of Material-like objects -> accessible_extrapolation_mode strings."""
+    if isinstance(boundaries, tuple):
+        return tuple(pressure_extrapolation(b) for b in boundaries)
+    return boundaries.accessible_extrapolation_mode
+
+
+class _Ctx(object):
+    """Host-side constants of one step."""
+    __slots__ = ("g", "m", "dy", "dx", "beta", "prod", "dx_factor", "pbc", "pbc_inc", "sim", "unrolling_step")
+
+
+def _linear_solve(c, values_neg, rhs, x0, transpose, unrolling_step):
+    ls = c.sim.linear_solver
+    shape = (rhs.shape[0], c.g.ny + 1, c.g.nx + 1, 2)
+    if getattr(ls, "_dpiso_native", False):
+        return ls.solve(values_neg, None, None, rhs, shape, x0, offset=1, transpose=transpose,
+                        unrolling_step=unrolling_step, structure=c.g)
+    rp, ci = c.g.csr_structure()
+    return ls.solve(values_neg, rp, ci, rhs, shape, x0, offset=1, transpose=transpose, unrolling_step=unrolling_step)
+
+
+def _pressure_solve(c, a_diag, div, unrolling_step):
+    ps = c.sim.pressure_solver
+    b = div.shape[0]
+    div4 = div.reshape(b, c.g.ny, c.g.nx, 1)
+    if getattr(ps, "_dpiso_native", False):
+        scaling = ScalingFromDiagonal(a_diag, c.beta, c.dx_factor)
+    else:   # foreign plug-in: materialise 1/(beta - A) * dx_factor as a staggered tensor (piso_tf.py:53-54)
+        scaling = stagger_flattened_data((1.0 / (c.beta - a_diag)) * c.dx_factor, (b, c.g.ny + 1, c.g.nx + 1, 2), True)
+    p, its, lap = ps.solve(scaling, div4, None, False, c.sim, unrolling_step=unrolling_step)
+    return p.reshape(b, c.g.nc), its, lap
+
+
+class _PisoStepFn(torch.autograd.Function):
+    """One PISO step on flat tensors: (vel [B,nf], pres [B,nc], dvals [1|B,nf], forcing [B,nf]|None, visc) ->
+    (vel_next, pres_next, p1, p2, warn, extras...)."""
+
+    @staticmethod
+    def forward(ctx, vel, pres, dvals, forcing, visc, c):
+        g, m = c.g, c.m
+        vel, pres = vel.contiguous(), pres.contiguous()
+        # advection matrices (piso_tf.py:29-33)
+        values, a_diag = ops.assemble(g, vel, m["dirichlet"], m["active"], m["noslip"], visc, c.dy, c.dx, c.beta)
+        # predictor (piso_tf.py:36-47)
+        rhs = ops.predictor_rhs(g, vel, pres, m["access"], m["dirichlet"], dvals, forcing, c.dy, c.dx, c.beta, c.pbc)
+        values_neg = torch.neg(values)
+        u_star, warn = _linear_solve(c, values_neg, rhs, vel, False, c.unrolling_step)
+        u_star = u_star.contiguous()
+        # corrector 1 (piso_tf.py:51-58)
+        div1 = ops.fv_divergence(g, u_star, c.dy, c.dx)
+        p1, its1, lap1 = _pressure_solve(c, a_diag, div1, c.unrolling_step)
+        u_s2 = ops.corrector1(g, u_star, p1, a_diag, m["access"], c.dy, c.dx, c.beta, c.pbc_inc)
+        # corrector 2 (piso_tf.py:61-75)
+        h = ops.h_apply(g, values, a_diag, u_star, u_s2, c.beta)
+        div2 = ops.fv_divergence(g, h, c.dy, c.dx, a_diag=a_diag, beta=c.beta)
+        p2, its2, lap2 = _pressure_solve(c, a_diag, div2, 1000 + c.unrolling_step)
+        vel_next, pres_next = ops.corrector2(g, u_s2, h, p2, a_diag, pres, p1, m["access"], c.dy, c.dx, c.beta, c.pbc_inc)
+        ctx.c = c
+        ctx.has_forcing = forcing is not None
+        ctx.dvals_batched = dvals.shape[0] == vel.shape[0]
+        ctx.save_for_backward(values, values_neg, a_diag, vel)
+        extras = (p1, p2, warn, values, a_diag, rhs, u_star, u_s2, h, div1, div2, lap1, lap2, its1, its2)
+        ctx.mark_non_differentiable(*extras)
+        return (vel_next, pres_next) + extras
+
+    @staticmethod
+    def backward(ctx, g_vel, g_pres, *unused):
+        c = ctx.c
+        g, m = c.g, c.m
+        values, values_neg, a_diag, vel = ctx.saved_tensors
+        b = vel.shape[0]
+        g_vel = torch.zeros_like(vel) if g_vel is None else g_vel.contiguous()
+        g_pres = torch.zeros((b, g.nc), dtype=torch.float32, device=vel.device) if g_pres is None else g_pres.contiguous()
+        # p_next = p + p1 + p2 ; u_next = u** + (h - G(p2)/prod)/(beta-A)
+        p2_bar = ops.fv_gradient_adj(g, g_vel, m["access"], c.dy, c.dx, c.pbc_inc, a_diag=a_diag, beta=c.beta,
+                                     divisor=c.prod, negate=True, base=g_pres)
+        d2_bar, _, _ = _pressure_solve(c, a_diag, p2_bar, 1100 + c.unrolling_step)
+        # h_bar = (g_vel + D^T d2_bar) / (beta - A)
+        h_bar = ops.fv_divergence_adj(g, d2_bar, c.dy, c.dx, base=g_vel, a_diag=a_diag, beta=c.beta)
+        delta_bar = ops.h_apply_adj(g, values, a_diag, h_bar, c.beta)
+        us2_bar = g_vel + delta_bar
+        # u** = u* - G(p1)/(beta-A)/prod
+        p1_bar = ops.fv_gradient_adj(g, us2_bar, m["access"], c.dy, c.dx, c.pbc_inc, a_diag=a_diag, beta=c.beta,
+                                     divisor=c.prod, negate=True, base=g_pres)
+        d1_bar, _, _ = _pressure_solve(c, a_diag, p1_bar, 100 + c.unrolling_step)
+        # u*_bar = (us2_bar - delta_bar) + D^T d1_bar
+        ustar_bar = ops.fv_divergence_adj(g, d1_bar, c.dy, c.dx, base=us2_bar - delta_bar)
+        # predictor: transposed solve, same initial-guess tensor as forward, times (1 - warn) (linear_solver.py:169-173)
+        rhs_bar, warn_b = _linear_solve(c, values_neg, ustar_bar, vel, True, 100 + c.unrolling_step)
+        rhs_bar = rhs_bar * (1.0 - warn_b)
+        need_dv = ctx.needs_input_grad[2]
+        gvel_in, gforce, gdvals, gfree = ops.predictor_rhs_adj(g, rhs_bar.contiguous(), m["dirichlet"], c.dy, c.dx, c.beta,
+                                                               ctx.has_forcing and ctx.needs_input_grad[3], need_dv)
+        gpres_in = ops.fv_gradient_adj(g, gfree, m["access"], c.dy, c.dx, c.pbc, negate=True, base=g_pres)
+        if need_dv and not ctx.dvals_batched:
+            gdvals = gdvals.sum(0, keepdim=True)
+        return gvel_in, gpres_in, gdvals, gforce, None, None
+
+
+def _flat_faces(x, b, g, name):
+    """staggered tensor / StaggeredGrid / flat -> [1|B, nf] float32 on the right device"""
+    if isinstance(x, StaggeredGrid):
+        return x.flat
+    t = as_tensor(x)
+    if t.dim() == 4:
+        return flatten_staggered_data(t, coord_flip=True).contiguous()
+    if t.dim() == 1:
+        t = t[None]
+    if t.dim() != 2 or t.shape[1] != g.nf:
+        raise ValueError("%s must be a staggered tensor [B, ny+1, nx+1, 2] or flat [B, n_u+n_v]" % name)
+    return t
+
+
+def make_step_context(velocity, pressure, pressure_inc, dt, simulation_physics, unrolling_step=0):
+    sim = simulation_physics
+    ny, nx = velocity.resolution
+    per_y, per_x = _periodic_flags(sim)
+    device = velocity.flat.device
+    if device.type != "cuda":
+        raise ops.N.DpisoError("piso_step needs CUDA tensors: the PISO path has no CPU implementation")
+    c = _Ctx()
+    c.g = ops.Geometry.get(ny, nx, per_y, per_x, device)
+    c.m = ops.to_device_masks(sim, c.g)
+    # the kernels take fp32 spacings (grid_spacing / cell_area are fp32 op inputs, piso_tf.py:96-97); the derived
+    # constants are formed in fp64 from those and rounded once, like the TF graph constants
+    c.dy, c.dx = float(np.float32(velocity.dx[0])), float(np.float32(velocity.dx[1]))
+    prod = c.dy * c.dx
+    c.prod = float(np.float32(prod))
+    c.beta = float(np.float32(prod / float(dt)))                       # piso_tf.py:26
+    c.dx_factor = float(np.float32(prod / (c.dy * c.dy)))              # piso_tf.py:53 (dx[0] = dy)
+    c.pbc = extrapolation_codes(pressure.extrapolation)
+    c.pbc_inc = extrapolation_codes(pressure_inc.extrapolation)
+    c.sim = sim
+    c.unrolling_step = unrolling_step
+    return c
+
+
+def piso_step(velocity, pressure, pressure_inc1, pressure_inc2, dt, simulation_physics, dirichlet_values,
+              viscosity_field=None, forcing_term=None, unrolling_step=0, warn=None, full_output=False, **kwargs):
+    """diffpiso/piso_tf.py:11-81."""
+    sim = simulation_physics
+    if sim.linear_solver is None or sim.pressure_solver is None:
+        raise ValueError("SimulationParameters needs linear_solver and pressure_solver")
+    c = make_step_context(velocity, pressure, pressure_inc1, dt, sim, unrolling_step)
+    g = c.g
+    vel = velocity.flat
+    b = vel.shape[0]
+    pres = as_tensor(pressure.data).reshape(b, g.nc)
+    dvals = _flat_faces(dirichlet_values, b, g, "dirichlet_values").to(vel.device)
+    forcing = None if forcing_term is None else _flat_faces(forcing_term, b, g, "forcing_term").to(vel.device)
+    if viscosity_field is None:
+        visc = torch.tensor([float(sim.viscosity)], dtype=torch.float32, device=vel.device)   # piso_tf.py:21-24
+    else:
+        visc = as_tensor(viscosity_field).to(vel.device)
+        if visc.dim() == 4:
+            visc = flatten_staggered_data(visc, coord_flip=True)
+    out = _PisoStepFn.apply(vel, pres, dvals, forcing, visc, c)
+    vel_next, pres_next, p1, p2, warn_new, values, a_diag, rhs, u_star, u_s2, h, div1, div2, lap1, lap2, its1, its2 = out
+    if warn is not None:
+        warn_new = torch.maximum(warn_new, as_tensor(warn).to(vel.device).reshape(-1)[:1].to(torch.float32))
+    velocity_s3 = velocity.copied_with(flat=vel_next)
+    pressure_new = pressure.copied_with(pres_next.reshape(b, g.ny, g.nx, 1))
+    if not full_output:
+        return velocity_s3, pressure_new, warn_new
+    shape = velocity.staggered_shape
+    rp, ci = g.csr_structure()
+    inc1 = pressure_inc1.copied_with(p1.reshape(b, g.ny, g.nx, 1))
+    inc2 = pressure_inc2.copied_with(p2.reshape(b, g.ny, g.nx, 1))
+    return (velocity_s3, pressure_new, inc1, inc2, values, ci, rp,
+            stagger_flattened_data(u_star, shape, True), stagger_flattened_data(u_s2, shape, True), a_diag, rhs,
+            stagger_flattened_data(u_star, shape, True), velocity_s3.staggered_tensor(),
+            div1.reshape(b, g.ny, g.nx, 1), lap1, lap2, warn_new)
+
+
+def advection_matrix_cuda(velocity, simulation_physics, viscosity, beta, unrolling_step=0):
+    """diffpiso/piso_tf.py:85-137 -> (matrix_values [B,nnz], row_pointers, column_indices, A staggered, matrix_nnz,
+    A_flat).  Takes the SimulationParameters instead of the reference's loose mask arguments."""
+    ny, nx = velocity.resolution
+    per_y, per_x = _periodic_flags(simulation_physics)
+    g = ops.Geometry.get(ny, nx, per_y, per_x, velocity.flat.device)
+    m = ops.to_device_masks(simulation_physics, g)
+    visc = as_tensor(viscosity).to(velocity.flat.device)
+    values, a_flat = ops.assemble(g, velocity.flat, m["dirichlet"], m["active"], m["noslip"], visc,
+                                  float(np.float32(velocity.dx[0])), float(np.float32(velocity.dx[1])),
+                                  float(np.float32(beta)))
+    rp, ci = g.csr_structure()
+    return values, rp, ci, stagger_flattened_data(a_flat, velocity.staggered_shape, True), \
+        np.array([g.nnz_u, g.nnz_v]), a_flat

@@ -1,0 +1,182 @@
+/*
+ * dpiso.h -- C ABI of libdpiso (sm_100a).  The drop-in boundary for the PISO-step hot path of
+ * tum-pbs/differentiable-piso.  Every entry point replaces one launcher behind a TF-1.14 custom op of
+ * the reference (paths relative to the reference checkout):
+ *
+ *   dpiso_csr_structure / dpiso_assemble   CentralDifferenceMatrixCsrKernelLauncher
+ *                                          CUDAsrc/central_difference_csr_op.cc:33-36, .cu.cc:543-664
+ *   dpiso_bicgstab_*                       MultiBicgstabIluLinearSolveLauncher
+ *                                          CUDAsrc/multi_bicgstab_ilu_linear_solve_op.cc:50-58, .cu.cc:85-531
+ *   dpiso_laplace_*                        LaplaceMatrixKernelLauncher
+ *                                          CUDAsrc/pressure_solve_op.cc:78-84, laplace_op.cu.cc:191-239
+ *   dpiso_pressure_cg_*                    LaunchPressureKernel
+ *                                          CUDAsrc/pressure_solve_op.cc:48-76, .cu.cc:140-696
+ *   dpiso_predictor_rhs / fv_* / corrector_* / h_apply   the TF graph ops of diffpiso/piso_tf.py:36-75
+ *                                          and diffpiso/piso_helpers.py:169-310 (and their gradients)
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless its name starts with h_;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
+ *   - every function returns 0 on success, a negative DPISO_E* code otherwise (never exit()/assert());
+ *     dpiso_last_error() returns a thread-local message for the last failure;
+ *   - batch-major contiguous arrays: face vectors [batch][n_u+n_v] = [u rows..., v rows...] (x fastest),
+ *     cell vectors [batch][ny*nx], CSR values [batch][nnz_u+nnz_v]; masks are shared by the batch and
+ *     are padded-centred [(ny+2)*(nx+2)];
+ *   - "ny,nx" is the centred resolution; u lives on ny x (nx+1) faces, v on (ny+1) x nx faces.
+ */
+#ifndef DPISO_H
+#define DPISO_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPISO_OK 0
+#define DPISO_EINVAL (-1)      /* bad argument (grid too small, null pointer, ...) */
+#define DPISO_ECUDA (-2)       /* CUDA runtime error, see dpiso_last_error() */
+#define DPISO_EUNSUPPORTED (-3) /* configuration outside what the kernels cover */
+
+/* pressure ghost-cell rule per side (PhiFlow extrapolation of the centred field) */
+#define DPISO_PBC_REPLICATE 0
+#define DPISO_PBC_ZERO 1
+#define DPISO_PBC_PERIODIC 2
+
+int dpiso_version(void);
+const char *dpiso_last_error(void);
+
+/* ---- sizes (host only; diffpiso/piso_tf.py:99-106) ---------------------------------------------- */
+/* h_n[2] = rows of (u, v); h_nnz[2] = stored entries of (u, v) */
+int dpiso_sizes(int ny, int nx, int per_x, int per_y, int *h_n, int *h_nnz);
+
+/* ---- CSR structure: row_ptr = two 0-based arrays back to back (n_u+1, n_v+1), col_ind 0-based per
+ *      component (calcCsrRowPtrGpu + the colInd stores of calcAdvetionMatrixX/Y). ------------------- */
+int dpiso_csr_structure(int ny, int nx, int per_x, int per_y, int *row_ptr, int *col_ind, void *stream);
+
+/* ---- advection-diffusion matrices (custom_padded + CentralDifferenceMatrixCsr) -------------------
+ * vel [batch][nf] unpadded; the padding of piso_helpers.py:35-55 is applied on the fly.
+ * dirichlet uint8 [nf]; active float [(ny+2)(nx+2)]; noslip uint8 [(ny+2)(nx+2)];
+ * visc: visc_mode 0 = scalar (1 float), 1 = face field [nf] shared, 2 = face field [batch][nf].
+ * outputs: values [batch][nnz] (centre = diag - beta), a_diag [batch][nf]. */
+int dpiso_assemble(int batch, int ny, int nx, int per_x, int per_y, float dy, float dx, float beta,
+                   const float *vel, const uint8_t *dirichlet, const float *active, const uint8_t *noslip,
+                   const float *visc, int visc_mode, float *values, float *a_diag, void *stream);
+
+/* ---- pointwise pieces of piso_step (forward) ------------------------------------------------------ */
+/* rhs = vel*beta - G(p) [+ forcing*dx*dy]; Dirichlet faces <- -dirichlet_value   (piso_tf.py:36-40)
+ * h_pbc[4] = ghost rule at y_lo,y_hi,x_lo,x_hi; dvals [dvals_batch ? batch : 1][nf]; forcing may be NULL */
+int dpiso_predictor_rhs(int batch, int ny, int nx, float dy, float dx, float beta, const int *h_pbc,
+                        const float *vel, const float *pres, const float *access, const uint8_t *dirichlet,
+                        const float *dvals, int dvals_batch, const float *forcing, float *rhs, void *stream);
+/* g = G(p) * min(accessible+, accessible-)   (piso_helpers.py:236-274) */
+int dpiso_fv_gradient(int batch, int ny, int nx, float dy, float dx, const int *h_pbc, const float *access,
+                      const float *p, float *g, void *stream);
+/* div = D(vel)  or, with a_diag != NULL,  D(vel / (beta - a_diag))   (piso_helpers.py:285-289, piso_tf.py:66) */
+int dpiso_fv_divergence(int batch, int ny, int nx, float dy, float dx, const float *vel, const float *a_diag,
+                        float beta, float *div, void *stream);
+/* u** = u* - G(p1)/(beta-A)/(dx*dy)   (piso_tf.py:58) */
+int dpiso_corrector1(int batch, int ny, int nx, float dy, float dx, float beta, const int *h_pbc,
+                     const float *access, const float *u_star, const float *p1, const float *a_diag,
+                     float *u_s2, void *stream);
+/* h = M (u**-u*) - (A-beta)(u**-u*)    (piso_helpers.py:209-223) */
+int dpiso_h_apply(int batch, int ny, int nx, int per_x, int per_y, float beta, const float *values,
+                  const float *a_diag, const float *u_star, const float *u_s2, float *h, void *stream);
+/* u_next = u** + (h - G(p2)/(dx*dy))/(beta-A);  p_next = p + p1 + p2     (piso_tf.py:71-75) */
+int dpiso_corrector2(int batch, int ny, int nx, float dy, float dx, float beta, const int *h_pbc,
+                     const float *access, const float *u_s2, const float *h, const float *p2,
+                     const float *a_diag, const float *p, const float *p1, float *u_next, float *p_next,
+                     void *stream);
+
+/* ---- pointwise adjoints (frozen coefficients) --------------------------------------
+ * These are the gradients TF-1.14 autodiff assembles from the reference's registrations; on periodic axes the
+ * registered gradients of the FV gradient / divergence are NOT the exact transposes and are
+ * reproduced as registered. */
+/* gp = [base] + G^T(t),  t = gs [/(beta - a_diag)] [/divisor] [negated] on the faces; gradient of
+ * finite_volume_gradient_tensor incl. the accessible-mask multiply (piso_helpers.py:226-266).
+ * a_diag and base may be NULL; divisor = 1 disables the division. */
+int dpiso_fv_gradient_adj(int batch, int ny, int nx, float dy, float dx, const int *h_pbc, const float *access,
+                          const float *gs, const float *a_diag, float beta, float divisor, int negate,
+                          const float *base, float *gp, void *stream);
+/* gv = ([base] + D^T gc) [/(beta - a_diag)]: registered gradient of finite_volume_divergence
+ * (piso_helpers.py:291-305).  base [batch][nf] and a_diag may be NULL. */
+int dpiso_fv_divergence_adj(int batch, int ny, int nx, int per_x, int per_y, float dy, float dx, const float *gc,
+                            const float *base, const float *a_diag, float beta, float *gv, void *stream);
+/* gfree = (1-m) grhs, gvel = gfree*beta, gforce = gfree*dx*dy, gdvals = -m grhs  (m = Dirichlet mask): adjoint of the
+ * rhs assembly (piso_tf.py:36-40); gforce / gdvals may be NULL.  The pressure part is -G^T(gfree). */
+int dpiso_predictor_rhs_adj(int batch, int ny, int nx, float dy, float dx, float beta, const uint8_t *dirichlet,
+                            const float *grhs, float *gvel, float *gforce, float *gdvals, float *gfree, void *stream);
+
+/* ---- ILU0-preconditioned BiCGStab, batched over samples and the two components --------------------
+ * Structure tables are built on the host by the caller (diffpiso_b200/structure.py) from the CSR pattern and
+ * uploaded once (all pointers inside dpiso_bicg_tables are DEVICE pointers; the struct itself lives on the host).
+ * M = A for the forward solve, M = A^T for the adjoint solve -- only the tables differ.
+ * One persistent CTA per (sample, component) system. */
+typedef struct {
+    int n;                /* rows of this component */
+    int n_levels;         /* wavefront levels (lx+ly hyperplanes) */
+    int wa;               /* ELL width: max entries per row of the (possibly transposed) matrix, <= 6 */
+    int max_level;        /* rows in the largest level */
+    const int *level_ptr; /* [n_levels+1] first position of each level (level-major numbering) */
+    const int *perm;      /* [n] level-major position -> original row */
+    const int *a_col;     /* [wa][n] column (as level-major position) per entry, in ascending ORIGINAL column
+                             order; padding entries come last and point at the row itself */
+    const int *a_src;     /* [wa][n] index into this component's CSR values holding M(row, col); -1 = padding */
+    const int *a_rev;     /* [wa][n] index into this component's CSR values holding M(col, row); -1 = absent */
+} dpiso_bicg_tables;
+
+/* gd = M^T gh - (A - beta) gh: adjoint of dpiso_h_apply w.r.t. (u** - u*); takes the tables of M = A^T */
+int dpiso_h_apply_adj(int batch, const dpiso_bicg_tables *h_tabT_u, const dpiso_bicg_tables *h_tabT_v, int nnz_u,
+                      int nnz_v, float beta, const float *values, const float *a_diag, const float *gh, float *gd,
+                      void *stream);
+
+/* workspace (floats) needed per (sample, component) system for the given tables */
+size_t dpiso_bicgstab_workspace_floats(const dpiso_bicg_tables *h_tab_u, const dpiso_bicg_tables *h_tab_v);
+
+/* Solves values*x = rhs for every sample and both components (values already carry the sign the caller wants).
+ * values [batch][nnz_u+nnz_v] (nnz_* = CSR entries of the NON-transposed pattern; transposition is expressed by
+ * the tables), rhs/x0/x [batch][n_u+n_v].  stats int [batch][2][4] = iterations, restarts, warn, exit kind;
+ * warn uint8 [1] is OR-ed with any NaN-norm warning (multi_bicgstab...cu.cc:251-256).
+ * workspace: float [batch*2*dpiso_bicgstab_workspace_floats()]. */
+int dpiso_bicgstab_ilu(int batch, const dpiso_bicg_tables *h_tab_u, const dpiso_bicg_tables *h_tab_v, int nnz_u,
+                       int nnz_v, const float *values, const float *rhs, const float *x0, float tol, int max_it,
+                       float *x, int *stats, uint8_t *warn, float *workspace, void *stream);
+
+/* ---- pressure matrix (calcPISOLaplaceMatrix) ----------------------------------------------------------
+ * mode 0: k_faces [batch][n_v+n_u] is the scaling field flattened [v,u] (piso_cuda_pressure_solver.py:70)
+ * mode 1: k_faces is a_diag [batch][n_u+n_v] ([u,v]); k = (1/(beta-a))*dx_factor is formed on the fly.
+ * lap [batch][ny*nx][5] = [y-, x-, diag, x+, y+] */
+int dpiso_laplace_f64(int batch, int ny, int nx, const float *active, const float *fluid, const float *k_faces,
+                      int mode, float beta, float dx_factor, double *lap, void *stream);
+int dpiso_laplace_f32(int batch, int ny, int nx, const float *active, const float *fluid, const float *k_faces,
+                      int mode, float beta, float dx_factor, float *lap, void *stream);
+
+/* ---- pressure CG (LaunchPressureKernel, init_with_zeros = true, randomized_restarts = 0) ------------
+ * One thread-block cluster per sample, state resident in registers/shared memory; every sample follows the
+ * reference's B=1 control flow (check cadence, residual resets) on its own.
+ * lap [batch][n_c][5], div [batch][n_c], x [batch][n_c] (output, T), iterations int [batch].
+ * x32 (optional, may be NULL): float copy of x (the reference casts the result to fp32). */
+int dpiso_pressure_cg_f64(int batch, int ny, int nx, int per_x, int per_y, const double *lap, const double *div,
+                          float accuracy, int max_it, int residual_reset, int rank_deficient, double *x,
+                          float *x32, int *iterations, void *stream);
+int dpiso_pressure_cg_f32(int batch, int ny, int nx, int per_x, int per_y, const float *lap, const float *div,
+                          float accuracy, int max_it, int residual_reset, int rank_deficient, float *x,
+                          float *x32, int *iterations, void *stream);
+/* fp32 divergence in, fp64 solve, fp32 pressure out: the cast_to_double=True path of
+ * PisoPressureSolverCudaCustom.solve (piso_cuda_pressure_solver.py:55-58,111) without materialising the casts */
+int dpiso_pressure_cg_mixed(int batch, int ny, int nx, int per_x, int per_y, const double *lap, const float *div32,
+                            float accuracy, int max_it, int residual_reset, int rank_deficient, float *x32,
+                            int *iterations, void *stream);
+
+/* launch-configuration report for the last pressure CG call on this thread: h_out[0]=cluster size,
+ * [1]=threads per CTA, [2]=cells per thread, [3]=dynamic smem bytes, [4]=kernel variant */
+int dpiso_pressure_cg_last_config(int *h_out);
+/* tuning hook for benchmarks / tests: force the cluster size (0 = heuristic) and the kernel variant (-1 = heuristic;
+ * 0: 1024 threads, coefficients in smem; 1: 512 threads, coefficients in registers; 2: 512 threads, 2 CTAs/SM) */
+int dpiso_pressure_cg_set_tuning(int cluster, int variant);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPISO_H */

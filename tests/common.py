@@ -1,0 +1,36 @@
+"""Shared helpers of the test-suite: seeded inputs and conversions between the reference-shaped API and the oracle."""
+import numpy as np
+
+from diffpiso_b200 import setups as SU
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    d = np.linalg.norm(b.ravel())
+    return np.linalg.norm((a - b).ravel()) / (d if d > 0 else 1.0)
+
+
+def random_fields(setup, seed, scale=1.0):
+    """Seeded velocity [nf] (Dirichlet faces set to their values) and pressure [nc]."""
+    rng = np.random.RandomState(seed)
+    ny, nx = setup["ny"], setup["nx"]
+    if setup["per_x"] and setup["per_y"]:
+        vel = SU.solenoidal_field(ny, nx, length=ny * setup["dy"], seed=seed) * scale
+    else:
+        vel = (rng.randn(ny * (nx + 1) + (ny + 1) * nx) * 0.1 * scale).astype(np.float32)
+        d = setup["dirichlet"].astype(bool)
+        vel[d] = setup["dirichlet_values"][d]
+    pres = (rng.randn(ny * nx) * 0.01).astype(np.float32)
+    return vel.astype(np.float32), pres
+
+
+SMALL_SETUPS = {
+    "ldc8": lambda: SU.lid_driven_cavity(n=8, re=100.0, dt=0.01, bicg_tol=1e-8, bicg_max_it=100, cg_tol=1e-8,
+                                         cg_max_it=1000, cg_reset=10),
+    "ldc32": lambda: SU.lid_driven_cavity(n=32, re=100.0, dt=0.01),
+    "periodic16": lambda: SU.periodic_box(16, 16, visc=1e-2, cg_reset=1000),
+    "periodic24x20": lambda: SU.periodic_box(24, 20, visc=1e-2, cg_reset=10),
+    "periodic32": lambda: SU.periodic_box(32, 32, visc=1e-3),
+    "tml16x24": lambda: SU.temporal_mixing_layer(ny=16, nx=24, visc=2e-3, dt=0.05),
+    "sml16x48": lambda: SU.spatial_mixing_layer(ny=16, nx=48, box=(8.0, 24.0), dt=0.05, solver_precision=1e-6),
+}
