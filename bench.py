@@ -1,0 +1,356 @@
+"""bench.py -- PISO cell-updates/s (forward + adjoint) on B200, BASELINE.json's metric on configs[1]:
+2-D decaying turbulence, periodic 128x128, batch 64 per GPU, fp32 predictor / fp64 pressure CG at the paper's 1e-8
+tolerances (residual_reset 1000).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one PISO step of the whole batch, forward AND adjoint (loss gradient back to the step's inputs), advancing
+a rollout.  `value` = batch * ny * nx * n_gpus * steps / time with inputs resident in HBM; `e2e` = the same through
+piso_step with HOST buffers (pinned H2D of the state, D2H of the new state and gradient every step).  The batch is
+sharded over GPUs with no data-path collective (weak scaling: 64 samples per GPU).
+`--impl reference` times the reference's CPU path = the oracle port (the reference has no CPU implementation of the
+step and its CUDA path cannot be built here) on all host cores, bounded sample.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "differentiable-piso_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+NY = NX = 128
+BATCH = 64
+WORKLOAD = "decaying_turbulence_periodic_128x128_batch64_fwd+adjoint"
+# algorithmic bytes per cell per CG iteration (fp64, 5 stored coefficients) and per reset
+CG_BYTES_PER_CELL_ITER = 168
+CG_BYTES_PER_CELL_RESET = 88
+
+
+def setup_case():
+    from diffpiso_b200 import setups as SU
+    return SU.periodic_box(NY, NX, visc=1e-3, cfl=0.5, umax=1.0, bicg_tol=1e-8, bicg_max_it=10000, cg_tol=1e-8,
+                           cg_max_it=10000, cg_reset=1000, cg_fp64=True)
+
+
+def initial_state(s, batch, seed0):
+    from diffpiso_b200 import setups as SU
+    vel = np.stack([SU.solenoidal_field(NY, NX, seed=seed0 + i) for i in range(batch)])
+    return vel.astype(np.float32), np.zeros((batch, NY * NX), np.float32)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port on host cores
+# ------------------------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    seed, steps, adjoint = args
+    from oracle import adjoint as A
+    from oracle import oracle as O
+    s = setup_case()
+    vel, pres = initial_state(s, 1, seed)
+    vel, pres = vel[0], pres[0]
+    rng = np.random.RandomState(seed)
+    w_u = rng.randn(vel.size).astype(np.float32)
+    w_p = rng.randn(pres.size).astype(np.float32)
+    w_p -= w_p.mean()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        if adjoint:
+            out = A.piso_step_adjoint(s, vel, pres, w_u, w_p)      # runs the forward step inside
+            vel, pres = out["vel_next"], out["pres_next"]
+        else:
+            vel, pres, _ = O.piso_step(s, vel, pres)
+    return time.perf_counter() - t0
+
+
+def cpu_throughput(cores, steps_per_core, adjoint=True):
+    """cell-updates/s of the oracle port: `cores` independent samples in parallel, `steps_per_core` steps each."""
+    import multiprocessing as mp
+    from oracle import oracle as O
+    O.lib()     # build once before forking
+    t0 = time.perf_counter()
+    if cores == 1:
+        _cpu_worker((1234, steps_per_core, adjoint))
+    else:
+        with mp.get_context("fork").Pool(cores) as pool:
+            pool.map(_cpu_worker, [(1234 + i, steps_per_core, adjoint) for i in range(cores)])
+    dt = time.perf_counter() - t0
+    return cores * steps_per_core * NY * NX / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    total = args.warmup + args.steps
+    per_step = []
+    # each "step" = every core advances one sample by one fwd+adjoint step (bounded sample of the 64-sample batch)
+    for i in range(total):
+        v, dt = cpu_throughput(cores, 1, adjoint=True)
+        if i >= args.warmup:
+            per_step.append(dt)
+    t = sum(per_step)
+    value = cores * args.steps * NY * NX / t
+    line = {"impl": "reference", "metric": "piso_cell_updates_per_s_fwd_adjoint", "value": value, "unit": "cell-updates/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "grid": [NY, NX], "batch_per_gpu": BATCH},
+            "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": cores, "kind": "port",
+                             "sample": "%d samples (one per core) x %d fwd+adjoint steps of the 128x128 case" % (cores, args.steps)},
+            "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                       "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for k, nme in enumerate(names):
+                if len(r) > 5 + k and "Active" in r[5 + k] and "Not" not in r[5 + k]:
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import diffpiso_b200 as dp
+    from diffpiso_b200 import ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    s = setup_case()
+    nf, nc = NY * (NX + 1) + (NY + 1) * NX, NY * NX
+    ls = dp.LinearSolverCudaMultiBicgstabILU(accuracy=s["bicg_tol"], max_iterations=s["bicg_max_it"])
+    ps = dp.PisoPressureSolverCudaCustom(dx=s["dx"], accuracy=s["cg_tol"], max_iterations=s["cg_max_it"],
+                                         residual_reset=s["cg_reset"])
+    sim = dp.SimulationParameters(s["dirichlet_mask"], s["dirichlet_values_staggered"], s["active_mask"],
+                                  s["accessible_mask"], bool_periodic=(True, True), no_slip_mask=s["no_slip_mask"],
+                                  viscosity=float(s["visc"]), linear_solver=ls, pressure_solver=ps)
+    vel_h, pres_h = initial_state(s, BATCH, 1234 + rank * BATCH)
+    box = (NY * s["dy"], NX * s["dx"])
+    dvals = torch.zeros(1, nf, device=dev)
+    rng = np.random.RandomState(99 + rank)
+    w_u = torch.as_tensor(rng.randn(BATCH, nf).astype(np.float32)).to(dev)
+    w_p = rng.randn(BATCH, nc).astype(np.float32)
+    w_p = torch.as_tensor(w_p - w_p.mean(axis=1, keepdims=True)).to(dev)
+
+    def step(vel, pres):
+        """forward + adjoint of one PISO step; returns the new state and the input gradients"""
+        vel = vel.detach().requires_grad_(True)
+        pres = pres.detach().requires_grad_(True)
+        velocity = dp.StaggeredGrid(flat=vel, resolution=(NY, NX), box=box, extrapolation="periodic")
+        pressure = dp.CenteredGrid(pres.reshape(BATCH, NY, NX, 1), box=box, extrapolation="periodic")
+        v_new, p_new, warn = dp.piso_step(velocity, pressure, pressure, pressure, s["dt"], sim, dvals)
+        loss = (v_new.flat * w_u).sum() + (p_new.data.reshape(BATCH, nc) * w_p).sum()
+        gv, gp = torch.autograd.grad(loss, (vel, pres))
+        return v_new.flat.detach(), p_new.data.reshape(BATCH, nc).detach(), gv, gp
+
+    # launch counting / per-kernel event timing hooks
+    launches = {"n": 0}
+    cg_events = []
+    orig_check = ops.N.check
+
+    def counting_check(rc, what):
+        launches["n"] += 1
+        return orig_check(rc, what)
+    ops.N.check = counting_check
+    orig_cg = ops.pressure_cg
+
+    def timed_cg(*a, **k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = orig_cg(*a, **k)
+        e1.record()
+        cg_events.append((e0, e1, out[1]))
+        return out
+    ops.pressure_cg = timed_cg
+
+    vel, pres = torch.as_tensor(vel_h).to(dev), torch.as_tensor(pres_h).to(dev)
+    for _ in range(args.warmup):
+        vel, pres, gv, gp = step(vel, pres)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing --------------------------------------------------------------------------------
+    cg_events.clear()
+    launches["n"] = 0
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        vel, pres, gv, gp = step(vel, pres)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    n_launch = launches["n"]
+    clocks = sampler.stop() if sampler else None
+    cg_ms = [a.elapsed_time(b) for a, b, _ in cg_events]
+    cg_its = np.concatenate([it.cpu().numpy() for _, _, it in cg_events]).astype(np.float64)
+    finite = bool(torch.isfinite(vel).all() and torch.isfinite(gv).all())
+
+    # ---- forward-only rollout (reported beside the headline) -------------------------------------------------------
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    vf, pf = vel.clone(), pres.clone()
+    f0.record()
+    with torch.no_grad():
+        for _ in range(args.steps):
+            velocity = dp.StaggeredGrid(flat=vf, resolution=(NY, NX), box=box, extrapolation="periodic")
+            pressure = dp.CenteredGrid(pf.reshape(BATCH, NY, NX, 1), box=box, extrapolation="periodic")
+            v_new, p_new, _ = dp.piso_step(velocity, pressure, pressure, pressure, s["dt"], sim, dvals)
+            vf, pf = v_new.flat, p_new.data.reshape(BATCH, nc)
+    f1.record()
+    barrier()
+    ms_fwd = f0.elapsed_time(f1)
+
+    # ---- end-to-end: host buffers in, host buffers out, every step ------------------------------------------------
+    hv = torch.as_tensor(vel.cpu().numpy()).pin_memory()
+    hp = torch.as_tensor(pres.cpu().numpy()).pin_memory()
+    out_v, out_p = torch.empty_like(hv).pin_memory(), torch.empty_like(hp).pin_memory()
+    out_gv, out_gp = torch.empty_like(hv).pin_memory(), torch.empty_like(hp).pin_memory()
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(args.steps):
+        dv = hv.to(dev, non_blocking=True)
+        dpres = hp.to(dev, non_blocking=True)
+        nv, npr, gv2, gp2 = step(dv, dpres)
+        out_v.copy_(nv, non_blocking=True); out_p.copy_(npr, non_blocking=True)
+        out_gv.copy_(gv2, non_blocking=True); out_gp.copy_(gp2, non_blocking=True)
+        torch.cuda.synchronize()
+        hv.copy_(out_v); hp.copy_(out_p)
+    g1.record()
+    barrier()
+    ms_e2e = g0.elapsed_time(g1)
+
+    times = torch.tensor([ms, ms_fwd, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms, ms_fwd, ms_e2e = [float(x) for x in times.cpu()]
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cells = BATCH * nc * world
+    value = cells * args.steps / (ms * 1e-3)
+    # roofline of the dominant kernel (pressure CG): algorithmic bytes of SURVEY 8(d) / measured launch duration
+    mean_it = float(cg_its.mean())
+    resets = math.floor((mean_it + 1) / s["cg_reset"])
+    bytes_per_launch = BATCH * nc * (CG_BYTES_PER_CELL_ITER * mean_it + CG_BYTES_PER_CELL_RESET * resets)
+    cg_avg_ms = float(np.mean(cg_ms))
+    achieved = bytes_per_launch / (cg_avg_ms * 1e-3) / 1e9
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "cg_dram_traffic.json")))["bytes_per_launch"]
+    except Exception:
+        pass
+    cfg = ops.pressure_cg_config()
+    line = {
+        "metric": "piso_cell_updates_per_s_fwd_adjoint", "value": value, "unit": "cell-updates/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "grid": [NY, NX], "batch_per_gpu": BATCH, "visc": 1e-3, "cfl": 0.5,
+                   "bicgstab": "fp32 tol 1e-8", "pressure_cg": "fp64 tol 1e-8 reset 1000",
+                   "l2": "per-step working set (~0.4 GB of solver workspace + state) exceeds the 126 MB L2; rollout "
+                         "state changes every step", "cg_launch": cfg},
+        "forward_only": {"value": cells * args.steps / (ms_fwd * 1e-3), "unit": "cell-updates/s",
+                         "ms_per_step": ms_fwd / args.steps},
+        "e2e": {"value": cells * args.steps / (ms_e2e * 1e-3), "unit": "cell-updates/s",
+                "h2d_bytes_per_step": int(BATCH * (nf + nc) * 4), "d2h_bytes_per_step": int(2 * BATCH * (nf + nc) * 4)},
+        "gpu_launches": n_launch,
+        "roofline": {"bound": "hbm", "kernel": "pressure_cg_kernel<double,float,4,...> (4 launches per fwd+adjoint step)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                     "algorithmic_bytes_per_launch": bytes_per_launch, "mean_cg_iterations": mean_it,
+                     "avg_launch_ms": cg_avg_ms, "cg_share_of_step": float(sum(cg_ms) / ms),
+                     "note": "state is register/smem resident: algorithmic HBM model of SURVEY 8(d) is exceeded by "
+                             "design; traffic = ncu-measured DRAM bytes per launch"},
+        "clocks": clocks, "finite": finite,
+    }
+    if args.cpu_baseline:
+        cores = 1
+        v, dt = cpu_throughput(cores, args.cpu_steps, adjoint=True)
+        line["cpu_baseline"] = {"value": v, "unit": "cell-updates/s", "cores": cores, "kind": "port",
+                                "sample": "1 sample x %d fwd+adjoint steps of the 128x128 case (%.1f s)" % (args.cpu_steps, dt)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--cpu-steps", type=int, default=4)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            args.cpu_baseline = args.cpu_baseline and int(os.environ.get("RANK", "0")) == 0
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

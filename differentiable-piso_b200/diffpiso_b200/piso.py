@@ -161,13 +161,14 @@ def make_step_context(velocity, pressure, pressure_inc, dt, simulation_physics, 
     c = _Ctx()
     c.g = ops.Geometry.get(ny, nx, per_y, per_x, device)
     c.m = ops.to_device_masks(sim, c.g)
-    # the kernels take fp32 spacings (grid_spacing / cell_area are fp32 op inputs, piso_tf.py:96-97); the derived
-    # constants are formed in fp64 from those and rounded once, like the TF graph constants
-    c.dy, c.dx = float(np.float32(velocity.dx[0])), float(np.float32(velocity.dx[1]))
-    prod = c.dy * c.dx
-    c.prod = float(np.float32(prod))
+    # fp32 spacings for the kernels (grid_spacing is an fp32 op input, piso_tf.py:96); the graph constants are formed
+    # in fp64 on the host and rounded once to fp32, as the TF graph does with the reference's numpy expressions
+    dy64, dx64 = float(velocity.dx[0]), float(velocity.dx[1])
+    c.dy, c.dx = float(np.float32(dy64)), float(np.float32(dx64))
+    prod = dy64 * dx64
+    c.prod = float(np.float32(float(np.float32(dy64)) * float(np.float32(dx64))))   # as the kernels form it
     c.beta = float(np.float32(prod / float(dt)))                       # piso_tf.py:26
-    c.dx_factor = float(np.float32(prod / (c.dy * c.dy)))              # piso_tf.py:53 (dx[0] = dy)
+    c.dx_factor = float(np.float32(prod / (dy64 * dy64)))              # piso_tf.py:53 (dx[0] = dy)
     c.pbc = extrapolation_codes(pressure.extrapolation)
     c.pbc_inc = extrapolation_codes(pressure_inc.extrapolation)
     c.sim = sim

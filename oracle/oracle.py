@@ -190,6 +190,14 @@ def h_apply(rp, ci, val, a_diag, beta, d):
     return h
 
 
+def step_constants(dy, dx, dt):
+    """fp32 graph constants formed in fp64 on the Python side of the reference: beta = prod(dx)/dt (piso_tf.py:26),
+    prod(dx), dx_factor = prod(dx)/dx[0]**2 (piso_tf.py:53; dx[0] = dy)."""
+    prod = float(dy) * float(dx)
+    return dict(beta=float(np.float32(prod / float(dt))), prod=float(np.float32(prod)),
+                dx_factor=float(np.float32(prod / (float(dy) ** 2))))
+
+
 class _Extra(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in
                 ("values", "a_diag", "rhs", "u_star", "div1", "p1", "u_s2", "h", "div2", "p2", "lap64", "lap32")]
@@ -211,7 +219,9 @@ def piso_step(setup, vel, pres, forcing=None, dirichlet_values=None, full_output
     ip = np.array([ny, nx, int(s["per_y"]), int(s["per_x"])] + list(s["pbc"]) + list(s["pbc_inc"]) +
                   [int(visc.size > 1), s["bicg_max_it"], s["cg_max_it"], s["cg_reset"], int(s["rank_deficient"]),
                    int(s.get("cg_fp64", True))], np.int32)
-    fp = np.array([s["dy"], s["dx"], s["dt"], s["bicg_tol"], s["cg_tol"]], np.float32)
+    c = step_constants(s["dy"], s["dx"], s["dt"])
+    fp = np.array([s["dy"], s["dx"], s["dt"], s["bicg_tol"], s["cg_tol"], c["beta"], c["prod"], c["dx_factor"]],
+                  np.float32)
     vel, pres = _f32(vel).ravel(), _f32(pres).ravel()
     assert vel.size == nf and pres.size == nc
     dmask = _u8(s["dirichlet"]).ravel()

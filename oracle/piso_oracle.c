@@ -569,7 +569,8 @@ void orc_h_apply(int n, const int *rp, const int *ci, const float *val, const fl
  * iparams: [0]=ny [1]=nx [2]=per_y [3]=per_x [4..7]=pbc of pressure (y_lo,y_hi,x_lo,x_hi)
  *          [8..11]=pbc of the pressure increments [12]=visc_is_field [13]=bicg max_it
  *          [14]=cg max_it [15]=cg residual_reset [16]=rank_deficient [17]=cg fp64 (1) / fp32 (0)
- * fparams: [0]=dy [1]=dx [2]=dt [3]=bicg tol [4]=cg accuracy
+ * fparams: [0]=dy [1]=dx [2]=dt [3]=bicg tol [4]=cg accuracy [5]=beta [6]=unused [7]=dx_factor
+ *          ([5..7] are the fp32 graph constants the Python side forms in fp64, piso_tf.py:26,53; 0 = derive here)
  * out_stats (int[12]): [0..3] u solve stats, [4..7] v solve stats, [8] cg1 its, [9] cg2 its
  * optional outputs may be NULL.
  * ---------------------------------------------------------------------------------------- */
@@ -590,9 +591,9 @@ int orc_piso_step(const int *ip, const float *fp, const float *vel, const float 
     if (orc_sizes(ny, nx, per_x, per_y, n, nnz)) return ORC_EBADGRID;
     const int nf = n[0] + n[1], nc = ny * nx, nz = nnz[0] + nnz[1];
     const double prod_d = (double)dy * (double)dx;
-    const float prod = (float)prod_d;
-    const float beta = (float)(prod_d / (double)dt);                         /* piso_tf.py:26 */
-    const float dx_factor = (float)(prod_d / ((double)dy * (double)dy));      /* piso_tf.py:53 (dx[0] = dy) */
+    const float prod = (float)prod_d;    /* as inside orc_fv_gradient / orc_fv_divergence */
+    const float beta = fp[5] != 0.0f ? fp[5] : (float)(prod_d / (double)dt);  /* piso_tf.py:26 */
+    const float dx_factor = fp[5] != 0.0f ? fp[7] : (float)(prod_d / ((double)dy * (double)dy)); /* piso_tf.py:53 (dx[0] = dy) */
 
     int *row_ptr = (int *)malloc(sizeof(int) * (size_t)(nf + 2));
     int *col_ind = (int *)malloc(sizeof(int) * (size_t)nz);

@@ -1,0 +1,127 @@
+"""GPU parity of the backward pass: the transposed pointwise kernels against their numpy restatements (incl. the
+reference's periodic-axis conventions Q19/Q20), exact-transpose dot-product tests on non-periodic grids, and the whole
+`piso_step` backward (torch.autograd through the public API) against oracle/adjoint.py."""
+import numpy as np
+import pytest
+import torch
+
+from common import SMALL_SETUPS, random_fields, rel_l2
+from oracle import adjoint as A
+from oracle import oracle as O
+from test_gpu_piso_step import DEV, build_sim, extrap
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(a, dtype=torch.float32):
+    return torch.as_tensor(np.ascontiguousarray(a)).to(dtype).to(DEV)
+
+
+@pytest.mark.parametrize("name", ["ldc8", "periodic16", "periodic24x20", "tml16x24", "sml16x48"])
+def test_pointwise_adjoint_kernels(name):
+    from diffpiso_b200 import ops
+    s = SMALL_SETUPS[name]()
+    g = ops.Geometry.get(s["ny"], s["nx"], s["per_y"], s["per_x"], DEV)
+    rng = np.random.RandomState(11)
+    access = _t(s["access"])
+    gs = rng.randn(2, g.nf).astype(np.float32)
+    gc = rng.randn(2, g.nc).astype(np.float32)
+    base_c = rng.randn(2, g.nc).astype(np.float32)
+    a_diag = (-rng.rand(2, g.nf)).astype(np.float32)
+    beta = 3.0
+    prod = np.float32(np.float64(np.float32(s["dy"])) * np.float64(np.float32(s["dx"])))
+    for pbc in (s["pbc"], s["pbc_inc"]):
+        out = ops.fv_gradient_adj(g, _t(gs), access, s["dy"], s["dx"], pbc).cpu().numpy()
+        out2 = ops.fv_gradient_adj(g, _t(gs), access, s["dy"], s["dx"], pbc, a_diag=_t(a_diag), beta=beta,
+                                   divisor=float(prod), negate=True, base=_t(base_c)).cpu().numpy()
+        for i in range(2):
+            ref = A.fv_gradient_adj(s["ny"], s["nx"], s["dy"], s["dx"], pbc, s["access"], gs[i])
+            assert rel_l2(out[i], ref) < 1e-6
+            t = -((gs[i] / (np.float32(beta) - a_diag[i])) / prod)
+            ref2 = base_c[i] + A.fv_gradient_adj(s["ny"], s["nx"], s["dy"], s["dx"], pbc, s["access"], t)
+            assert rel_l2(out2[i], ref2) < 1e-6
+    dv = ops.fv_divergence_adj(g, _t(gc), s["dy"], s["dx"]).cpu().numpy()
+    dv2 = ops.fv_divergence_adj(g, _t(gc), s["dy"], s["dx"], base=_t(gs), a_diag=_t(a_diag), beta=beta).cpu().numpy()
+    for i in range(2):
+        ref = A.fv_divergence_adj(s["ny"], s["nx"], s["per_x"], s["per_y"], s["dy"], s["dx"], gc[i])
+        assert np.array_equal(dv[i], ref)
+        assert rel_l2(dv2[i], (gs[i] + ref) / (np.float32(beta) - a_diag[i])) < 1e-6
+    # H^T against scipy's transposed product on assembled matrices
+    vels = np.stack([random_fields(s, 30 + i)[0] for i in range(2)])
+    m = dict(dirichlet=_t(s["dirichlet"], torch.uint8), active=_t(s["active"]), noslip=_t(s["noslip"], torch.uint8))
+    c = O.step_constants(s["dy"], s["dx"], s["dt"])
+    values, adg = ops.assemble(g, _t(vels), m["dirichlet"], m["active"], m["noslip"], _t(np.atleast_1d(s["visc"])),
+                               s["dy"], s["dx"], c["beta"])
+    ht = ops.h_apply_adj(g, values, adg, _t(gs), c["beta"]).cpu().numpy()
+    for i in range(2):
+        ref = A.h_apply_adj(s, values[i].cpu().numpy(), adg[i].cpu().numpy(), c["beta"], gs[i])
+        assert rel_l2(ht[i], ref) < 1e-6
+    # forward H and H^T are transposes of each other: <H d, w> == <d, H^T w>
+    d = rng.randn(2, g.nf).astype(np.float32)
+    hd = ops.h_apply(g, values, adg, torch.zeros(2, g.nf, device=DEV), _t(d), c["beta"]).cpu().numpy().astype(np.float64)
+    assert abs((hd * gs).sum() - (d.astype(np.float64) * ht).sum()) < 1e-4 * abs((hd * gs).sum()) + 1e-6
+
+
+@pytest.mark.parametrize("name", ["ldc8", "sml16x48"])
+def test_nonperiodic_adjoints_are_exact_transposes(name):
+    """<G p, s> == <p, G^T s> and <D v, g> == <v, D^T g> on grids without periodic axes."""
+    from diffpiso_b200 import ops
+    s = SMALL_SETUPS[name]()
+    g = ops.Geometry.get(s["ny"], s["nx"], s["per_y"], s["per_x"], DEV)
+    rng = np.random.RandomState(2)
+    access = _t(s["access"])
+    p, sf = _t(rng.randn(1, g.nc)), _t(rng.randn(1, g.nf))
+    for pbc in (s["pbc"], s["pbc_inc"]):
+        lhs = (ops.fv_gradient(g, p, access, s["dy"], s["dx"], pbc).double() * sf.double()).sum()
+        rhs = (p.double() * ops.fv_gradient_adj(g, sf, access, s["dy"], s["dx"], pbc).double()).sum()
+        assert abs(lhs - rhs) < 1e-5 * abs(lhs) + 1e-7
+    v, gc = _t(rng.randn(1, g.nf)), _t(rng.randn(1, g.nc))
+    lhs = (ops.fv_divergence(g, v, s["dy"], s["dx"]).double() * gc.double()).sum()
+    rhs = (v.double() * ops.fv_divergence_adj(g, gc, s["dy"], s["dx"]).double()).sum()
+    assert abs(lhs - rhs) < 1e-5 * abs(lhs) + 1e-7
+
+
+@pytest.mark.parametrize("name", ["periodic16", "periodic24x20", "tml16x24", "sml16x48", "ldc8"])
+def test_piso_step_backward_matches_oracle(name):
+    """loss = <w_u, u_next> + <w_p, p_next>; gradients w.r.t. velocity, pressure, forcing and Dirichlet values from
+    torch.autograd through piso_step against oracle/adjoint.py: 1e-4 relative L2 (three nested iterative solves at the
+    same tolerance on both sides)."""
+    import diffpiso_b200 as dp
+    s = SMALL_SETUPS[name]()
+    sim = build_sim(s)
+    ny, nx = s["ny"], s["nx"]
+    nf, nc = ny * (nx + 1) + (ny + 1) * nx, ny * nx
+    rng = np.random.RandomState(5)
+    states = [random_fields(s, 50 + i) for i in range(2)]
+    vel = np.stack([v for v, _ in states])
+    pres = np.stack([p for _, p in states])
+    forcing = (rng.randn(2, nf) * 0.01).astype(np.float32)
+    w_u, w_p = rng.randn(2, nf).astype(np.float32), rng.randn(2, nc).astype(np.float32)
+    if s["rank_deficient"]:      # keep the adjoint pressure right-hand sides compatible (zero mean on active cells)
+        act = s["active"].reshape(ny + 2, nx + 2)[1:-1, 1:-1].ravel() != 0
+        w_p[:, ~act] = 0
+        w_p[:, act] -= w_p[:, act].mean(axis=1, keepdims=True)
+    box = (ny * s["dy"], nx * s["dx"])
+    tv = _t(vel).requires_grad_(True)
+    tp = _t(pres).requires_grad_(True)
+    tf = _t(forcing).requires_grad_(True)
+    td = _t(s["dirichlet_values"])[None].clone().requires_grad_(True)
+    velocity = dp.StaggeredGrid(flat=tv, resolution=(ny, nx), box=box)
+    pressure = dp.CenteredGrid(tp.reshape(2, ny, nx, 1), box=box, extrapolation=extrap(s["pbc"]))
+    inc = dp.CenteredGrid(torch.zeros(2, ny, nx, 1, device=DEV), box=box, extrapolation=extrap(s["pbc_inc"]))
+    visc_field = _t(s["visc"]) if np.atleast_1d(s["visc"]).size > 1 else None
+    v_new, p_new, warn = dp.piso_step(velocity, pressure, inc, inc, s["dt"], sim, td, viscosity_field=visc_field,
+                                      forcing_term=tf)
+    loss = (v_new.flat * _t(w_u)).sum() + (p_new.data.reshape(2, nc) * _t(w_p)).sum()
+    loss.backward()
+    gd_total = np.zeros(nf, np.float32)
+    for i in range(2):
+        ref = A.piso_step_adjoint(s, vel[i], pres[i], w_u[i], w_p[i], forcing=forcing[i])
+        assert rel_l2(tv.grad[i].cpu().numpy(), ref["g_vel"]) < 1e-4, (name, i, "vel")
+        assert rel_l2(tp.grad[i].cpu().numpy(), ref["g_pres"]) < 1e-4, (name, i, "pres")
+        assert rel_l2(tf.grad[i].cpu().numpy(), ref["g_forcing"]) < 1e-4, (name, i, "forcing")
+        gd_total += ref["g_dvals"]
+        cg_adj = [int(sim.pressure_solver.last_adjoint_iterations[i])]
+        assert abs(cg_adj[0] - ref["stats"]["cg_adj"][1]) <= 5
+    if s["dirichlet"].any():
+        assert rel_l2(td.grad[0].cpu().numpy(), gd_total) < 1e-4

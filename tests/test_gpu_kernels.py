@@ -1,0 +1,199 @@
+"""GPU parity tests: every native entry point, called through the C ABI binding, against the CPU oracle on the same
+seeded inputs.  Integer outputs bit-exact; fp32 fields within the tolerances written next to each assert
+(north_star: 1e-5 relative L2 per step, iteration counts within +-1)."""
+import numpy as np
+import pytest
+import torch
+
+from common import SMALL_SETUPS, random_fields, rel_l2
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _geom(s):
+    from diffpiso_b200 import ops
+    return ops.Geometry.get(s["ny"], s["nx"], s["per_y"], s["per_x"], DEV)
+
+
+def _t(a, dtype=torch.float32):
+    return torch.as_tensor(np.ascontiguousarray(a)).to(dtype).to(DEV)
+
+
+def _masks(s):
+    return dict(dirichlet=_t(s["dirichlet"], torch.uint8), active=_t(s["active"]), access=_t(s["access"]),
+                noslip=_t(s["noslip"], torch.uint8))
+
+
+def _beta(s):
+    prod = float(np.float32(s["dy"])) * float(np.float32(s["dx"]))
+    return float(np.float32(prod / float(np.float32(s["dt"]))))
+
+
+@pytest.mark.parametrize("ny,nx", [(3, 3), (4, 5), (7, 6), (33, 32), (128, 128), (40, 300)])
+@pytest.mark.parametrize("per_x,per_y", [(0, 0), (1, 1), (1, 0), (0, 1)])
+def test_csr_structure_bit_exact(ny, nx, per_x, per_y):
+    from diffpiso_b200 import ops
+    g = ops.Geometry.get(ny, nx, bool(per_y), bool(per_x), DEV)
+    rp, ci = g.csr_structure()
+    orp, oci = O.csr_structure(ny, nx, per_x, per_y)
+    assert rp.dtype == torch.int32 and ci.dtype == torch.int32
+    assert np.array_equal(rp.cpu().numpy(), orp)
+    assert np.array_equal(ci.cpu().numpy(), oci)
+
+
+@pytest.mark.parametrize("name", list(SMALL_SETUPS))
+def test_assemble_matches_oracle(name):
+    """values / A of a batch of 3 samples: bit-exact against the oracle (same operation order)."""
+    from diffpiso_b200 import ops
+    s = SMALL_SETUPS[name]()
+    g, m = _geom(s), _masks(s)
+    vels = np.stack([random_fields(s, 10 + i)[0] for i in range(3)])
+    visc = _t(np.atleast_1d(s["visc"]))
+    values, a_diag = ops.assemble(g, _t(vels), m["dirichlet"], m["active"], m["noslip"], visc, s["dy"], s["dx"], _beta(s))
+    orp, _ = O.csr_structure(s["ny"], s["nx"], s["per_x"], s["per_y"])
+    n_u = g.n_u
+    for i in range(3):
+        u, v = vels[i][:n_u].reshape(s["ny"], s["nx"] + 1), vels[i][n_u:].reshape(s["ny"] + 1, s["nx"])
+        up, vp = O.pad_velocity(s["ny"], s["nx"], s["per_x"], s["per_y"], u, v)
+        ov, oa = O.assemble(s["ny"], s["nx"], s["per_x"], s["per_y"], s["dy"], s["dx"], _beta(s), up, vp, s["dirichlet"],
+                            s["active"], s["noslip"], s["visc"], orp)
+        assert np.array_equal(values[i].cpu().numpy(), ov)
+        assert np.array_equal(a_diag[i].cpu().numpy(), oa)
+
+
+@pytest.mark.parametrize("name", ["ldc8", "periodic16", "tml16x24", "sml16x48"])
+def test_gradient_divergence_laplace_match_oracle(name):
+    from diffpiso_b200 import ops
+    s = SMALL_SETUPS[name]()
+    g, m = _geom(s), _masks(s)
+    rng = np.random.RandomState(3)
+    p = rng.randn(2, g.nc).astype(np.float32)
+    vel = rng.randn(2, g.nf).astype(np.float32)
+    a_diag = (-rng.rand(2, g.nf)).astype(np.float32)
+    beta = _beta(s)
+    gr = ops.fv_gradient(g, _t(p), m["access"], s["dy"], s["dx"], s["pbc"]).cpu().numpy()
+    dv = ops.fv_divergence(g, _t(vel), s["dy"], s["dx"]).cpu().numpy()
+    dv2 = ops.fv_divergence(g, _t(vel), s["dy"], s["dx"], a_diag=_t(a_diag), beta=beta).cpu().numpy()
+    for i in range(2):
+        assert np.array_equal(gr[i], O.fv_gradient(s["ny"], s["nx"], s["dy"], s["dx"], s["pbc"], s["access"], p[i]))
+        assert np.array_equal(dv[i], O.fv_divergence(s["ny"], s["nx"], s["dy"], s["dx"], vel[i]))
+        scaled = (vel[i] / (np.float32(beta) - a_diag[i])).astype(np.float32)
+        assert np.array_equal(dv2[i], O.fv_divergence(s["ny"], s["nx"], s["dy"], s["dx"], scaled))
+    # Laplace: mode 0 ([v,u] scaling field) and mode 1 (from the diagonal), fp64 and fp32
+    dx_factor = float(np.float32(s["dx"] / s["dy"]))
+    k_uv = ((np.float32(1.0) / (np.float32(beta) - a_diag)) * np.float32(dx_factor)).astype(np.float32)
+    k_vu = np.concatenate([k_uv[:, g.n_u:], k_uv[:, :g.n_u]], axis=1)
+    for fp64, dt in ((True, np.float64), (False, np.float32)):
+        l0 = ops.laplace(g, m["active"], m["access"], _t(k_vu), 0, 0.0, 1.0, fp64=fp64).cpu().numpy()
+        l1 = ops.laplace(g, m["active"], m["access"], _t(a_diag), 1, beta, dx_factor, fp64=fp64).cpu().numpy()
+        for i in range(2):
+            ref = O.laplace(s["ny"], s["nx"], s["active"], s["access"], k_vu[i], dt)
+            assert np.array_equal(l0[i].ravel(), ref)
+            assert np.array_equal(l1[i].ravel(), ref)
+
+
+def _cg_problem(s, seed, batch):
+    """Laplace matrix from a random negative diagonal + a compatible right-hand side per sample."""
+    from diffpiso_b200 import ops
+    g, m = _geom(s), _masks(s)
+    rng = np.random.RandomState(seed)
+    a_diag = (-rng.rand(batch, g.nf) * 0.5).astype(np.float32)
+    beta = _beta(s)
+    dx_factor = float(np.float32(s["dx"] / s["dy"]))
+    div = (rng.randn(batch, g.nc) * 0.1).astype(np.float32)
+    if s["rank_deficient"]:
+        act = s["active"].reshape(s["ny"] + 2, s["nx"] + 2)[1:-1, 1:-1].ravel() != 0
+        div[:, ~act] = 0
+        div[:, act] -= div[:, act].mean(axis=1, keepdims=True)
+    return g, m, a_diag, beta, dx_factor, div
+
+
+@pytest.mark.parametrize("name", ["ldc8", "ldc32", "periodic16", "periodic24x20", "periodic32", "tml16x24", "sml16x48"])
+@pytest.mark.parametrize("fp64", [True, False])
+def test_pressure_cg_matches_oracle(name, fp64):
+    """x within 1e-6 relative L2 (fp64) of the oracle at the same tolerance; iteration counts identical up to one
+    check period (the counts are quantised to the 5-iteration check cadence)."""
+    from diffpiso_b200 import ops
+    s = SMALL_SETUPS[name]()
+    g, m, a_diag, beta, dx_factor, div = _cg_problem(s, 5, 3)
+    tol = s["cg_tol"] if fp64 else 1e-4
+    lap = ops.laplace(g, m["active"], m["access"], _t(a_diag), 1, beta, dx_factor, fp64=fp64)
+    x, its = ops.pressure_cg(g, lap, _t(div), tol, s["cg_max_it"], s["cg_reset"], s["rank_deficient"])
+    x, its = x.cpu().numpy(), its.cpu().numpy()
+    cfg = ops.pressure_cg_config()
+    assert cfg["cluster"] >= 1 and cfg["threads"] % 32 == 0
+    lap_h = lap.cpu().numpy()
+    for i in range(3):
+        d = div[i].astype(np.float64 if fp64 else np.float32)
+        ox, oit = O.pressure_cg(s["ny"], s["nx"], s["per_x"], s["per_y"], lap_h[i].ravel(), d, tol, s["cg_max_it"],
+                                s["cg_reset"], s["rank_deficient"])
+        assert abs(int(its[i]) - oit) <= 5, (name, i, int(its[i]), oit)
+        if fp64:
+            assert int(its[i]) == oit, (name, i, int(its[i]), oit)
+            assert rel_l2(x[i], ox.astype(np.float32)) < 1e-6
+        else:
+            assert rel_l2(x[i], ox) < 5e-3
+
+
+def test_pressure_cg_zero_rhs_and_max_iterations():
+    """Edge cases: zero right-hand side returns zeros (documented deviation D1 from the reference's 0/0) and the
+    iteration cap is honoured."""
+    from diffpiso_b200 import ops
+    s = SMALL_SETUPS["periodic16"]()
+    g, m, a_diag, beta, dx_factor, div = _cg_problem(s, 6, 2)
+    lap = ops.laplace(g, m["active"], m["access"], _t(a_diag), 1, beta, dx_factor, fp64=True)
+    x, its = ops.pressure_cg(g, lap, _t(np.zeros_like(div)), 1e-8, 1000, 1000, True)
+    assert torch.all(x == 0) and its.cpu().tolist() == [10, 10]
+    x, its = ops.pressure_cg(g, lap, _t(div), 1e-30, 37, 1000, True)
+    assert its.cpu().tolist() == [37, 37] and torch.isfinite(x).all()
+
+
+@pytest.mark.parametrize("name", ["ldc8", "periodic16", "periodic24x20", "tml16x24", "sml16x48"])
+@pytest.mark.parametrize("transpose", [False, True])
+def test_bicgstab_matches_oracle(name, transpose):
+    """Assembled -M systems of 2 samples: solution within 1e-5 relative L2 of the oracle, iteration counts / restarts /
+    exit kind identical (+-1 iteration allowed), for A and for A^T."""
+    from diffpiso_b200 import ops
+    s = SMALL_SETUPS[name]()
+    g, m = _geom(s), _masks(s)
+    vels = np.stack([random_fields(s, 20 + i)[0] for i in range(2)])
+    visc = _t(np.atleast_1d(s["visc"]))
+    values, _ = ops.assemble(g, _t(vels), m["dirichlet"], m["active"], m["noslip"], visc, s["dy"], s["dx"], _beta(s))
+    neg = torch.neg(values)
+    rng = np.random.RandomState(7)
+    rhs = rng.randn(2, g.nf).astype(np.float32)
+    x, stats, warn = ops.bicgstab_ilu(g, neg, _t(rhs), _t(vels), s["bicg_tol"], s["bicg_max_it"], transpose)
+    x, stats = x.cpu().numpy(), stats.cpu().numpy()
+    assert int(warn.item()) == 0
+    orp, oci = O.csr_structure(s["ny"], s["nx"], s["per_x"], s["per_y"])
+    negh = neg.cpu().numpy()
+    for i in range(2):
+        for comp, (r0, r1, z0, z1, rp) in enumerate(((0, g.n_u, 0, g.nnz_u, orp[:g.n_u + 1]),
+                                                     (g.n_u, g.nf, g.nnz_u, g.nnz, orp[g.n_u + 1:]))):
+            ox, st = O.bicgstab_ilu(rp, oci[z0:z1], negh[i, z0:z1], rhs[i, r0:r1], vels[i, r0:r1], s["bicg_tol"],
+                                    s["bicg_max_it"], transpose)
+            got = stats[i, comp]
+            assert abs(int(got[0]) - st["iterations"]) <= 1, (name, i, comp, got, st)
+            assert int(got[1]) == st["restarts"] and int(got[2]) == st["warn"], (name, i, comp, got, st)
+            assert rel_l2(x[i, r0:r1], ox) < 1e-5, (name, i, comp, rel_l2(x[i, r0:r1], ox), got, st)
+
+
+def test_bicgstab_nan_sets_warn_and_lucky_guess():
+    from diffpiso_b200 import ops
+    s = SMALL_SETUPS["periodic16"]()
+    g, m = _geom(s), _masks(s)
+    vel = random_fields(s, 1)[0][None]
+    values, _ = ops.assemble(g, _t(vel), m["dirichlet"], m["active"], m["noslip"], _t(np.atleast_1d(s["visc"])), s["dy"],
+                             s["dx"], _beta(s))
+    neg = torch.neg(values)
+    # exact solution as initial guess -> "lucky guess" exit without iterations
+    x0 = _t(np.random.RandomState(0).randn(1, g.nf).astype(np.float32))
+    x1, st1, _ = ops.bicgstab_ilu(g, neg, _t(np.zeros((1, g.nf), np.float32)), torch.zeros_like(x0), 1e-6, 50)
+    assert st1.cpu().numpy()[0, :, 0].tolist() == [0, 0] and st1.cpu().numpy()[0, :, 3].tolist() == [0, 0]
+    assert torch.all(x1 == 0)
+    rhs = torch.full((1, g.nf), float("nan"), device=DEV)
+    _, st2, warn = ops.bicgstab_ilu(g, neg, rhs, x0, 1e-6, 5)
+    assert int(warn.item()) == 1 and st2.cpu().numpy()[0, :, 2].tolist() == [1, 1]

@@ -1,0 +1,157 @@
+"""GPU parity of the whole PISO step through the reference-shaped API (`piso_step`, `SimulationParameters`, the two
+solver classes) against the CPU oracle, plus domain-level known answers (Taylor-Green decay, divergence-free output)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from common import SMALL_SETUPS, random_fields, rel_l2
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def build_sim(s):
+    import diffpiso_b200 as dp
+    ls = dp.LinearSolverCudaMultiBicgstabILU(accuracy=s["bicg_tol"], max_iterations=s["bicg_max_it"])
+    ps = dp.PisoPressureSolverCudaCustom(dx=s["dx"], accuracy=s["cg_tol"], max_iterations=s["cg_max_it"],
+                                         residual_reset=s["cg_reset"], cast_to_double=s.get("cg_fp64", True))
+    sim = dp.SimulationParameters(dirichlet_mask=s["dirichlet_mask"], dirichlet_values=s["dirichlet_values_staggered"],
+                                  active_mask=s["active_mask"], accessible_mask=s["accessible_mask"],
+                                  bool_periodic=(s["per_y"], s["per_x"]), no_slip_mask=s["no_slip_mask"],
+                                  viscosity=float(np.atleast_1d(s["visc"])[0]), linear_solver=ls, pressure_solver=ps)
+    return sim
+
+
+_CODE = {0: "boundary", 1: "constant", 2: "periodic"}
+
+
+def extrap(pbc):
+    return ((_CODE[pbc[0]], _CODE[pbc[1]]), (_CODE[pbc[2]], _CODE[pbc[3]]))
+
+
+def run_step(s, sim, vel_flat, pres, forcing=None, full_output=False):
+    import diffpiso_b200 as dp
+    b = vel_flat.shape[0]
+    ny, nx = s["ny"], s["nx"]
+    box = (ny * s["dy"], nx * s["dx"])
+    velocity = dp.StaggeredGrid(flat=torch.as_tensor(vel_flat).to(DEV), resolution=(ny, nx), box=box)
+    pressure = dp.CenteredGrid(torch.as_tensor(pres).reshape(b, ny, nx, 1).to(DEV), box=box, extrapolation=extrap(s["pbc"]))
+    inc = dp.CenteredGrid(torch.zeros(b, ny, nx, 1, device=DEV), box=box, extrapolation=extrap(s["pbc_inc"]))
+    visc_field = None
+    if np.atleast_1d(s["visc"]).size > 1:
+        visc_field = torch.as_tensor(s["visc"]).to(DEV)
+    return dp.piso_step(velocity, pressure, inc, inc, s["dt"], sim, torch.as_tensor(s["dirichlet_values"])[None].to(DEV),
+                        viscosity_field=visc_field, forcing_term=forcing, full_output=full_output)
+
+
+@pytest.mark.parametrize("name", list(SMALL_SETUPS))
+def test_piso_step_matches_oracle(name):
+    """Three consecutive steps of a batch of 2 seeded samples; every intermediate of the first step and the state after
+    each step within 1e-5 relative L2 of the oracle (north_star tolerance), solver iteration counts within +-1
+    (BiCGStab) / one check period (CG)."""
+    s = SMALL_SETUPS[name]()
+    sim = build_sim(s)
+    states = [random_fields(s, 40 + i) for i in range(2)]
+    vel = np.stack([v for v, _ in states])
+    pres = np.stack([p for _, p in states])
+    g_nu = s["ny"] * (s["nx"] + 1)
+    ovel, opres = vel.copy(), pres.copy()
+    for step in range(3):
+        out = run_step(s, sim, vel, pres, full_output=True)
+        v_new = out[0].flat.cpu().numpy()
+        p_new = out[1].data.reshape(2, -1).cpu().numpy()
+        bicg = sim.linear_solver.last_stats.cpu().numpy()
+        for i in range(2):
+            ov, op, st, ex = O.piso_step(s, ovel[i], opres[i], full_output=True)
+            if step == 0:
+                assert np.array_equal(out[4][i].cpu().numpy(), ex["values"])                    # matrix values
+                assert np.array_equal(out[9][i].cpu().numpy(), ex["a_diag"])                    # A
+                assert np.array_equal(out[10][i].cpu().numpy(), ex["rhs"])                      # implicit rhs
+                assert rel_l2(out[7][i].cpu().numpy()[:-1, :, 1].ravel(), ex["u_star"][:g_nu]) < 1e-5
+                assert rel_l2(out[13][i].cpu().numpy().ravel(), ex["div1"]) < 1e-4             # differences of u*
+                assert rel_l2(out[2].data[i].cpu().numpy().ravel(), ex["p1"]) < 1e-4
+            assert abs(int(bicg[i, 0, 0]) - st["bicg_u"][0]) <= 1 and abs(int(bicg[i, 1, 0]) - st["bicg_v"][0]) <= 1
+            assert rel_l2(v_new[i], ov) < 1e-5, (name, step, i, rel_l2(v_new[i], ov))
+            assert rel_l2(p_new[i], op) < 1e-4, (name, step, i, rel_l2(p_new[i], op))
+            ovel[i], opres[i] = ov, op
+        vel, pres = v_new, p_new
+
+
+def test_full_output_layout_and_csr():
+    """full_output returns the reference's 17-tuple (piso_tf.py:77-79) with bit-exact row_ptr / col_ind."""
+    s = SMALL_SETUPS["ldc8"]()
+    sim = build_sim(s)
+    vel, pres = random_fields(s, 1)
+    out = run_step(s, sim, vel[None], pres[None], full_output=True)
+    assert len(out) == 17
+    orp, oci = O.csr_structure(s["ny"], s["nx"], s["per_x"], s["per_y"])
+    assert np.array_equal(out[5].cpu().numpy(), oci) and np.array_equal(out[6].cpu().numpy(), orp)
+    assert tuple(out[0].staggered_tensor().shape) == (1, s["ny"] + 1, s["nx"] + 1, 2)
+    assert tuple(out[1].data.shape) == (1, s["ny"], s["nx"], 1)
+    assert out[14].dtype == torch.float64 and out[14].shape[1] == 5 * s["ny"] * s["nx"]
+
+
+def test_taylor_green_decay_known_answer():
+    """Periodic 32^2, 2pi box, nu = 0.1, dt = 0.01, 50 steps: the analytic Taylor-Green decay exp(-2 nu t) is
+    reproduced to 1e-3 relative L2, the duplicated periodic faces stay identical and the result is divergence free."""
+    from diffpiso_b200 import setups as SU
+    s = SU.periodic_box(32, 32, visc=0.1, dt=0.01, bicg_tol=1e-8, cg_tol=1e-8, cg_reset=1000)
+    sim = build_sim(s)
+    vel = SU.taylor_green(32, 32, t=0.0, visc=0.1)[None]
+    pres = np.zeros((1, 32 * 32), np.float32)
+    for _ in range(50):
+        out = run_step(s, sim, vel, pres)
+        vel, pres = out[0].flat.cpu().numpy(), out[1].data.reshape(1, -1).cpu().numpy()
+    exact = SU.taylor_green(32, 32, t=0.5, visc=0.1)
+    assert rel_l2(vel[0], exact) < 2e-3
+    u = vel[0][:32 * 33].reshape(32, 33)
+    assert np.abs(u[:, 0] - u[:, -1]).max() < 1e-6
+    div = O.fv_divergence(32, 32, s["dy"], s["dx"], vel[0])
+    assert np.abs(div).max() < 1e-6
+
+
+def test_lid_driven_cavity_divergence_free():
+    """LDC 32^2 (shipped layout Domain([N+1, N])), Re=100, 20 steps from rest: stable, max |div u| at rounding level in
+    the active cells, lid row keeps u = 1."""
+    s = SMALL_SETUPS["ldc32"]()
+    sim = build_sim(s)
+    vel = np.zeros((1, s["ny"] * (s["nx"] + 1) + (s["ny"] + 1) * s["nx"]), np.float32)
+    d = s["dirichlet"].astype(bool)
+    vel[0, d] = s["dirichlet_values"][d]
+    pres = np.zeros((1, s["ny"] * s["nx"]), np.float32)
+    for _ in range(20):
+        out = run_step(s, sim, vel, pres)
+        vel, pres = out[0].flat.cpu().numpy(), out[1].data.reshape(1, -1).cpu().numpy()
+    assert np.isfinite(vel).all()
+    div = O.fv_divergence(s["ny"], s["nx"], s["dy"], s["dx"], vel[0]).reshape(s["ny"], s["nx"])
+    assert np.abs(div[:-1]).max() < 1e-6
+    u = vel[0][:s["ny"] * (s["nx"] + 1)].reshape(s["ny"], s["nx"] + 1)
+    assert np.allclose(u[-1], 1.0)
+
+
+def test_batch_is_independent_samples():
+    """A batch of B samples gives exactly what B single-sample calls give (samples never interact)."""
+    s = SMALL_SETUPS["periodic16"]()
+    sim = build_sim(s)
+    states = [random_fields(s, 70 + i) for i in range(4)]
+    vel = np.stack([v for v, _ in states])
+    pres = np.stack([p for _, p in states])
+    out = run_step(s, sim, vel, pres)
+    vb = out[0].flat.cpu().numpy()
+    for i in range(4):
+        o1 = run_step(s, sim, vel[i:i + 1], pres[i:i + 1])
+        assert np.array_equal(o1[0].flat.cpu().numpy()[0], vb[i])
+
+
+def test_cpu_tensors_fail_loudly():
+    import diffpiso_b200 as dp
+    s = SMALL_SETUPS["ldc8"]()
+    sim = build_sim(s)
+    vel, pres = random_fields(s, 1)
+    velocity = dp.StaggeredGrid(flat=torch.as_tensor(vel[None]), resolution=(s["ny"], s["nx"]))
+    pressure = dp.CenteredGrid(torch.as_tensor(pres).reshape(1, s["ny"], s["nx"], 1))
+    with pytest.raises(dp._native.DpisoError):
+        dp.piso_step(velocity, pressure, pressure, pressure, 0.01, sim, torch.as_tensor(s["dirichlet_values"])[None])

@@ -1,0 +1,137 @@
+"""Pins the CPU oracle against the REFERENCE'S OWN CUDA kernels.
+
+oracle/_ref/libdiffpiso_ref.so is the reference's central_difference_csr_op.cu.cc, laplace_op.cu.cc and
+pressure_solve_op.cu.cc compiled in place for sm_100a (oracle/build.py --ref) behind oracle/ref_shim.cu.  Inputs are
+staged the way diffpiso/piso_tf.py:85-137 and diffpiso/piso_cuda_pressure_solver.py:51-114 stage them.  The outputs are
+also written to gpurun_out/golden_ref/ so that they can be frozen under tests/golden/ (see tests/test_cpu_golden.py).
+The BiCGStab launcher cannot be built against CUDA 12.9 (cuSPARSE csrsv2 / CsrmvEx / csr2csc are gone), so the
+predictor stays pinned only by the oracle's generic ILU(0)/BiCGStab restatement.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from common import SMALL_SETUPS, random_fields, rel_l2
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref", "libdiffpiso_ref.so")
+OUT = os.path.join(ROOT, "gpurun_out", "golden_ref")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    if not os.path.exists(REF):
+        pytest.skip("oracle/_ref not built (python oracle/build.py --ref needs /root/reference)")
+    lib = C.CDLL(REF)
+    os.makedirs(OUT, exist_ok=True)
+    return lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def ref_assemble(lib, s, vel):
+    ny, nx = s["ny"], s["nx"]
+    n_u, n_v, z_u, z_v = O.sizes(ny, nx, s["per_x"], s["per_y"])
+    u, v = vel[:n_u].reshape(ny, nx + 1), vel[n_u:].reshape(ny + 1, nx)
+    up, vp = O.pad_velocity(ny, nx, s["per_x"], s["per_y"], u, v)
+    padded = np.concatenate([up.ravel(), vp.ravel()]).astype(np.float32)          # flatten(..., coord_flip=True)
+    dx64 = np.array([s["dy"], s["dx"]], np.float64)                               # velocity.dx = (dy, dx)
+    grid_spacing = dx64[::-1].astype(np.float32)                                  # piso_tf.py:96
+    cell_area = (np.prod(dx64) / dx64[::-1].astype(np.float32)).astype(np.float32)  # piso_tf.py:97
+    dims4 = np.array([nx + 1, ny, nx, ny + 1], np.int32)                          # piso_tf.py:99
+    beta = np.float32(np.prod(dx64) / s["dt"])
+    visc = np.ascontiguousarray(np.atleast_1d(s["visc"]), np.float32)
+    values, a_diag = np.zeros(z_u + z_v, np.float32), np.zeros(n_u + n_v, np.float32)
+    col_ind, row_ptr = np.zeros(z_u + z_v, np.int32), np.zeros(n_u + n_v + 2, np.int32)
+    per = np.array([s["per_x"], s["per_y"]], np.uint8)
+    f = lib.ref_assemble
+    f.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                  C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float] + [C.c_void_p] * 4
+    rc = f(padded.size, _p(padded), n_u, n_v, z_u + z_v, _p(np.ascontiguousarray(s["dirichlet"], np.uint8)),
+           (ny + 2) * (nx + 2), _p(np.ascontiguousarray(s["active"], np.float32)),
+           _p(np.ascontiguousarray(s["access"], np.float32)), _p(visc), visc.size, _p(dims4), _p(cell_area),
+           _p(grid_spacing), _p(np.ascontiguousarray(s["noslip"], np.uint8)), _p(per), float(beta), _p(values), _p(col_ind),
+           _p(row_ptr), _p(a_diag))
+    assert rc == 0
+    return values, col_ind, row_ptr, a_diag, float(beta), cell_area, grid_spacing
+
+
+@pytest.mark.parametrize("name", list(SMALL_SETUPS))
+def test_oracle_assembly_equals_reference_kernels(ref, name):
+    """row_ptr / col_ind bit-exact; matrix values and the diagonal A bit-exact when the reference's fp32 cell_area
+    equals the fp32 spacing the oracle uses (it does for these grids), otherwise within 1 ulp."""
+    s = SMALL_SETUPS[name]()
+    vel, _ = random_fields(s, 91)
+    values, col_ind, row_ptr, a_diag, beta, cell_area, grid_spacing = ref_assemble(ref, s, vel)
+    ny, nx = s["ny"], s["nx"]
+    n_u = ny * (nx + 1)
+    orp, oci = O.csr_structure(ny, nx, s["per_x"], s["per_y"])
+    assert np.array_equal(row_ptr, orp)
+    assert np.array_equal(col_ind, oci)
+    up, vp = O.pad_velocity(ny, nx, s["per_x"], s["per_y"], vel[:n_u].reshape(ny, nx + 1), vel[n_u:].reshape(ny + 1, nx))
+    ov, oa = O.assemble(ny, nx, s["per_x"], s["per_y"], s["dy"], s["dx"], beta, up, vp, s["dirichlet"], s["active"],
+                        s["noslip"], s["visc"], orp)
+    same_consts = cell_area[0] == np.float32(s["dy"]) and cell_area[1] == np.float32(s["dx"])
+    if same_consts:
+        assert np.array_equal(values, ov) and np.array_equal(a_diag, oa)
+    else:
+        assert np.allclose(values, ov, rtol=3e-7, atol=1e-9) and np.allclose(a_diag, oa, rtol=3e-7, atol=1e-9)
+    np.savez_compressed(os.path.join(OUT, "assemble_%s.npz" % name), vel=vel, values=values, col_ind=col_ind,
+                        row_ptr=row_ptr, a_diag=a_diag, beta=np.float32(beta), cell_area=cell_area,
+                        grid_spacing=grid_spacing)
+
+
+def ref_pressure(lib, s, k_vu, div, fp64, tol):
+    ny, nx = s["ny"], s["nx"]
+    T = np.float64 if fp64 else np.float32
+    lap, x, it = np.zeros(5 * ny * nx, T), np.zeros(ny * nx, T), np.zeros(1, np.int32)
+    per = np.array([s["per_x"], s["per_y"]], np.uint8)
+    f = lib.ref_pressure_solve
+    f.argtypes = [C.c_int] * 4 + [C.c_void_p] * 4 + [C.c_float, C.c_int, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 3
+    rc = f(int(fp64), nx, ny, 1, _p(np.ascontiguousarray(s["active"], np.float32)),
+           _p(np.ascontiguousarray(s["access"], np.float32)), _p(np.ascontiguousarray(k_vu, np.float32)),
+           _p(np.ascontiguousarray(div, T)), tol, s["cg_max_it"], _p(per), int(s["rank_deficient"]), s["cg_reset"], _p(lap),
+           _p(x), _p(it))
+    assert rc == 0
+    return lap, x, int(it[0])
+
+
+@pytest.mark.parametrize("name", ["ldc8", "ldc32", "periodic16", "periodic24x20", "periodic32", "tml16x24", "sml16x48"])
+@pytest.mark.parametrize("fp64", [True, False])
+def test_oracle_pressure_solve_equals_reference_kernels(ref, name, fp64):
+    """Laplace matrix bit-exact; CG iteration count identical (the quantised cadence of SURVEY Q2 is reproduced by the
+    reference itself) and the solution within 1e-9 (fp64) relative L2 -- cuBLAS reductions associate differently."""
+    s = SMALL_SETUPS[name]()
+    ny, nx = s["ny"], s["nx"]
+    n_u, n_v = ny * (nx + 1), (ny + 1) * nx
+    rng = np.random.RandomState(17)
+    a_diag = (-rng.rand(n_u + n_v) * 0.5).astype(np.float32)
+    beta = np.float32(s["dy"] * s["dx"] / s["dt"])
+    k_uv = ((np.float32(1.0) / (beta - a_diag)) * np.float32(s["dx"] / s["dy"])).astype(np.float32)
+    k_vu = np.concatenate([k_uv[n_u:], k_uv[:n_u]])
+    div = (rng.randn(ny * nx) * 0.1).astype(np.float32)
+    if s["rank_deficient"]:
+        act = s["active"].reshape(ny + 2, nx + 2)[1:-1, 1:-1].ravel() != 0
+        div[~act] = 0
+        div[act] -= div[act].mean()
+    tol = s["cg_tol"] if fp64 else 1e-4
+    lap, x, it = ref_pressure(ref, s, k_vu, div, fp64, tol)
+    T = np.float64 if fp64 else np.float32
+    olap = O.laplace(ny, nx, s["active"], s["access"], k_vu, T)
+    assert np.array_equal(lap, olap)
+    ox, oit = O.pressure_cg(ny, nx, s["per_x"], s["per_y"], olap, div.astype(T), tol, s["cg_max_it"], s["cg_reset"],
+                            s["rank_deficient"])
+    if fp64:
+        assert it == oit, (name, it, oit)
+        assert rel_l2(ox, x) < 1e-7, rel_l2(ox, x)
+    else:
+        assert abs(it - oit) <= 10, (name, it, oit)
+        assert rel_l2(ox, x) < 5e-3, rel_l2(ox, x)
+    np.savez_compressed(os.path.join(OUT, "pressure_%s_%s.npz" % (name, "f64" if fp64 else "f32")), k_vu=k_vu, div=div,
+                        lap=lap, x=x, iterations=np.int32(it), tol=np.float32(tol))
