@@ -43,7 +43,8 @@ __global__ void csr_structure_kernel(int ny, int nx, int per_x, int per_y, int n
         if (k == 4 || L.has[k]) ci[L.rp + L.slot[k]] = L.col[k];
 }
 
-__global__ void assemble_kernel(int batch, Grid g, float dy, float dx, float beta, const float *__restrict__ vel,
+__global__ void assemble_kernel(int batch, Grid g, float dy, float dx, float area_x, float area_y, float beta,
+                                const float *__restrict__ vel,
                                 const uint8_t *__restrict__ dirichlet, const float *__restrict__ active,
                                 const uint8_t *__restrict__ noslip, const float *__restrict__ visc, int visc_mode,
                                 float *__restrict__ values, float *__restrict__ a_diag) {
@@ -57,7 +58,8 @@ __global__ void assemble_kernel(int batch, Grid g, float dy, float dx, float bet
     const float *visc_c = visc;
     if (visc_mode == 1) visc_c = visc + face_off;
     else if (visc_mode == 2) visc_c = visc + (size_t)b * nf + face_off;
-    assemble_row(comp, row, g.ny, g.nx, g.per_x, g.per_y, dy, dx, beta, vel + (size_t)b * nf, dirichlet + face_off,
+    assemble_row(comp, row, g.ny, g.nx, g.per_x, g.per_y, dy, dx, area_x, area_y, beta, vel + (size_t)b * nf,
+                 dirichlet + face_off,
                  active, noslip, visc_c, visc_mode != 0, values + (size_t)b * g.nnz() + (comp ? g.nnz_u : 0),
                  a_diag + (size_t)b * nf + face_off);
 }
@@ -233,7 +235,8 @@ int dpiso_csr_structure(int ny, int nx, int per_x, int per_y, int *row_ptr, int 
     return DPISO_OK;
 }
 
-int dpiso_assemble(int batch, int ny, int nx, int per_x, int per_y, float dy, float dx, float beta, const float *vel,
+int dpiso_assemble(int batch, int ny, int nx, int per_x, int per_y, float dy, float dx, float area_x, float area_y,
+                   float beta, const float *vel,
                    const uint8_t *dirichlet, const float *active, const uint8_t *noslip, const float *visc,
                    int visc_mode, float *values, float *a_diag, void *stream) {
     if (int rc = check_grid(batch, ny, nx)) return rc;
@@ -241,7 +244,7 @@ int dpiso_assemble(int batch, int ny, int nx, int per_x, int per_y, float dy, fl
     DPISO_REQUIRE(visc_mode >= 0 && visc_mode <= 2, "visc_mode must be 0, 1 or 2");
     const Grid g = make_grid(ny, nx, per_x, per_y);
     assemble_kernel<<<blocks_for((long long)batch * g.nf()), kThreads, 0, (cudaStream_t)stream>>>(
-        batch, g, dy, dx, beta, vel, dirichlet, active, noslip, visc, visc_mode, values, a_diag);
+        batch, g, dy, dx, area_x, area_y, beta, vel, dirichlet, active, noslip, visc, visc_mode, values, a_diag);
     DPISO_CHECK_LAUNCH();
     return DPISO_OK;
 }

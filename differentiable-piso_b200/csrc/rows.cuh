@@ -48,8 +48,8 @@ DPISO_HD float flux(float a, float b, float cell_area) {
 // ---- one row of the advection-diffusion matrix (calcAdvetionMatrixX/Y, ":148-453") ----------------------------
 // vel: this sample's flat [u, v]; values/a_diag: this component's output blocks of this sample.
 // dirichlet/visc point at this component's block (visc_stride 0 = scalar).
-DPISO_HD void assemble_row(int comp, int row, int ny, int nx, int per_x, int per_y, float dy, float dx, float beta,
-                           const float *vel, const uint8_t *dirichlet_c, const float *active,
+DPISO_HD void assemble_row(int comp, int row, int ny, int nx, int per_x, int per_y, float dy, float dx, float area_x,
+                           float area_y, float beta, const float *vel, const uint8_t *dirichlet_c, const float *active,
                            const uint8_t *noslip, const float *visc_c, int visc_is_field, float *values_c,
                            float *a_diag_c) {
     const CompDims cd = comp_dims(ny, nx, comp);
@@ -63,7 +63,7 @@ DPISO_HD void assemble_row(int comp, int row, int ny, int nx, int per_x, int per
         return;
     }
     const float *u = vel, *v = vel + ny * (nx + 1);
-    const float cell_area[2] = {dy, dx};                     // piso_tf.py:97
+    const float cell_area[2] = {area_x, area_y};             // piso_tf.py:97: prod(dx) / (dx, dy) ~ (dy, dx)
     const float spacing[2] = {dx, dy};                       // piso_tf.py:96
     float F[4];
     if (comp == 0) {       // calcCellFluxesX (":35-69"); padded location (ly+1, lx+1)

@@ -42,7 +42,7 @@ _SIGS = {
     "dpiso_last_error": ([], C.c_char_p),
     "dpiso_sizes": ([_I, _I, _I, _I, _P, _P], _I),
     "dpiso_csr_structure": ([_I, _I, _I, _I, _P, _P, _P], _I),
-    "dpiso_assemble": ([_I, _I, _I, _I, _I, _F, _F, _F, _P, _P, _P, _P, _P, _I, _P, _P, _P], _I),
+    "dpiso_assemble": ([_I, _I, _I, _I, _I, _F, _F, _F, _F, _F, _P, _P, _P, _P, _P, _I, _P, _P, _P], _I),
     "dpiso_predictor_rhs": ([_I, _I, _I, _F, _F, _F, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P], _I),
     "dpiso_fv_gradient": ([_I, _I, _I, _F, _F, _P, _P, _P, _P, _P], _I),
     "dpiso_fv_divergence": ([_I, _I, _I, _F, _F, _P, _P, _F, _P, _P], _I),

@@ -64,8 +64,16 @@ def _f32(t):
     return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.to(torch.float32).contiguous()
 
 
-def assemble(g, vel, dirichlet_u8, active, noslip_u8, visc, dy, dx, beta):
+def cell_areas(dy64, dx64):
+    """The op's `cell_area` input (piso_tf.py:97): prod(dx) / dx[::-1].astype(float32), rounded to fp32 ->
+    (area of a face normal to x, area of a face normal to y)."""
+    prod = float(dy64) * float(dx64)
+    return float(np.float32(prod / float(np.float32(dx64)))), float(np.float32(prod / float(np.float32(dy64))))
+
+
+def assemble(g, vel, dirichlet_u8, active, noslip_u8, visc, dy, dx, beta, areas=None):
     """-> values [B, nnz], a_diag [B, nf]   (advection_matrix_cuda, diffpiso/piso_tf.py:85-137)"""
+    area_x, area_y = cell_areas(dy, dx) if areas is None else areas
     vel = _f32(vel)
     b = vel.shape[0]
     visc = _f32(visc).reshape(-1) if visc.dim() < 2 else _f32(visc)
@@ -81,7 +89,7 @@ def assemble(g, vel, dirichlet_u8, active, noslip_u8, visc, dy, dx, beta):
         raise ValueError("viscosity must be a scalar or a flat [u, v] face field")
     values = torch.empty((b, g.nnz), dtype=torch.float32, device=vel.device)
     a_diag = torch.empty((b, g.nf), dtype=torch.float32, device=vel.device)
-    N.check(N.lib.dpiso_assemble(b, g.ny, g.nx, int(g.per_x), int(g.per_y), dy, dx, beta, N.ptr(vel), N.ptr(dirichlet_u8),
+    N.check(N.lib.dpiso_assemble(b, g.ny, g.nx, int(g.per_x), int(g.per_y), dy, dx, area_x, area_y, beta, N.ptr(vel), N.ptr(dirichlet_u8),
                                  N.ptr(active), N.ptr(noslip_u8), N.ptr(visc), mode, N.ptr(values), N.ptr(a_diag),
                                  N.stream()), "dpiso_assemble")
     return values, a_diag

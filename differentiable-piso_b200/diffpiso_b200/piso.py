@@ -46,7 +46,7 @@ def pressure_extrapolation(boundaries):
 
 class _Ctx(object):
     """Host-side constants of one step."""
-    __slots__ = ("g", "m", "dy", "dx", "beta", "prod", "dx_factor", "pbc", "pbc_inc", "sim", "unrolling_step")
+    __slots__ = ("g", "m", "dy", "dx", "areas", "beta", "prod", "dx_factor", "pbc", "pbc_inc", "sim", "unrolling_step")
 
 
 def _linear_solve(c, values_neg, rhs, x0, transpose, unrolling_step):
@@ -80,7 +80,7 @@ class _PisoStepFn(torch.autograd.Function):
         g, m = c.g, c.m
         vel, pres = vel.contiguous(), pres.contiguous()
         # advection matrices (piso_tf.py:29-33)
-        values, a_diag = ops.assemble(g, vel, m["dirichlet"], m["active"], m["noslip"], visc, c.dy, c.dx, c.beta)
+        values, a_diag = ops.assemble(g, vel, m["dirichlet"], m["active"], m["noslip"], visc, c.dy, c.dx, c.beta, c.areas)
         # predictor (piso_tf.py:36-47)
         rhs = ops.predictor_rhs(g, vel, pres, m["access"], m["dirichlet"], dvals, forcing, c.dy, c.dx, c.beta, c.pbc)
         values_neg = torch.neg(values)
@@ -166,6 +166,7 @@ def make_step_context(velocity, pressure, pressure_inc, dt, simulation_physics, 
     dy64, dx64 = float(velocity.dx[0]), float(velocity.dx[1])
     c.dy, c.dx = float(np.float32(dy64)), float(np.float32(dx64))
     prod = dy64 * dx64
+    c.areas = ops.cell_areas(dy64, dx64)                               # piso_tf.py:97
     c.prod = float(np.float32(float(np.float32(dy64)) * float(np.float32(dx64))))   # as the kernels form it
     c.beta = float(np.float32(prod / float(dt)))                       # piso_tf.py:26
     c.dx_factor = float(np.float32(prod / (dy64 * dy64)))              # piso_tf.py:53 (dx[0] = dy)
@@ -223,7 +224,7 @@ def advection_matrix_cuda(velocity, simulation_physics, viscosity, beta, unrolli
     visc = as_tensor(viscosity).to(velocity.flat.device)
     values, a_flat = ops.assemble(g, velocity.flat, m["dirichlet"], m["active"], m["noslip"], visc,
                                   float(np.float32(velocity.dx[0])), float(np.float32(velocity.dx[1])),
-                                  float(np.float32(beta)))
+                                  float(np.float32(beta)), ops.cell_areas(velocity.dx[0], velocity.dx[1]))
     rp, ci = g.csr_structure()
     return values, rp, ci, stagger_flattened_data(a_flat, velocity.staggered_shape, True), \
         np.array([g.nnz_u, g.nnz_v]), a_flat

@@ -239,3 +239,24 @@ def taylor_green(ny, nx, length=2 * math.pi, t=0.0, visc=0.1):
     u = np.cos(xu) * np.sin(yu) * decay
     v = -np.sin(xv) * np.cos(yv) * decay
     return np.concatenate([u.ravel(), v.ravel()]).astype(np.float32)
+
+
+def wall_bounded_field(ny, nx, ly, lx, seed=1234, modes=3, umax=1.0):
+    """Divergence-free field for a channel that is periodic in x with impermeable walls in y: discrete curl of a
+    stream function that vanishes on both walls (v = 0 on the wall faces, zero net flux).  Flat [u, v] float32."""
+    rng = np.random.RandomState(seed)
+    dy, dx = ly / ny, lx / nx
+    X, Y = np.meshgrid(np.arange(nx + 1) * dx, np.arange(ny + 1) * dy)
+    psi = np.zeros((ny + 1, nx + 1))
+    for m in range(1, modes + 1):
+        for n in range(1, modes + 1):
+            a = rng.randn() / (m * m + n * n)
+            ph = rng.uniform(0, 2 * math.pi)
+            psi += a * np.sin(2 * math.pi * m * X / lx + ph) * np.sin(math.pi * n * Y / ly)
+    psi[0, :] = 0.0
+    psi[-1, :] = 0.0
+    psi[:, -1] = psi[:, 0]
+    u = (psi[1:, :] - psi[:-1, :]) / dy
+    v = -(psi[:, 1:] - psi[:, :-1]) / dx
+    scale = umax / max(np.abs(u).max(), np.abs(v).max())
+    return np.concatenate([(u * scale).ravel(), (v * scale).ravel()]).astype(np.float32)

@@ -57,11 +57,13 @@ int dpiso_csr_structure(int ny, int nx, int per_x, int per_y, int *row_ptr, int 
 
 /* ---- advection-diffusion matrices (custom_padded + CentralDifferenceMatrixCsr) -------------------
  * vel [batch][nf] unpadded; the padding of piso_helpers.py:35-55 is applied on the fly.
+ * dy, dx = grid_spacing (y, x); area_x, area_y = the op's cell_area input = prod(dx)/(dx, dy) as fp32 (piso_tf.py:96-97),
+ * i.e. the area of a face normal to x (~dy) and normal to y (~dx).
  * dirichlet uint8 [nf]; active float [(ny+2)(nx+2)]; noslip uint8 [(ny+2)(nx+2)];
  * visc: visc_mode 0 = scalar (1 float), 1 = face field [nf] shared, 2 = face field [batch][nf].
  * outputs: values [batch][nnz] (centre = diag - beta), a_diag [batch][nf]. */
-int dpiso_assemble(int batch, int ny, int nx, int per_x, int per_y, float dy, float dx, float beta,
-                   const float *vel, const uint8_t *dirichlet, const float *active, const uint8_t *noslip,
+int dpiso_assemble(int batch, int ny, int nx, int per_x, int per_y, float dy, float dx, float area_x, float area_y,
+                   float beta, const float *vel, const uint8_t *dirichlet, const float *active, const uint8_t *noslip,
                    const float *visc, int visc_mode, float *values, float *a_diag, void *stream);
 
 /* ---- pointwise pieces of piso_step (forward) ------------------------------------------------------ */

@@ -67,7 +67,13 @@ def pad_velocity(ny, nx, per_x, per_y, u, v):
     return up, vp
 
 
-def assemble(ny, nx, per_x, per_y, dy, dx, beta, up, vp, dirichlet, active, noslip, visc, row_ptr):
+def cell_areas(dy, dx):
+    """cell_area op input (diffpiso/piso_tf.py:97): prod(dx) / dx[::-1].astype(float32) -> fp32"""
+    prod = float(dy) * float(dx)
+    return float(np.float32(prod / float(np.float32(dx)))), float(np.float32(prod / float(np.float32(dy))))
+
+
+def assemble(ny, nx, per_x, per_y, dy, dx, beta, up, vp, dirichlet, active, noslip, visc, row_ptr, areas=None):
     n_u, n_v, z_u, z_v = sizes(ny, nx, per_x, per_y)
     up, vp, active, visc = _f32(up), _f32(vp), _f32(active).ravel(), _f32(np.atleast_1d(visc)).ravel()
     dirichlet, noslip, row_ptr = _u8(dirichlet).ravel(), _u8(noslip).ravel(), _i32(row_ptr)
@@ -76,8 +82,9 @@ def assemble(ny, nx, per_x, per_y, dy, dx, beta, up, vp, dirichlet, active, nosl
     values = np.zeros(z_u + z_v, np.float32)
     a_diag = np.zeros(n_u + n_v, np.float32)
     f = lib().orc_assemble
-    f.argtypes = [C.c_int] * 4 + [C.c_float] * 3 + [C.c_void_p] * 6 + [C.c_int] + [C.c_void_p] * 3
-    rc = f(ny, nx, int(per_x), int(per_y), dy, dx, beta, up.ctypes.data, vp.ctypes.data, dirichlet.ctypes.data,
+    f.argtypes = [C.c_int] * 4 + [C.c_float] * 5 + [C.c_void_p] * 6 + [C.c_int] + [C.c_void_p] * 3
+    area_x, area_y = cell_areas(dy, dx) if areas is None else areas
+    rc = f(ny, nx, int(per_x), int(per_y), dy, dx, area_x, area_y, beta, up.ctypes.data, vp.ctypes.data, dirichlet.ctypes.data,
            active.ctypes.data, noslip.ctypes.data, visc.ctypes.data, int(visc.size > 1), row_ptr.ctypes.data,
            values.ctypes.data, a_diag.ctypes.data)
     assert rc == 0
@@ -220,7 +227,8 @@ def piso_step(setup, vel, pres, forcing=None, dirichlet_values=None, full_output
                   [int(visc.size > 1), s["bicg_max_it"], s["cg_max_it"], s["cg_reset"], int(s["rank_deficient"]),
                    int(s.get("cg_fp64", True))], np.int32)
     c = step_constants(s["dy"], s["dx"], s["dt"])
-    fp = np.array([s["dy"], s["dx"], s["dt"], s["bicg_tol"], s["cg_tol"], c["beta"], c["prod"], c["dx_factor"]],
+    ax, ay = cell_areas(s["dy"], s["dx"])
+    fp = np.array([s["dy"], s["dx"], s["dt"], s["bicg_tol"], s["cg_tol"], c["beta"], c["prod"], c["dx_factor"], ax, ay],
                   np.float32)
     vel, pres = _f32(vel).ravel(), _f32(pres).ravel()
     assert vel.size == nf and pres.size == nc

@@ -169,7 +169,7 @@ void orc_pad_velocity(int ny, int nx, int per_x, int per_y, const float *u, cons
 /* ------------------------------------------------------------------------------------------
  * advection-diffusion matrix values -- CUDAsrc/central_difference_csr_op.cu.cc:148-453
  * ---------------------------------------------------------------------------------------- */
-int orc_assemble(int ny, int nx, int per_x, int per_y, float dy, float dx, float beta,
+int orc_assemble(int ny, int nx, int per_x, int per_y, float dy, float dx, float area_x, float area_y, float beta,
                  const float *up, const float *vp, const uint8_t *dirichlet /* n_u+n_v */,
                  const float *active /* (ny+2)(nx+2) */, const uint8_t *noslip /* (ny+2)(nx+2) */,
                  const float *visc, int visc_is_field,
@@ -177,7 +177,7 @@ int orc_assemble(int ny, int nx, int per_x, int per_y, float dy, float dx, float
     int n[2], nnz[2];
     if (orc_sizes(ny, nx, per_x, per_y, n, nnz)) return ORC_EBADGRID;
     const int per[2] = { per_x, per_y };
-    const float cell_area[2] = { dy, dx };     /* piso_tf.py:97  */
+    const float cell_area[2] = { area_x, area_y };   /* piso_tf.py:97: prod(dx)/(dx, dy) as fp32, ~ (dy, dx) */
     const float spacing[2] = { dx, dy };       /* piso_tf.py:96  */
     const int wu = nx + 3, wv = nx + 2, wm = nx + 2;
     memset(values, 0, sizeof(float) * (size_t)(nnz[0] + nnz[1]));  /* initWithZeros, ":627" */
@@ -569,7 +569,7 @@ void orc_h_apply(int n, const int *rp, const int *ci, const float *val, const fl
  * iparams: [0]=ny [1]=nx [2]=per_y [3]=per_x [4..7]=pbc of pressure (y_lo,y_hi,x_lo,x_hi)
  *          [8..11]=pbc of the pressure increments [12]=visc_is_field [13]=bicg max_it
  *          [14]=cg max_it [15]=cg residual_reset [16]=rank_deficient [17]=cg fp64 (1) / fp32 (0)
- * fparams: [0]=dy [1]=dx [2]=dt [3]=bicg tol [4]=cg accuracy [5]=beta [6]=unused [7]=dx_factor
+ * fparams: [0]=dy [1]=dx [2]=dt [3]=bicg tol [4]=cg accuracy [5]=beta [6]=unused [7]=dx_factor [8]=cell_area x [9]=cell_area y
  *          ([5..7] are the fp32 graph constants the Python side forms in fp64, piso_tf.py:26,53; 0 = derive here)
  * out_stats (int[12]): [0..3] u solve stats, [4..7] v solve stats, [8] cg1 its, [9] cg2 its
  * optional outputs may be NULL.
@@ -610,7 +610,8 @@ int orc_piso_step(const int *ip, const float *fp, const float *vel, const float 
     /* advection matrices (piso_tf.py:29-33) */
     orc_csr_structure(ny, nx, per_x, per_y, row_ptr, col_ind);
     orc_pad_velocity(ny, nx, per_x, per_y, vel, vel + n[0], up, vp);
-    orc_assemble(ny, nx, per_x, per_y, dy, dx, beta, up, vp, dirichlet, active, noslip, visc, ip[12],
+    orc_assemble(ny, nx, per_x, per_y, dy, dx, fp[8] != 0.0f ? fp[8] : dy, fp[8] != 0.0f ? fp[9] : dx, beta, up, vp,
+                 dirichlet, active, noslip, visc, ip[12],
                  row_ptr, values, a_diag);
 
     /* predictor rhs (piso_tf.py:36-40, piso_helpers.py:169-172) */

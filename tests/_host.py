@@ -36,14 +36,16 @@ def csr_structure(ny, nx, per_x, per_y, n_u, n_v, nnz):
     return rp, ci
 
 
-def assemble(ny, nx, per_x, per_y, dy, dx, beta, vel, dirichlet, active, noslip, visc, nnz):
+def assemble(ny, nx, per_x, per_y, dy, dx, beta, vel, dirichlet, active, noslip, visc, nnz, areas=None):
+    from oracle import oracle as O
+    area_x, area_y = O.cell_areas(dy, dx) if areas is None else areas
     vel = np.ascontiguousarray(vel, np.float32)
     visc = np.ascontiguousarray(np.atleast_1d(visc), np.float32).ravel()
     values = np.zeros(nnz, np.float32)
     a_diag = np.zeros(vel.size, np.float32)
     f = lib().hs_assemble
-    f.argtypes = [C.c_int] * 4 + [C.c_float] * 3 + [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 2
-    f(ny, nx, int(per_x), int(per_y), dy, dx, beta, _p(vel), _p(np.ascontiguousarray(dirichlet, np.uint8)),
+    f.argtypes = [C.c_int] * 4 + [C.c_float] * 5 + [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 2
+    f(ny, nx, int(per_x), int(per_y), dy, dx, area_x, area_y, beta, _p(vel), _p(np.ascontiguousarray(dirichlet, np.uint8)),
       _p(np.ascontiguousarray(active, np.float32)), _p(np.ascontiguousarray(noslip, np.uint8)), _p(visc),
       int(visc.size > 1), _p(values), _p(a_diag))
     return values, a_diag

