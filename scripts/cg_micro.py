@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--nx", type=int, default=128)
     ap.add_argument("--fp32", action="store_true")
     ap.add_argument("--max-it", type=int, default=10000)
+    ap.add_argument("--check", type=int, default=0, help="compare the first N samples with the CPU oracle")
     args = ap.parse_args()
     from diffpiso_b200 import ops, setups as SU
     from diffpiso_b200 import _native as N
@@ -58,9 +59,20 @@ def main():
         times.append(e0.elapsed_time(e1))
     its = its.cpu().numpy()
     ms = float(np.median(times))
+    check = None
+    if args.check:
+        from oracle import oracle as O
+        lap_h, div_h, x_h = lap.cpu().numpy(), div.cpu().numpy(), x.cpu().numpy()
+        check = []
+        for i in range(args.check):
+            ox, oit = O.pressure_cg(args.ny, args.nx, True, True, lap_h[i].ravel(), div_h[i].astype(lap_h.dtype), tol,
+                                    args.max_it, 1000, True)
+            rel = float(np.linalg.norm(x_h[i] - ox) / np.linalg.norm(ox))
+            check.append({"gpu_it": int(its[i]), "oracle_it": int(oit), "rel_l2": rel})
     print(json.dumps({"ms": ms, "mean_it": float(its.mean()), "max_it": int(its.max()), "min_it": int(its.min()),
                       "us_per_iteration_whole_batch": 1e3 * ms / float(its.mean()), "config": ops.pressure_cg_config(),
-                      "batch": args.batch, "grid": [args.ny, args.nx], "finite": bool(torch.isfinite(x).all())}))
+                      "batch": args.batch, "grid": [args.ny, args.nx], "finite": bool(torch.isfinite(x).all()),
+                      "its_hist": np.unique(its, return_counts=True)[0].tolist(), "check": check}))
 
 
 if __name__ == "__main__":
