@@ -36,6 +36,17 @@ SMALL_SETUPS = {
     "tml16x24": lambda: SU.temporal_mixing_layer(ny=16, nx=24, visc=2e-3, dt=0.05),
     "sml16x48": lambda: SU.spatial_mixing_layer(ny=16, nx=48, box=(8.0, 24.0), dt=0.05, solver_precision=1e-6),
 }
+# grids that take the strip-layout fast path of the pressure CG (rows per CTA = 8*G, G*nx threads in {256, 512})
+STRIP_SETUPS = {
+    "periodic64": lambda: SU.periodic_box(64, 64, visc=1e-3),                      # 1 CTA, 512 threads
+    "periodic128": lambda: SU.periodic_box(128, 128, visc=1e-3),                   # cluster of 4, 512 threads
+    "periodic64x32": lambda: SU.periodic_box(64, 32, visc=1e-2, cg_reset=10),       # 1 CTA, 256 threads, frequent resets
+    "tml64x128": lambda: SU.temporal_mixing_layer(ny=64, nx=128, visc=2e-3, dt=0.05),   # cluster of 2, walls in y
+    "sml32x128": lambda: SU.spatial_mixing_layer(ny=32, nx=128, box=(16.0, 64.0), dt=0.05, solver_precision=1e-6),
+    "ldc_like64": lambda: SU.lid_driven_cavity(n=64, re=100.0, dt=0.01, cg_reset=1000, cg_max_it=5000),  # 65 x 64: general path, cluster 2
+}
+ALL_SETUPS = dict(SMALL_SETUPS)
+ALL_SETUPS.update(STRIP_SETUPS)
 
 
 def pressure_problem(setup, seed):

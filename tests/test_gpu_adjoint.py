@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from common import SMALL_SETUPS, random_fields, rel_l2
+from common import ALL_SETUPS, SMALL_SETUPS, random_fields, rel_l2
 from oracle import adjoint as A
 from oracle import oracle as O
 from test_gpu_piso_step import DEV, build_sim, extrap
@@ -81,13 +81,13 @@ def test_nonperiodic_adjoints_are_exact_transposes(name):
     assert abs(lhs - rhs) < 1e-5 * abs(lhs) + 1e-7
 
 
-@pytest.mark.parametrize("name", ["periodic16", "periodic24x20", "tml16x24", "sml16x48", "ldc8"])
+@pytest.mark.parametrize("name", ["periodic16", "periodic24x20", "tml16x24", "sml16x48", "ldc8", "periodic64"])
 def test_piso_step_backward_matches_oracle(name):
     """loss = <w_u, u_next> + <w_p, p_next>; gradients w.r.t. velocity, pressure, forcing and Dirichlet values from
     torch.autograd through piso_step against oracle/adjoint.py: 1e-4 relative L2 (three nested iterative solves at the
     same tolerance on both sides)."""
     import diffpiso_b200 as dp
-    s = SMALL_SETUPS[name]()
+    s = ALL_SETUPS[name]()
     sim = build_sim(s)
     ny, nx = s["ny"], s["nx"]
     nf, nc = ny * (nx + 1) + (ny + 1) * nx, ny * nx
@@ -122,6 +122,7 @@ def test_piso_step_backward_matches_oracle(name):
         assert rel_l2(tf.grad[i].cpu().numpy(), ref["g_forcing"]) < 1e-4, (name, i, "forcing")
         gd_total += ref["g_dvals"]
         # the last pressure solve issued by backward is the first-corrector adjoint
-        assert abs(int(sim.pressure_solver.last_iterations[i]) - ref["stats"]["cg_adj"][1]) <= 5
+        oit = ref["stats"]["cg_adj"][1]
+        assert abs(int(sim.pressure_solver.last_iterations[i]) - oit) <= max(2 * min(s["cg_reset"], 10), 0.1 * oit)
     if s["dirichlet"].any():
         assert rel_l2(td.grad[0].cpu().numpy(), gd_total) < 1e-4

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from common import SMALL_SETUPS, random_fields, rel_l2
+from common import ALL_SETUPS, SMALL_SETUPS, random_fields, rel_l2
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -47,12 +47,12 @@ def run_step(s, sim, vel_flat, pres, forcing=None, full_output=False):
                         viscosity_field=visc_field, forcing_term=forcing, full_output=full_output)
 
 
-@pytest.mark.parametrize("name", list(SMALL_SETUPS))
+@pytest.mark.parametrize("name", list(SMALL_SETUPS) + ["periodic64", "tml64x128", "sml32x128"])
 def test_piso_step_matches_oracle(name):
     """Three consecutive steps of a batch of 2 seeded samples; every intermediate of the first step and the state after
     each step within 1e-5 relative L2 of the oracle (north_star tolerance), solver iteration counts within +-1
     (BiCGStab) / one check period (CG)."""
-    s = SMALL_SETUPS[name]()
+    s = ALL_SETUPS[name]()
     sim = build_sim(s)
     states = [random_fields(s, 40 + i) for i in range(2)]
     vel = np.stack([v for v, _ in states])
