@@ -19,7 +19,7 @@
 
 namespace dpiso {
 
-constexpr int kBicgThreads = 1024;
+constexpr int kBicgThreads = 512;
 constexpr int kMaxWa = 6;
 
 struct BicgTab {
@@ -35,6 +35,8 @@ struct BicgParams {
     int n_max;             // max(n_u, n_v): plane stride inside the workspace
     int zs_in_smem;
     size_t ws_floats;      // per system
+    int stage_rows;        // rows per stage buffer (0 = staged fast path disabled)
+    int lp_cap;            // ints reserved for the level_ptr copy in smem
     const float *values, *rhs, *x0;
     float *x;
     int *stats;
@@ -134,87 +136,141 @@ __device__ void wavefront(const BicgTab &T, int n_max, const float *__restrict__
     __syncthreads();
 }
 
-// fast path: at most one row per participating thread and level; the next level's row is prefetched before the
-// barrier so that the critical path of a level is  smem load -> fma chain -> smem store -> bar.sync
+// Fast path: staged wavefront.  Levels are processed in chunks of K consecutive levels.  While the solver threads
+// (the first P = roundup32(max_level) threads) sweep the levels of chunk c out of a shared-memory stage buffer, ALL
+// threads of the CTA prefetch the coefficient rows of chunk c+1 from global memory into registers and drop them into the
+// other stage buffer -- the L2 latency of the coefficient stream is hidden behind the recurrence, and the critical path
+// of a level is  LDS (stage) -> LDS (zs gather) -> fma chain -> STS -> named barrier over the solver warps only.
+// Requires max_level <= blockDim.x and stage_rows >= max_level.
+struct Stage {
+    int *col;      // [kMaxWa][rows]
+    float *val;    // [kMaxWa][rows]
+    float *aux;    // [kMaxWa][rows]  MODE 0: u(col, row);  MODE 1: aux[0][.] = right-hand side
+};
+
 template <int MODE>
-__device__ void wavefront_prefetch(const BicgTab &T, int n_max, const float *__restrict__ values_c, const float *a_val,
-                                   float *lu, const float *in, float *zs) {
-    const int wa = T.wa, n = T.n;
-    const int P = (T.max_level + 31) & ~31;
+__device__ void wavefront_staged(const BicgTab &T, const int *__restrict__ lp /* level_ptr in smem */, int n_max,
+                                 const float *__restrict__ plane_a /* a_val (MODE 0) or lu */,
+                                 const float *__restrict__ plane_rv /* MODE 0: M(col,row) planes */, float *lu,
+                                 const float *in, float *zs, int *stage_mem, int stage_rows) {
+    const int wa = T.wa, n = T.n, nl = T.n_levels;
     const int t = threadIdx.x;
-    __syncthreads();
-    if (t < P) {
-        const int nl = T.n_levels;
-        RowRegs cur, nxt;
-        auto load = [&](RowRegs &R, int s) {
-            int q = -1;
-            if (s < nl) {
-                const int d = MODE == 2 ? nl - 1 - s : s;
-                q = T.level_ptr[d] + t;
-                if (q >= T.level_ptr[d + 1]) q = -1;
+    const int P = (T.max_level + 31) & ~31;
+    const int K = max(1, stage_rows / T.max_level);
+    const int nchunks = (nl + K - 1) / K;
+    Stage st[2];
+    for (int b = 0; b < 2; b++) {
+        int *base = stage_mem + (size_t)b * stage_rows * (3 * kMaxWa);
+        st[b].col = base;
+        st[b].val = (float *)(base + stage_rows * kMaxWa);
+        st[b].aux = (float *)(base + 2 * stage_rows * kMaxWa);
+    }
+    // chunk c covers levels [la, lb) (ascending sweeps) or levels lb-1 .. la (descending sweep, MODE 2)
+    auto chunk_levels = [&](int c, int &la, int &lb) {
+        if (MODE != 2) { la = c * K; lb = min(nl, la + K); }
+        else { lb = nl - c * K; la = max(0, lb - K); }
+    };
+    int reg_col[kMaxWa];
+    float reg_val[kMaxWa], reg_aux[kMaxWa];
+    int reg_q = -1;
+    auto fetch = [&](int c) {            // global -> registers, one row per thread (rows of a chunk <= stage_rows <= NT)
+        reg_q = -1;
+        if (c < nchunks) {
+            int la, lb;
+            chunk_levels(c, la, lb);
+            const int q = lp[la] + t;
+            if (q < lp[lb]) {
+                reg_q = q;
+#pragma unroll
+                for (int k = 0; k < kMaxWa; k++) {
+                    const bool on = k < wa;
+                    reg_col[k] = on ? T.a_col[k * n + q] : -1;
+                    reg_val[k] = on ? plane_a[k * n_max + q] : 0.0f;
+                    if (MODE == 0) reg_aux[k] = on ? plane_rv[k * n_max + q] : 0.0f;
+                }
+                if (MODE == 1) reg_aux[0] = in[q];
             }
-            R.q = q;
-            const float *src_val = MODE == 0 ? a_val : lu;
+        }
+    };
+    auto stash = [&](int c) {            // registers -> stage buffer of chunk c
+        if (reg_q >= 0) {
+            int la, lb;
+            chunk_levels(c, la, lb);
+            const int i = reg_q - lp[la];
+            Stage &S = st[c & 1];
 #pragma unroll
             for (int k = 0; k < kMaxWa; k++) {
-                const bool on = q >= 0 && k < wa;
-                R.col[k] = on ? T.a_col[k * n + q] : -1;
-                R.val[k] = on ? src_val[k * n_max + q] : 0.0f;
-                if (MODE == 0) {
-                    const int rev = on ? T.a_rev[k * n + q] : -1;
-                    R.aux[k] = rev >= 0 ? values_c[rev] : 0.0f;
-                }
+                S.col[k * stage_rows + i] = reg_col[k];
+                S.val[k * stage_rows + i] = reg_val[k];
+                if (MODE == 0) S.aux[k * stage_rows + i] = reg_aux[k];
             }
-            R.rhs = (q >= 0 && MODE == 1) ? in[q] : 0.0f;
-        };
-        load(cur, 0);
-        for (int s = 0; s < nl; s++) {
-            load(nxt, s + 1);
-            const int q = cur.q;
-            if (q >= 0) {
-                if (MODE == 0) {
-                    // pivot = first self entry in column order (padding, also col == q, sits behind the real entries)
-                    float diag = 0.0f;
-                    int dslot = -1;
+            if (MODE == 1) S.aux[i] = reg_aux[0];
+        }
+    };
+    __syncthreads();
+    fetch(0);
+    stash(0);
+    __syncthreads();
+    for (int c = 0; c < nchunks; c++) {
+        fetch(c + 1);                                     // loads in flight while the solver threads sweep chunk c
+        if (t < P) {
+            int la, lb;
+            chunk_levels(c, la, lb);
+            const int q_base = lp[la];
+            const Stage &S = st[c & 1];
+            for (int s = 0; s < lb - la; s++) {
+                const int d = MODE == 2 ? lb - 1 - s : la + s;
+                const int q = lp[d] + t;
+                if (q < lp[d + 1]) {
+                    const int i = q - q_base;
+                    int col[kMaxWa];
+                    float val[kMaxWa];
 #pragma unroll
-                    for (int k = 0; k < kMaxWa; k++)
-                        if (cur.col[k] == q && dslot < 0) { dslot = k; diag = cur.val[k]; }
+                    for (int k = 0; k < kMaxWa; k++) { col[k] = S.col[k * stage_rows + i]; val[k] = S.val[k * stage_rows + i]; }
+                    if (MODE == 0) {
+                        // pivot = first self entry in column order (padding, also col == q, sits behind the real entries)
+                        float diag = 0.0f;
+                        int dslot = -1;
 #pragma unroll
-                    for (int k = 0; k < kMaxWa; k++) {
-                        if (k < wa) {
-                            if (cur.col[k] >= 0 && cur.col[k] < q) {
-                                const float lik = __fdiv_rn(cur.val[k], zs[cur.col[k]]);
-                                lu[k * n_max + q] = lik;
-                                diag = fmaf(-lik, cur.aux[k], diag);
-                            } else if (k != dslot) {
-                                lu[k * n_max + q] = cur.val[k];
+                        for (int k = 0; k < kMaxWa; k++)
+                            if (col[k] == q && dslot < 0) { dslot = k; diag = val[k]; }
+#pragma unroll
+                        for (int k = 0; k < kMaxWa; k++) {
+                            if (k < wa) {
+                                if (col[k] >= 0 && col[k] < q) {
+                                    const float lik = __fdiv_rn(val[k], zs[col[k]]);
+                                    lu[k * n_max + q] = lik;
+                                    diag = fmaf(-lik, S.aux[k * stage_rows + i], diag);
+                                } else if (k != dslot) {
+                                    lu[k * n_max + q] = val[k];   // U entries are unchanged by ILU(0) on this pattern
+                                }
                             }
                         }
-                    }
-                    lu[dslot * n_max + q] = diag;
-                    zs[q] = diag;
-                } else if (MODE == 1) {
-                    float acc = cur.rhs;
+                        lu[dslot * n_max + q] = diag;
+                        zs[q] = diag;
+                    } else if (MODE == 1) {
+                        float acc = S.aux[i];
 #pragma unroll
-                    for (int k = 0; k < kMaxWa; k++)
-                        if (cur.col[k] >= 0 && cur.col[k] < q) acc = fmaf(-cur.val[k], zs[cur.col[k]], acc);
-                    zs[q] = acc;
-                } else {
-                    float acc = zs[q], dg = 1.0f;
-                    bool seen_diag = false;
+                        for (int k = 0; k < kMaxWa; k++)
+                            if (col[k] >= 0 && col[k] < q) acc = fmaf(-val[k], zs[col[k]], acc);
+                        zs[q] = acc;
+                    } else {
+                        float acc = zs[q], dg = 1.0f;
+                        bool seen_diag = false;
 #pragma unroll
-                    for (int k = 0; k < kMaxWa; k++) {
-                        if (cur.col[k] > q) acc = fmaf(-cur.val[k], zs[cur.col[k]], acc);
-                        else if (cur.col[k] == q && !seen_diag) { dg = cur.val[k]; seen_diag = true; }
+                        for (int k = 0; k < kMaxWa; k++) {
+                            if (col[k] > q) acc = fmaf(-val[k], zs[col[k]], acc);
+                            else if (col[k] == q && !seen_diag) { dg = val[k]; seen_diag = true; }
+                        }
+                        zs[q] = __fdiv_rn(acc, dg);
                     }
-                    zs[q] = __fdiv_rn(acc, dg);
                 }
+                named_bar(1, P);
             }
-            named_bar(1, P);
-            cur = nxt;
         }
+        stash(c + 1);
+        __syncthreads();
     }
-    __syncthreads();
 }
 
 __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_kernel(const BicgParams prm) {
@@ -233,11 +289,17 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_kernel(const BicgPar
     float *x_g = prm.x + (size_t)sample * prm.n_face + face_off;
 
     float *ws = prm.workspace + (size_t)sys * prm.ws_floats;
-    float *a_val = ws;                       // [kMaxWa][n_max]
+    float *a_val = ws;                       // [kMaxWa][n_max]  M(row, col)
     float *lu = a_val + (size_t)kMaxWa * n_max;
-    float *b = lu + (size_t)kMaxWa * n_max;
+    float *a_rv = lu + (size_t)kMaxWa * n_max;   // [kMaxWa][n_max]  M(col, row) (0 where absent): ILU(0) pivot updates
+    float *b = a_rv + (size_t)kMaxWa * n_max;
     float *x = b + n_max, *r = x + n_max, *rh = r + n_max, *p = rh + n_max, *v = p + n_max, *tt = v + n_max;
-    float *zs = prm.zs_in_smem ? (float *)smem_raw : tt + n_max;
+    // dynamic smem: [level_ptr copy][stage buffers][zs]
+    int *lp_s = (int *)smem_raw;
+    int *stage_mem = lp_s + prm.lp_cap;
+    float *zs = prm.zs_in_smem ? (float *)(stage_mem + (size_t)2 * prm.stage_rows * 3 * kMaxWa) : tt + n_max;
+    const bool fast = prm.stage_rows > 0;
+    if (fast) for (int i = tid; i <= T.n_levels; i += NT) lp_s[i] = T.level_ptr[i];
 
     // ---- setup: permuted copies, NaN guard (":245-256") ------------------------------------------------------
     double nv = 0.0, nb = 0.0;
@@ -248,22 +310,22 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_kernel(const BicgPar
         b[q] = bq; nb += (double)bq * bq;
         x[q] = x0_g[orig];                                           // cublasScopy(x_old -> x) (":261")
         for (int k = 0; k < wa; k++) {
-            const int src = T.a_src[k * n + q];
+            const int src = T.a_src[k * n + q], rev = T.a_rev[k * n + q];
             a_val[k * n_max + q] = src >= 0 ? values_c[src] : 0.0f;
+            a_rv[k * n_max + q] = rev >= 0 ? values_c[rev] : 0.0f;
         }
     }
     block_sum2(nv, nb, red);
     int warn = (isnan((float)sqrt(nv)) || isnan((float)sqrt(nb))) ? 1 : 0;
 
     // ---- ILU(0) (csrilu02, ":181-218") ---------------------------------------------------------------------
-    const bool fast = ((T.max_level + 31) & ~31) <= NT;
-    if (fast) wavefront_prefetch<0>(T, n_max, values_c, a_val, lu, nullptr, zs);
+    if (fast) wavefront_staged<0>(T, lp_s, n_max, a_val, a_rv, lu, nullptr, zs, stage_mem, prm.stage_rows);
     else wavefront<0>(T, n_max, values_c, a_val, lu, nullptr, zs);
 
     auto precondition = [&](const float *src) {                      // zs = U^-1 L^-1 src   (csrsv2 x2, ":321-327")
         if (fast) {
-            wavefront_prefetch<1>(T, n_max, nullptr, nullptr, lu, src, zs);
-            wavefront_prefetch<2>(T, n_max, nullptr, nullptr, lu, nullptr, zs);
+            wavefront_staged<1>(T, lp_s, n_max, lu, nullptr, nullptr, src, zs, stage_mem, prm.stage_rows);
+            wavefront_staged<2>(T, lp_s, n_max, lu, nullptr, nullptr, nullptr, zs, stage_mem, prm.stage_rows);
         } else {
             wavefront<1>(T, n_max, nullptr, nullptr, lu, src, zs);
             wavefront<2>(T, n_max, nullptr, nullptr, lu, nullptr, zs);
@@ -370,7 +432,7 @@ extern "C" {
 
 size_t dpiso_bicgstab_workspace_floats(const dpiso_bicg_tables *h_tab_u, const dpiso_bicg_tables *h_tab_v) {
     const size_t n_max = (size_t)(h_tab_u->n > h_tab_v->n ? h_tab_u->n : h_tab_v->n);
-    return (2 * (size_t)kMaxWa + 8) * n_max;
+    return (3 * (size_t)kMaxWa + 8) * n_max;
 }
 
 int dpiso_bicgstab_ilu(int batch, const dpiso_bicg_tables *h_tab_u, const dpiso_bicg_tables *h_tab_v, int nnz_u,
@@ -389,12 +451,35 @@ int dpiso_bicgstab_ilu(int batch, const dpiso_bicg_tables *h_tab_u, const dpiso_
     prm.ws_floats = dpiso_bicgstab_workspace_floats(h_tab_u, h_tab_v);
     prm.values = values; prm.rhs = rhs; prm.x0 = x0; prm.x = x; prm.stats = stats; prm.warn = warn;
     prm.workspace = workspace; prm.tol = tol; prm.max_it = max_it;
-    const size_t smem_need = (size_t)prm.n_max * sizeof(float);
-    prm.zs_in_smem = smem_need <= 200 * 1024 ? 1 : 0;
-    const size_t smem = prm.zs_in_smem ? smem_need : 0;
+    // shared memory plan: level_ptr copy + two stage buffers (staged wavefront) + the solve vector zs
+    const size_t kBudget = 200 * 1024;
+    const int max_level = h_tab_u->max_level > h_tab_v->max_level ? h_tab_u->max_level : h_tab_v->max_level;
+    const int n_levels = h_tab_u->n_levels > h_tab_v->n_levels ? h_tab_u->n_levels : h_tab_v->n_levels;
+    prm.lp_cap = (n_levels + 1 + 3) & ~3;
+    const size_t zs_bytes = (size_t)prm.n_max * sizeof(float);
+    const size_t row_bytes = (size_t)2 * 3 * kMaxWa * sizeof(int);      // both stage buffers, per staged row
+    prm.stage_rows = 0;
+    prm.zs_in_smem = 0;
+    size_t smem = 0;
+    if (max_level <= kBicgThreads) {
+        size_t avail = kBudget - prm.lp_cap * sizeof(int);
+        int rows = max_level * 4 < kBicgThreads ? max_level * 4 : kBicgThreads;     // aim at 4 levels per chunk
+        if (rows < max_level) rows = max_level;
+        if (zs_bytes + rows * row_bytes <= avail) prm.zs_in_smem = 1;
+        else if (zs_bytes + max_level * row_bytes <= avail) { prm.zs_in_smem = 1; rows = (int)((avail - zs_bytes) / row_bytes); }
+        if ((size_t)rows * row_bytes <= avail) {
+            prm.stage_rows = rows;
+            smem = prm.lp_cap * sizeof(int) + rows * row_bytes + (prm.zs_in_smem ? zs_bytes : 0);
+        }
+    }
+    if (!prm.stage_rows) {
+        prm.lp_cap = 0;
+        prm.zs_in_smem = zs_bytes <= kBudget ? 1 : 0;
+        smem = prm.zs_in_smem ? zs_bytes : 0;
+    }
     static bool attr_set = false;
     if (!attr_set) {
-        DPISO_CUDA_TRY(cudaFuncSetAttribute(bicgstab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        DPISO_CUDA_TRY(cudaFuncSetAttribute(bicgstab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 1024));
         attr_set = true;
     }
     bicgstab_kernel<<<batch * 2, kBicgThreads, smem, (cudaStream_t)stream>>>(prm);

