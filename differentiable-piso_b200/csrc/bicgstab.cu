@@ -80,7 +80,7 @@ struct RowRegs {
 //   MODE 1: L solve   zs[q] = in[q] - sum_{col<q} lu*zs[col]
 //   MODE 2: U solve   zs[q] = (zs[q] - sum_{col>q} lu*zs[col]) / lu_diag
 template <int MODE>
-__device__ void wavefront(const BicgTab &T, int n_max, const float *__restrict__ values_c, const float *a_val,
+__device__ __noinline__ void wavefront(const BicgTab &T, int n_max, const float *__restrict__ values_c, const float *a_val,
                           float *lu, const float *in, float *zs) {
     const int wa = T.wa, n = T.n;
     const int P = min((int)blockDim.x, (T.max_level + 31) & ~31);
@@ -142,29 +142,25 @@ __device__ void wavefront(const BicgTab &T, int n_max, const float *__restrict__
 // other stage buffer -- the L2 latency of the coefficient stream is hidden behind the recurrence, and the critical path
 // of a level is  LDS (stage) -> LDS (zs gather) -> fma chain -> STS -> named barrier over the solver warps only.
 // Requires max_level <= blockDim.x and stage_rows >= max_level.
-struct Stage {
-    int *col;      // [kMaxWa][rows]
-    float *val;    // [kMaxWa][rows]
-    float *aux;    // [kMaxWa][rows]  MODE 0: u(col, row);  MODE 1: aux[0][.] = right-hand side
-};
-
-template <int MODE>
-__device__ void wavefront_staged(const BicgTab &T, const int *__restrict__ lp /* level_ptr in smem */, int n_max,
+// Stage buffer b (0/1) holds, for up to stage_rows rows: col[kMaxWa][rows] (int), val[kMaxWa][rows], aux[kMaxWa][rows]
+// (MODE 0: u(col,row); MODE 1: aux[0][.] = right-hand side).  All shared-memory pointers are derived from the extern
+// array inside this function so that the compiler keeps them in the shared address space (LDS/STS, no generic or
+// local-memory traffic on the per-level critical path).
+template <int MODE, bool kZsSmem>
+__device__ __noinline__ void wavefront_staged(const BicgTab &T, int lp_cap, int n_max,
                                  const float *__restrict__ plane_a /* a_val (MODE 0) or lu */,
                                  const float *__restrict__ plane_rv /* MODE 0: M(col,row) planes */, float *lu,
-                                 const float *in, float *zs, int *stage_mem, int stage_rows) {
+                                 const float *in, float *zs_global, int stage_rows) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int *lp = (const int *)smem_raw;
+    int *const stage0 = (int *)smem_raw + lp_cap;
+    const int sbuf = stage_rows * (3 * kMaxWa);          // ints per stage buffer
+    float *const zs = kZsSmem ? (float *)(stage0 + 2 * sbuf) : zs_global;
     const int wa = T.wa, n = T.n, nl = T.n_levels;
     const int t = threadIdx.x;
     const int P = (T.max_level + 31) & ~31;
     const int K = max(1, stage_rows / T.max_level);
     const int nchunks = (nl + K - 1) / K;
-    Stage st[2];
-    for (int b = 0; b < 2; b++) {
-        int *base = stage_mem + (size_t)b * stage_rows * (3 * kMaxWa);
-        st[b].col = base;
-        st[b].val = (float *)(base + stage_rows * kMaxWa);
-        st[b].aux = (float *)(base + 2 * stage_rows * kMaxWa);
-    }
     // chunk c covers levels [la, lb) (ascending sweeps) or levels lb-1 .. la (descending sweep, MODE 2)
     auto chunk_levels = [&](int c, int &la, int &lb) {
         if (MODE != 2) { la = c * K; lb = min(nl, la + K); }
@@ -197,14 +193,15 @@ __device__ void wavefront_staged(const BicgTab &T, const int *__restrict__ lp /*
             int la, lb;
             chunk_levels(c, la, lb);
             const int i = reg_q - lp[la];
-            Stage &S = st[c & 1];
+            int *sc = stage0 + (c & 1) * sbuf;
+            float *sv = (float *)(sc + stage_rows * kMaxWa), *sa = (float *)(sc + 2 * stage_rows * kMaxWa);
 #pragma unroll
             for (int k = 0; k < kMaxWa; k++) {
-                S.col[k * stage_rows + i] = reg_col[k];
-                S.val[k * stage_rows + i] = reg_val[k];
-                if (MODE == 0) S.aux[k * stage_rows + i] = reg_aux[k];
+                sc[k * stage_rows + i] = reg_col[k];
+                sv[k * stage_rows + i] = reg_val[k];
+                if (MODE == 0) sa[k * stage_rows + i] = reg_aux[k];
             }
-            if (MODE == 1) S.aux[i] = reg_aux[0];
+            if (MODE == 1) sa[i] = reg_aux[0];
         }
     };
     __syncthreads();
@@ -217,7 +214,8 @@ __device__ void wavefront_staged(const BicgTab &T, const int *__restrict__ lp /*
             int la, lb;
             chunk_levels(c, la, lb);
             const int q_base = lp[la];
-            const Stage &S = st[c & 1];
+            const int *sc = stage0 + (c & 1) * sbuf;
+            const float *sv = (const float *)(sc + stage_rows * kMaxWa), *sa = (const float *)(sc + 2 * stage_rows * kMaxWa);
             for (int s = 0; s < lb - la; s++) {
                 const int d = MODE == 2 ? lb - 1 - s : la + s;
                 const int q = lp[d] + t;
@@ -226,7 +224,7 @@ __device__ void wavefront_staged(const BicgTab &T, const int *__restrict__ lp /*
                     int col[kMaxWa];
                     float val[kMaxWa];
 #pragma unroll
-                    for (int k = 0; k < kMaxWa; k++) { col[k] = S.col[k * stage_rows + i]; val[k] = S.val[k * stage_rows + i]; }
+                    for (int k = 0; k < kMaxWa; k++) { col[k] = sc[k * stage_rows + i]; val[k] = sv[k * stage_rows + i]; }
                     if (MODE == 0) {
                         // pivot = first self entry in column order (padding, also col == q, sits behind the real entries)
                         float diag = 0.0f;
@@ -240,7 +238,7 @@ __device__ void wavefront_staged(const BicgTab &T, const int *__restrict__ lp /*
                                 if (col[k] >= 0 && col[k] < q) {
                                     const float lik = __fdiv_rn(val[k], zs[col[k]]);
                                     lu[k * n_max + q] = lik;
-                                    diag = fmaf(-lik, S.aux[k * stage_rows + i], diag);
+                                    diag = fmaf(-lik, sa[k * stage_rows + i], diag);
                                 } else if (k != dslot) {
                                     lu[k * n_max + q] = val[k];   // U entries are unchanged by ILU(0) on this pattern
                                 }
@@ -249,7 +247,7 @@ __device__ void wavefront_staged(const BicgTab &T, const int *__restrict__ lp /*
                         lu[dslot * n_max + q] = diag;
                         zs[q] = diag;
                     } else if (MODE == 1) {
-                        float acc = S.aux[i];
+                        float acc = sa[i];
 #pragma unroll
                         for (int k = 0; k < kMaxWa; k++)
                             if (col[k] >= 0 && col[k] < q) acc = fmaf(-val[k], zs[col[k]], acc);
@@ -296,8 +294,9 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_kernel(const BicgPar
     float *x = b + n_max, *r = x + n_max, *rh = r + n_max, *p = rh + n_max, *v = p + n_max, *tt = v + n_max;
     // dynamic smem: [level_ptr copy][stage buffers][zs]
     int *lp_s = (int *)smem_raw;
-    int *stage_mem = lp_s + prm.lp_cap;
-    float *zs = prm.zs_in_smem ? (float *)(stage_mem + (size_t)2 * prm.stage_rows * 3 * kMaxWa) : tt + n_max;
+    float *const zs_smem = (float *)((int *)smem_raw + prm.lp_cap + (size_t)2 * prm.stage_rows * 3 * kMaxWa);
+    float *const zs_glob = tt + n_max;
+    float *zs = prm.zs_in_smem ? zs_smem : zs_glob;
     const bool fast = prm.stage_rows > 0;
     if (fast) for (int i = tid; i <= T.n_levels; i += NT) lp_s[i] = T.level_ptr[i];
 
@@ -319,13 +318,19 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_kernel(const BicgPar
     int warn = (isnan((float)sqrt(nv)) || isnan((float)sqrt(nb))) ? 1 : 0;
 
     // ---- ILU(0) (csrilu02, ":181-218") ---------------------------------------------------------------------
-    if (fast) wavefront_staged<0>(T, lp_s, n_max, a_val, a_rv, lu, nullptr, zs, stage_mem, prm.stage_rows);
-    else wavefront<0>(T, n_max, values_c, a_val, lu, nullptr, zs);
+    const bool zsm = prm.zs_in_smem != 0;
+    if (fast) {
+        if (zsm) wavefront_staged<0, true>(T, prm.lp_cap, n_max, a_val, a_rv, lu, nullptr, zs_glob, prm.stage_rows);
+        else wavefront_staged<0, false>(T, prm.lp_cap, n_max, a_val, a_rv, lu, nullptr, zs_glob, prm.stage_rows);
+    } else wavefront<0>(T, n_max, values_c, a_val, lu, nullptr, zs);
 
     auto precondition = [&](const float *src) {                      // zs = U^-1 L^-1 src   (csrsv2 x2, ":321-327")
-        if (fast) {
-            wavefront_staged<1>(T, lp_s, n_max, lu, nullptr, nullptr, src, zs, stage_mem, prm.stage_rows);
-            wavefront_staged<2>(T, lp_s, n_max, lu, nullptr, nullptr, nullptr, zs, stage_mem, prm.stage_rows);
+        if (fast && zsm) {
+            wavefront_staged<1, true>(T, prm.lp_cap, n_max, lu, nullptr, nullptr, src, zs_glob, prm.stage_rows);
+            wavefront_staged<2, true>(T, prm.lp_cap, n_max, lu, nullptr, nullptr, nullptr, zs_glob, prm.stage_rows);
+        } else if (fast) {
+            wavefront_staged<1, false>(T, prm.lp_cap, n_max, lu, nullptr, nullptr, src, zs_glob, prm.stage_rows);
+            wavefront_staged<2, false>(T, prm.lp_cap, n_max, lu, nullptr, nullptr, nullptr, zs_glob, prm.stage_rows);
         } else {
             wavefront<1>(T, n_max, nullptr, nullptr, lu, src, zs);
             wavefront<2>(T, n_max, nullptr, nullptr, lu, nullptr, zs);
