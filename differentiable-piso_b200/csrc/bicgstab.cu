@@ -23,7 +23,7 @@ constexpr int kBicgThreads = 512;
 constexpr int kMaxWa = 6;
 
 struct BicgTab {
-    int n, n_levels, wa, max_level;
+    int n, n_levels, wa, max_level, wl, wu;
     const int *level_ptr, *perm, *a_col, *a_src, *a_rev;
 };
 
@@ -37,6 +37,7 @@ struct BicgParams {
     size_t ws_floats;      // per system
     int stage_rows;        // rows per stage buffer (0 = staged fast path disabled)
     int lp_cap;            // ints reserved for the level_ptr copy in smem
+    int compact;           // rows have <= 4 lower and <= 4 upper entries: compact triangular sweeps
     const float *values, *rhs, *x0;
     float *x;
     int *stats;
@@ -271,6 +272,131 @@ __device__ __noinline__ void wavefront_staged(const BicgTab &T, int lp_cap, int 
     }
 }
 
+// Triangular sweeps (MODE 1: L, MODE 2: U) with COMPACT staged rows.  A single warp per scheduler executes the level
+// loop, so its cost is (dependent instructions) x (pipeline latency): the per-level work is therefore reduced to the
+// bare recurrence.  While staging a chunk, every thread compacts its row to the <= 4 entries the sweep needs (L entries
+// for MODE 1, U entries + pivot for MODE 2, zero-padded), stored as int4 / float4; the solver threads prefetch the next
+// level's row from the stage buffer before the level barrier, so that a level is
+//     LDS zs[col] x4 -> 4 fma -> (div) -> STS -> bar.sync over the solver warps.
+// Requires wl, wu <= 4 (host-checked).
+template <int MODE, bool kZsSmem>
+__device__ __noinline__ void wavefront_compact(const BicgTab &T, int lp_cap, int n_max, const float *__restrict__ lu,
+                                               const float *in, float *zs_global, int stage_rows) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int *lp = (const int *)smem_raw;
+    int *const stage0 = (int *)smem_raw + lp_cap;
+    const int sbuf_full = stage_rows * (3 * kMaxWa);     // ints per stage buffer (sized for the generic path)
+    float *const zs = kZsSmem ? (float *)(stage0 + 2 * sbuf_full) : zs_global;
+    const int wa = T.wa, n = T.n, nl = T.n_levels;
+    const int t = threadIdx.x;
+    const int P = (T.max_level + 31) & ~31;
+    const int K = max(1, stage_rows / T.max_level);
+    const int nchunks = (nl + K - 1) / K;
+    auto chunk_levels = [&](int c, int &la, int &lb) {
+        if (MODE != 2) { la = c * K; lb = min(nl, la + K); }
+        else { lb = nl - c * K; la = max(0, lb - K); }
+    };
+    // compact stage buffer b: int4 col[rows], float4 val[rows], float ext[rows]  (9 ints per row <= 18)
+    auto st_col = [&](int b) { return (int4 *)(stage0 + b * sbuf_full); };
+    auto st_val = [&](int b) { return (float4 *)(stage0 + b * sbuf_full + 4 * stage_rows); };
+    auto st_ext = [&](int b) { return (float *)(stage0 + b * sbuf_full + 8 * stage_rows); };
+
+    int4 rc = make_int4(0, 0, 0, 0);
+    float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+    float rext = 0.f;
+    int reg_q = -1;
+    auto fetch = [&](int c) {            // global -> registers (compacted), one row per thread
+        reg_q = -1;
+        if (c < nchunks) {
+            int la, lb;
+            chunk_levels(c, la, lb);
+            const int q = lp[la] + t;
+            if (q < lp[lb]) {
+                reg_q = q;
+                int cc[4] = {q, q, q, q};
+                float vv[4] = {0.f, 0.f, 0.f, 0.f};
+                float ext = MODE == 1 ? in[q] : 1.0f;
+                int cnt = 0;
+                bool seen_diag = false;
+#pragma unroll
+                for (int k = 0; k < kMaxWa; k++) {
+                    if (k < wa) {
+                        const int col = T.a_col[k * n + q];
+                        const float val = lu[k * n_max + q];
+                        const bool take = MODE == 1 ? col < q : col > q;
+                        if (take) {
+#pragma unroll
+                            for (int m = 0; m < 4; m++)
+                                if (cnt == m) { cc[m] = col; vv[m] = val; }
+                            cnt++;
+                        } else if (MODE == 2 && col == q && !seen_diag) {
+                            ext = val;          // pivot: first self entry in column order (padding sits behind it)
+                            seen_diag = true;
+                        }
+                    }
+                }
+                rc = make_int4(cc[0], cc[1], cc[2], cc[3]);
+                rv = make_float4(vv[0], vv[1], vv[2], vv[3]);
+                rext = ext;
+            }
+        }
+    };
+    auto stash = [&](int c) {
+        if (reg_q >= 0) {
+            int la, lb;
+            chunk_levels(c, la, lb);
+            const int i = reg_q - lp[la];
+            st_col(c & 1)[i] = rc;
+            st_val(c & 1)[i] = rv;
+            st_ext(c & 1)[i] = rext;
+        }
+    };
+    __syncthreads();
+    fetch(0);
+    stash(0);
+    __syncthreads();
+    for (int c = 0; c < nchunks; c++) {
+        fetch(c + 1);
+        if (t < P) {
+            int la, lb;
+            chunk_levels(c, la, lb);
+            const int q_base = lp[la];
+            const int4 *sc = st_col(c & 1);
+            const float4 *sv = st_val(c & 1);
+            const float *se = st_ext(c & 1);
+            const int nlev = lb - la;
+            // row of the first level of this chunk
+            int d = MODE == 2 ? lb - 1 : la;
+            int q = lp[d] + t;
+            bool act = q < lp[d + 1];
+            int4 c4 = make_int4(0, 0, 0, 0);
+            float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            float e = 1.0f;
+            if (act) { c4 = sc[q - q_base]; v4 = sv[q - q_base]; e = se[q - q_base]; }
+            for (int s = 0; s < nlev; s++) {
+                if (act) {
+                    float acc = MODE == 1 ? e : zs[q];
+                    acc = fmaf(-v4.x, zs[c4.x], acc);
+                    acc = fmaf(-v4.y, zs[c4.y], acc);
+                    acc = fmaf(-v4.z, zs[c4.z], acc);
+                    acc = fmaf(-v4.w, zs[c4.w], acc);
+                    zs[q] = MODE == 1 ? acc : __fdiv_rn(acc, e);
+                }
+                // prefetch the next level's row (coefficients only; zs is read after the barrier)
+                if (s + 1 < nlev) {
+                    d = MODE == 2 ? d - 1 : d + 1;
+                    q = lp[d] + t;
+                    act = q < lp[d + 1];
+                    if (act) { c4 = sc[q - q_base]; v4 = sv[q - q_base]; e = se[q - q_base]; }
+                }
+                named_bar(1, P);
+            }
+        }
+        stash(c + 1);
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_kernel(const BicgParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red[64];
@@ -325,7 +451,10 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_kernel(const BicgPar
     } else wavefront<0>(T, n_max, values_c, a_val, lu, nullptr, zs);
 
     auto precondition = [&](const float *src) {                      // zs = U^-1 L^-1 src   (csrsv2 x2, ":321-327")
-        if (fast && zsm) {
+        if (fast && zsm && prm.compact) {
+            wavefront_compact<1, true>(T, prm.lp_cap, n_max, lu, src, zs_glob, prm.stage_rows);
+            wavefront_compact<2, true>(T, prm.lp_cap, n_max, lu, nullptr, zs_glob, prm.stage_rows);
+        } else if (fast && zsm) {
             wavefront_staged<1, true>(T, prm.lp_cap, n_max, lu, nullptr, nullptr, src, zs_glob, prm.stage_rows);
             wavefront_staged<2, true>(T, prm.lp_cap, n_max, lu, nullptr, nullptr, nullptr, zs_glob, prm.stage_rows);
         } else if (fast) {
@@ -429,7 +558,7 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_kernel(const BicgPar
 using namespace dpiso;
 
 static void to_tab(const dpiso_bicg_tables *h, BicgTab &t) {
-    t.n = h->n; t.n_levels = h->n_levels; t.wa = h->wa; t.max_level = h->max_level;
+    t.n = h->n; t.n_levels = h->n_levels; t.wa = h->wa; t.max_level = h->max_level; t.wl = h->wl; t.wu = h->wu;
     t.level_ptr = h->level_ptr; t.perm = h->perm; t.a_col = h->a_col; t.a_src = h->a_src; t.a_rev = h->a_rev;
 }
 
@@ -482,6 +611,7 @@ int dpiso_bicgstab_ilu(int batch, const dpiso_bicg_tables *h_tab_u, const dpiso_
         prm.zs_in_smem = zs_bytes <= kBudget ? 1 : 0;
         smem = prm.zs_in_smem ? zs_bytes : 0;
     }
+    prm.compact = (h_tab_u->wl <= 4 && h_tab_u->wu <= 4 && h_tab_v->wl <= 4 && h_tab_v->wu <= 4) ? 1 : 0;
     static bool attr_set = false;
     if (!attr_set) {
         DPISO_CUDA_TRY(cudaFuncSetAttribute(bicgstab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 1024));

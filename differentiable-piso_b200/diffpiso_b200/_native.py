@@ -32,7 +32,7 @@ lib = _load()
 
 class BicgTables(C.Structure):
     _fields_ = [("n", C.c_int), ("n_levels", C.c_int), ("wa", C.c_int), ("max_level", C.c_int),
-                ("level_ptr", C.c_void_p), ("perm", C.c_void_p), ("a_col", C.c_void_p), ("a_src", C.c_void_p),
+                ("wl", C.c_int), ("wu", C.c_int), ("level_ptr", C.c_void_p), ("perm", C.c_void_p), ("a_col", C.c_void_p), ("a_src", C.c_void_p),
                 ("a_rev", C.c_void_p)]
 
 

@@ -41,7 +41,8 @@ class Geometry(object):
             for comp in (0, 1):
                 h = S.bicg_tables(self.ny, self.nx, self.per_x, self.per_y, comp, bool(transpose))
                 dev = {k: torch.from_numpy(h[k]).to(self.device) for k in ("level_ptr", "perm", "a_col", "a_src", "a_rev")}
-                st = N.BicgTables(h["n"], h["n_levels"], h["wa"], h["max_level"], dev["level_ptr"].data_ptr(),
+                st = N.BicgTables(h["n"], h["n_levels"], h["wa"], h["max_level"], h["wl"], h["wu"],
+                                  dev["level_ptr"].data_ptr(),
                                   dev["perm"].data_ptr(), dev["a_col"].data_ptr(), dev["a_src"].data_ptr(),
                                   dev["a_rev"].data_ptr())
                 structs.append(st)

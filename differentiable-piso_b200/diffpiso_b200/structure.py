@@ -140,7 +140,9 @@ def bicg_tables(ny, nx, per_x, per_y, comp, transpose):
     orig_row = perm[None, :].repeat(wa, 0)
     assert np.all((a_col < q[None, :])[real & (colp < orig_row)])
     assert np.all((a_col > q[None, :])[real & (colp > orig_row)])
-    return dict(n=n, n_levels=int(counts.size), wa=wa, max_level=int(counts.max()),
+    wl = int(np.bincount(row_of[lower], minlength=n).max()) if lower.any() else 0
+    wu = int(np.bincount(row_of[upper], minlength=n).max()) if upper.any() else 0
+    return dict(n=n, n_levels=int(counts.size), wa=wa, max_level=int(counts.max()), wl=wl, wu=wu,
                 level_ptr=level_ptr.astype(np.int32), perm=perm.astype(np.int32),
                 a_col=np.ascontiguousarray(a_col, np.int32), a_src=np.ascontiguousarray(a_src, np.int32),
                 a_rev=np.ascontiguousarray(a_rev, np.int32), nnz=int(a.nnz))

@@ -120,6 +120,7 @@ typedef struct {
     int n_levels;         /* wavefront levels (lx+ly hyperplanes) */
     int wa;               /* ELL width: max entries per row of the (possibly transposed) matrix, <= 6 */
     int max_level;        /* rows in the largest level */
+    int wl, wu;           /* max number of lower / upper entries in a row */
     const int *level_ptr; /* [n_levels+1] first position of each level (level-major numbering) */
     const int *perm;      /* [n] level-major position -> original row */
     const int *a_col;     /* [wa][n] column (as level-major position) per entry, in ascending ORIGINAL column

@@ -1,0 +1,54 @@
+"""CPU suite: the N > 1 host logic (batch sharding, max-over-ranks timing) with world_size = 2 over gloo."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from diffpiso_b200 import sharding
+
+
+def test_shard_bounds_cover_batch_exactly():
+    for total in (1, 2, 7, 64, 65, 256):
+        for world in (1, 2, 3, 4, 8):
+            seen = []
+            for r in range(world):
+                s, c = sharding.shard_bounds(total, world, r)
+                seen += list(range(s, s + c))
+            assert seen == list(range(total))
+    with pytest.raises(ValueError):
+        sharding.shard_bounds(8, 2, 2)
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    batch = torch.arange(13 * 3, dtype=torch.float32).reshape(13, 3)
+    mine = sharding.local_batch(batch)
+    counts = sharding.gather_counts(mine.shape[0])
+    times = sharding.max_over_ranks([10.0 + rank, 5.0 - rank])
+    first = float(mine[0, 0])
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, counts, times, first, mine.shape[0]))
+
+
+def test_two_rank_gloo_sharding_and_timing():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [r[1] for r in res] == [[7, 6], [7, 6]]            # every rank sees the same whole-job counts
+    assert [r[2] for r in res] == [[11.0, 5.0], [11.0, 5.0]]  # max over ranks
+    assert [r[3] for r in res] == [0.0, 21.0] and [r[4] for r in res] == [7, 6]
