@@ -38,6 +38,7 @@ struct BicgParams {
     int stage_rows;        // rows per stage buffer (0 = staged fast path disabled)
     int lp_cap;            // ints reserved for the level_ptr copy in smem
     int compact;           // rows have <= 4 lower and <= 4 upper entries: compact triangular sweeps
+    int ring_depth;        // levels in flight in the cp.async ring (16, 8 or 2)
     const float *values, *rhs, *x0;
     float *x;
     int *stats;
@@ -45,6 +46,7 @@ struct BicgParams {
     float *workspace;
     float tol;
     int max_it;
+    long long *timing;     // optional [8] cycle counters of system 0 (debug / profiling), may be NULL
 };
 
 __device__ __forceinline__ double warp_sum_d(double v) {
@@ -272,132 +274,99 @@ __device__ __noinline__ void wavefront_staged(const BicgTab &T, int lp_cap, int 
     }
 }
 
-// Triangular sweeps (MODE 1: L, MODE 2: U) with COMPACT staged rows.  A single warp per scheduler executes the level
-// loop, so its cost is (dependent instructions) x (pipeline latency): the per-level work is therefore reduced to the
-// bare recurrence.  While staging a chunk, every thread compacts its row to the <= 4 entries the sweep needs (L entries
-// for MODE 1, U entries + pivot for MODE 2, zero-padded), stored as int4 / float4; the solver threads prefetch the next
-// level's row from the stage buffer before the level barrier, so that a level is
-//     LDS zs[col] x4 -> 4 fma -> (div) -> STS -> bar.sync over the solver warps.
-// Requires wl, wu <= 4 (host-checked).
-template <int MODE, bool kZsSmem>
-__device__ __noinline__ void wavefront_compact(const BicgTab &T, int lp_cap, int n_max, const float *__restrict__ lu,
-                                               const float *in, float *zs_global, int stage_rows) {
+// Triangular sweeps (MODE 1: L, MODE 2: U) over COMPACT rows with a per-thread cp.async ring.
+//
+// After ILU(0) every row is compacted once to the <= 4 entries each sweep needs (CompactPlanes, level-major, 16-byte
+// vectors).  Only the solver warps (first P = roundup32(max_level) threads) run a sweep; thread t owns row lp[d] + t of
+// level d.  Each thread streams ITS OWN rows D levels ahead of the recurrence with cp.async into a private shared-memory
+// ring slot, so the L2 latency of the coefficient stream is hidden D levels deep without staging threads, chunk
+// barriers or registers.  A level is then:  LDS ring slot -> LDS zs[col] x4 -> 4 fma (-> div) -> STS zs -> bar.sync
+// over the solver warps.  Requires wl, wu <= 4 (host-checked) and max_level <= blockDim.x.
+struct CompactPlanes {
+    const int4 *lcol, *ucol;        // [n]
+    const float4 *lval, *uval;      // [n]
+    const float *udiag;             // [n]
+};
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int MODE, bool kZsSmem, int D>
+__device__ __noinline__ void wavefront_ring(const BicgTab &T, int lp_cap, const CompactPlanes cp, const float *in,
+                                            float *zs_global, int stage_rows) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int *lp = (const int *)smem_raw;
-    int *const stage0 = (int *)smem_raw + lp_cap;
-    const int sbuf_full = stage_rows * (3 * kMaxWa);     // ints per stage buffer (sized for the generic path)
+    int *const stage0 = (int *)smem_raw + lp_cap;                      // ring lives in the stage-buffer region
+    const int sbuf_full = stage_rows * (3 * kMaxWa);
     float *const zs = kZsSmem ? (float *)(stage0 + 2 * sbuf_full) : zs_global;
-    const int wa = T.wa, n = T.n, nl = T.n_levels;
+    const int nl = T.n_levels;
     const int t = threadIdx.x;
     const int P = (T.max_level + 31) & ~31;
-    const int K = max(1, stage_rows / T.max_level);
-    const int nchunks = (nl + K - 1) / K;
-    auto chunk_levels = [&](int c, int &la, int &lb) {
-        if (MODE != 2) { la = c * K; lb = min(nl, la + K); }
-        else { lb = nl - c * K; la = max(0, lb - K); }
-    };
-    // compact stage buffer b: int4 col[rows], float4 val[rows], float ext[rows]  (9 ints per row <= 18)
-    auto st_col = [&](int b) { return (int4 *)(stage0 + b * sbuf_full); };
-    auto st_val = [&](int b) { return (float4 *)(stage0 + b * sbuf_full + 4 * stage_rows); };
-    auto st_ext = [&](int b) { return (float *)(stage0 + b * sbuf_full + 8 * stage_rows); };
-
-    int4 rc = make_int4(0, 0, 0, 0);
-    float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
-    float rext = 0.f;
-    int reg_q = -1;
-    auto fetch = [&](int c) {            // global -> registers (compacted), one row per thread
-        reg_q = -1;
-        if (c < nchunks) {
-            int la, lb;
-            chunk_levels(c, la, lb);
-            const int q = lp[la] + t;
-            if (q < lp[lb]) {
-                reg_q = q;
-                int cc[4] = {q, q, q, q};
-                float vv[4] = {0.f, 0.f, 0.f, 0.f};
-                float ext = MODE == 1 ? in[q] : 1.0f;
-                int cnt = 0;
-                bool seen_diag = false;
-#pragma unroll
-                for (int k = 0; k < kMaxWa; k++) {
-                    if (k < wa) {
-                        const int col = T.a_col[k * n + q];
-                        const float val = lu[k * n_max + q];
-                        const bool take = MODE == 1 ? col < q : col > q;
-                        if (take) {
-#pragma unroll
-                            for (int m = 0; m < 4; m++)
-                                if (cnt == m) { cc[m] = col; vv[m] = val; }
-                            cnt++;
-                        } else if (MODE == 2 && col == q && !seen_diag) {
-                            ext = val;          // pivot: first self entry in column order (padding sits behind it)
-                            seen_diag = true;
-                        }
-                    }
-                }
-                rc = make_int4(cc[0], cc[1], cc[2], cc[3]);
-                rv = make_float4(vv[0], vv[1], vv[2], vv[3]);
-                rext = ext;
-            }
-        }
-    };
-    auto stash = [&](int c) {
-        if (reg_q >= 0) {
-            int la, lb;
-            chunk_levels(c, la, lb);
-            const int i = reg_q - lp[la];
-            st_col(c & 1)[i] = rc;
-            st_val(c & 1)[i] = rv;
-            st_ext(c & 1)[i] = rext;
-        }
-    };
+    int4 *const rc = (int4 *)stage0;                                   // [D][P]
+    float4 *const rv = (float4 *)(stage0 + 4 * D * P);                 // [D][P]
+    float *const re = (float *)(stage0 + 8 * D * P);                   // [D][P]
     __syncthreads();
-    fetch(0);
-    stash(0);
-    __syncthreads();
-    for (int c = 0; c < nchunks; c++) {
-        fetch(c + 1);
-        if (t < P) {
-            int la, lb;
-            chunk_levels(c, la, lb);
-            const int q_base = lp[la];
-            const int4 *sc = st_col(c & 1);
-            const float4 *sv = st_val(c & 1);
-            const float *se = st_ext(c & 1);
-            const int nlev = lb - la;
-            // row of the first level of this chunk
-            int d = MODE == 2 ? lb - 1 : la;
-            int q = lp[d] + t;
-            bool act = q < lp[d + 1];
-            int4 c4 = make_int4(0, 0, 0, 0);
-            float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            float e = 1.0f;
-            if (act) { c4 = sc[q - q_base]; v4 = sv[q - q_base]; e = se[q - q_base]; }
-            for (int s = 0; s < nlev; s++) {
-                if (act) {
-                    float acc = MODE == 1 ? e : zs[q];
-                    acc = fmaf(-v4.x, zs[c4.x], acc);
-                    acc = fmaf(-v4.y, zs[c4.y], acc);
-                    acc = fmaf(-v4.z, zs[c4.z], acc);
-                    acc = fmaf(-v4.w, zs[c4.w], acc);
-                    zs[q] = MODE == 1 ? acc : __fdiv_rn(acc, e);
+    if (t < P) {
+        const int4 *gcol = MODE == 1 ? cp.lcol : cp.ucol;
+        const float4 *gval = MODE == 1 ? cp.lval : cp.uval;
+        const float *gext = MODE == 1 ? in : cp.udiag;
+        auto issue = [&](int s) {                                      // sweep step s -> ring slot s % D
+            if (s < nl) {
+                const int d = MODE == 2 ? nl - 1 - s : s;
+                const int q = lp[d] + t;
+                if (q < lp[d + 1]) {
+                    const int slot = (s & (D - 1)) * P + t;
+                    cp_async16(rc + slot, gcol + q);
+                    cp_async16(rv + slot, gval + q);
+                    cp_async4(re + slot, gext + q);
                 }
-                // prefetch the next level's row (coefficients only; zs is read after the barrier)
-                if (s + 1 < nlev) {
-                    d = MODE == 2 ? d - 1 : d + 1;
-                    q = lp[d] + t;
-                    act = q < lp[d + 1];
-                    if (act) { c4 = sc[q - q_base]; v4 = sv[q - q_base]; e = se[q - q_base]; }
-                }
-                named_bar(1, P);
             }
+            cp_async_commit();
+        };
+#pragma unroll 1
+        for (int s = 0; s < D; s++) issue(s);
+#pragma unroll 1
+        for (int s = 0; s < nl; s++) {
+            cp_async_wait<D - 1>();                                    // this thread's row of step s has landed
+            const int d = MODE == 2 ? nl - 1 - s : s;
+            const int q = lp[d] + t;
+            if (q < lp[d + 1]) {
+                const int slot = (s & (D - 1)) * P + t;
+                const int4 c4 = rc[slot];
+                const float4 v4 = rv[slot];
+                const float e = re[slot];
+                float acc = MODE == 1 ? e : zs[q];
+                acc = fmaf(-v4.x, zs[c4.x], acc);
+                acc = fmaf(-v4.y, zs[c4.y], acc);
+                acc = fmaf(-v4.z, zs[c4.z], acc);
+                acc = fmaf(-v4.w, zs[c4.w], acc);
+                zs[q] = MODE == 1 ? acc : __fdiv_rn(acc, e);
+            }
+            issue(s + D);                                              // refill the slot just consumed
+            named_bar(1, P);
         }
-        stash(c + 1);
-        __syncthreads();
+        cp_async_wait<0>();
     }
+    __syncthreads();
 }
 
+#define DPISO_TICK(slot)                                                             \
+    do {                                                                             \
+        if (prm.timing && blockIdx.x == 0 && threadIdx.x == 0) {                     \
+            const long long _now = clock64();                                        \
+            atomicAdd((unsigned long long *)&prm.timing[slot], (unsigned long long)(_now - tick)); \
+            tick = _now;                                                             \
+        }                                                                            \
+    } while (0)
+
 __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_kernel(const BicgParams prm) {
+    long long tick = clock64();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red[64];
     const int sys = blockIdx.x;
@@ -418,6 +387,16 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_kernel(const BicgPar
     float *a_rv = lu + (size_t)kMaxWa * n_max;   // [kMaxWa][n_max]  M(col, row) (0 where absent): ILU(0) pivot updates
     float *b = a_rv + (size_t)kMaxWa * n_max;
     float *x = b + n_max, *r = x + n_max, *rh = r + n_max, *p = rh + n_max, *v = p + n_max, *tt = v + n_max;
+    // compact L / U planes for the ring sweeps (16-byte aligned: n_max is padded to a multiple of 4 by the host)
+    CompactPlanes cpl;
+    {
+        float *cbase = tt + 2 * (size_t)n_max;
+        cpl.lcol = (const int4 *)cbase;
+        cpl.lval = (const float4 *)(cbase + 4 * (size_t)n_max);
+        cpl.ucol = (const int4 *)(cbase + 8 * (size_t)n_max);
+        cpl.uval = (const float4 *)(cbase + 12 * (size_t)n_max);
+        cpl.udiag = cbase + 16 * (size_t)n_max;
+    }
     // dynamic smem: [level_ptr copy][stage buffers][zs]
     int *lp_s = (int *)smem_raw;
     float *const zs_smem = (float *)((int *)smem_raw + prm.lp_cap + (size_t)2 * prm.stage_rows * 3 * kMaxWa);
@@ -442,6 +421,7 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_kernel(const BicgPar
     }
     block_sum2(nv, nb, red);
     int warn = (isnan((float)sqrt(nv)) || isnan((float)sqrt(nb))) ? 1 : 0;
+    DPISO_TICK(0);
 
     // ---- ILU(0) (csrilu02, ":181-218") ---------------------------------------------------------------------
     const bool zsm = prm.zs_in_smem != 0;
@@ -449,11 +429,49 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_kernel(const BicgPar
         if (zsm) wavefront_staged<0, true>(T, prm.lp_cap, n_max, a_val, a_rv, lu, nullptr, zs_glob, prm.stage_rows);
         else wavefront_staged<0, false>(T, prm.lp_cap, n_max, a_val, a_rv, lu, nullptr, zs_glob, prm.stage_rows);
     } else wavefront<0>(T, n_max, values_c, a_val, lu, nullptr, zs);
+    __syncthreads();
+    DPISO_TICK(1);
+    if (fast && zsm && prm.compact) {            // compact every row once: <= 4 lower entries, <= 4 upper entries + pivot
+        for (int q = tid; q < n; q += NT) {
+            int lc[4] = {q, q, q, q}, uc[4] = {q, q, q, q};
+            float lv[4] = {0.f, 0.f, 0.f, 0.f}, uv[4] = {0.f, 0.f, 0.f, 0.f};
+            float dg = 1.0f;
+            int nl_ = 0, nu_ = 0;
+            bool seen_diag = false;
+            for (int k = 0; k < wa; k++) {
+                const int col = T.a_col[k * n + q];
+                const float val = lu[k * n_max + q];
+                if (col < q) {
+#pragma unroll
+                    for (int m = 0; m < 4; m++) if (nl_ == m) { lc[m] = col; lv[m] = val; }
+                    nl_++;
+                } else if (col > q) {
+#pragma unroll
+                    for (int m = 0; m < 4; m++) if (nu_ == m) { uc[m] = col; uv[m] = val; }
+                    nu_++;
+                } else if (!seen_diag) { dg = val; seen_diag = true; }   // padding (also col == q) sits behind the pivot
+            }
+            ((int4 *)cpl.lcol)[q] = make_int4(lc[0], lc[1], lc[2], lc[3]);
+            ((float4 *)cpl.lval)[q] = make_float4(lv[0], lv[1], lv[2], lv[3]);
+            ((int4 *)cpl.ucol)[q] = make_int4(uc[0], uc[1], uc[2], uc[3]);
+            ((float4 *)cpl.uval)[q] = make_float4(uv[0], uv[1], uv[2], uv[3]);
+            ((float *)cpl.udiag)[q] = dg;
+        }
+        __syncthreads();
+    }
 
     auto precondition = [&](const float *src) {                      // zs = U^-1 L^-1 src   (csrsv2 x2, ":321-327")
         if (fast && zsm && prm.compact) {
-            wavefront_compact<1, true>(T, prm.lp_cap, n_max, lu, src, zs_glob, prm.stage_rows);
-            wavefront_compact<2, true>(T, prm.lp_cap, n_max, lu, nullptr, zs_glob, prm.stage_rows);
+            if (prm.ring_depth == 16) {
+                wavefront_ring<1, true, 16>(T, prm.lp_cap, cpl, src, zs_glob, prm.stage_rows);
+                wavefront_ring<2, true, 16>(T, prm.lp_cap, cpl, nullptr, zs_glob, prm.stage_rows);
+            } else if (prm.ring_depth == 8) {
+                wavefront_ring<1, true, 8>(T, prm.lp_cap, cpl, src, zs_glob, prm.stage_rows);
+                wavefront_ring<2, true, 8>(T, prm.lp_cap, cpl, nullptr, zs_glob, prm.stage_rows);
+            } else {
+                wavefront_ring<1, true, 2>(T, prm.lp_cap, cpl, src, zs_glob, prm.stage_rows);
+                wavefront_ring<2, true, 2>(T, prm.lp_cap, cpl, nullptr, zs_glob, prm.stage_rows);
+            }
         } else if (fast && zsm) {
             wavefront_staged<1, true>(T, prm.lp_cap, n_max, lu, nullptr, nullptr, src, zs_glob, prm.stage_rows);
             wavefront_staged<2, true>(T, prm.lp_cap, n_max, lu, nullptr, nullptr, nullptr, zs_glob, prm.stage_rows);
@@ -502,7 +520,10 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_kernel(const BicgPar
                 pq = __fmul_rn(beta, pq);
                 p[q] = __fadd_rn(pq, r[q]);
             }
+            DPISO_TICK(4);
             precondition(p);                                         // zs = p_hat
+            __syncthreads();
+            DPISO_TICK(2);
             s0 = 0.0; s1 = 0.0;
             for (int q = tid; q < n; q += NT) {                      // v = A p_hat ; rh.v
                 const float vq = spmv_row(zs, q);
@@ -519,7 +540,10 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_kernel(const BicgPar
             block_sum2(s0, s1, red);
             nrm_r = (float)sqrt(s0);
             if (nrm_r < tol) { exit_kind = 1; break; }
+            DPISO_TICK(4);
             precondition(r);                                         // zs = s_hat
+            __syncthreads();
+            DPISO_TICK(2);
             s0 = 0.0; s1 = 0.0;
             for (int q = tid; q < n; q += NT) {                      // t = A s_hat ; t.r ; t.t
                 const float tq = spmv_row(zs, q);
@@ -545,6 +569,7 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_kernel(const BicgPar
         } else break;
     }
     __syncthreads();
+    DPISO_TICK(4);
     for (int q = tid; q < n; q += NT) x_g[T.perm[q]] = x[q];
     if (tid == 0) {
         int *st = prm.stats + (size_t)sys * 4;
@@ -557,6 +582,8 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_kernel(const BicgPar
 
 using namespace dpiso;
 
+static long long *g_bicg_timing = nullptr;
+
 static void to_tab(const dpiso_bicg_tables *h, BicgTab &t) {
     t.n = h->n; t.n_levels = h->n_levels; t.wa = h->wa; t.max_level = h->max_level; t.wl = h->wl; t.wu = h->wu;
     t.level_ptr = h->level_ptr; t.perm = h->perm; t.a_col = h->a_col; t.a_src = h->a_src; t.a_rev = h->a_rev;
@@ -564,9 +591,17 @@ static void to_tab(const dpiso_bicg_tables *h, BicgTab &t) {
 
 extern "C" {
 
+/* profiling hook: device buffer of 8 int64 cycle counters accumulated by system 0 (0 setup, 1 ILU(0), 2 triangular
+ * sweeps, 4 streaming phases); NULL disables */
+int dpiso_bicgstab_set_timing(long long *dev_counters) {
+    g_bicg_timing = dev_counters;
+    return DPISO_OK;
+}
+
 size_t dpiso_bicgstab_workspace_floats(const dpiso_bicg_tables *h_tab_u, const dpiso_bicg_tables *h_tab_v) {
     const size_t n_max = (size_t)(h_tab_u->n > h_tab_v->n ? h_tab_u->n : h_tab_v->n);
-    return (3 * (size_t)kMaxWa + 8) * n_max;
+    const size_t n_pad = (n_max + 3) & ~(size_t)3;
+    return (3 * (size_t)kMaxWa + 8) * n_pad + 17 * n_pad;
 }
 
 int dpiso_bicgstab_ilu(int batch, const dpiso_bicg_tables *h_tab_u, const dpiso_bicg_tables *h_tab_v, int nnz_u,
@@ -581,10 +616,11 @@ int dpiso_bicgstab_ilu(int batch, const dpiso_bicg_tables *h_tab_u, const dpiso_
     to_tab(h_tab_v, prm.tab[1]);
     prm.nnz[0] = nnz_u; prm.nnz[1] = nnz_v; prm.nnz_total = nnz_u + nnz_v;
     prm.n_face = h_tab_u->n + h_tab_v->n;
-    prm.n_max = h_tab_u->n > h_tab_v->n ? h_tab_u->n : h_tab_v->n;
+    prm.n_max = ((h_tab_u->n > h_tab_v->n ? h_tab_u->n : h_tab_v->n) + 3) & ~3;     // plane stride, 16-byte aligned
     prm.ws_floats = dpiso_bicgstab_workspace_floats(h_tab_u, h_tab_v);
     prm.values = values; prm.rhs = rhs; prm.x0 = x0; prm.x = x; prm.stats = stats; prm.warn = warn;
     prm.workspace = workspace; prm.tol = tol; prm.max_it = max_it;
+    prm.timing = g_bicg_timing;
     // shared memory plan: level_ptr copy + two stage buffers (staged wavefront) + the solve vector zs
     const size_t kBudget = 200 * 1024;
     const int max_level = h_tab_u->max_level > h_tab_v->max_level ? h_tab_u->max_level : h_tab_v->max_level;
@@ -612,6 +648,12 @@ int dpiso_bicgstab_ilu(int batch, const dpiso_bicg_tables *h_tab_u, const dpiso_
         smem = prm.zs_in_smem ? zs_bytes : 0;
     }
     prm.compact = (h_tab_u->wl <= 4 && h_tab_u->wu <= 4 && h_tab_v->wl <= 4 && h_tab_v->wu <= 4) ? 1 : 0;
+    {
+        const size_t region_ints = (size_t)2 * prm.stage_rows * 3 * kMaxWa;
+        const size_t P = (size_t)((max_level + 31) & ~31);
+        prm.ring_depth = region_ints >= 16 * P * 9 ? 16 : (region_ints >= 8 * P * 9 ? 8 : 2);
+        if (region_ints < 2 * P * 9) prm.compact = 0;
+    }
     static bool attr_set = false;
     if (!attr_set) {
         DPISO_CUDA_TRY(cudaFuncSetAttribute(bicgstab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 1024));

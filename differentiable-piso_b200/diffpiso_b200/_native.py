@@ -54,6 +54,7 @@ _SIGS = {
     "dpiso_h_apply_adj": ([_I, _P, _P, _I, _I, _F, _P, _P, _P, _P, _P], _I),
     "dpiso_predictor_rhs_adj": ([_I, _I, _I, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P], _I),
     "dpiso_bicgstab_workspace_floats": ([_P, _P], _SZ),
+    "dpiso_bicgstab_set_timing": ([_P], _I),
     "dpiso_bicgstab_ilu": ([_I, _P, _P, _I, _I, _P, _P, _P, _F, _I, _P, _P, _P, _P, _P], _I),
     "dpiso_laplace_f64": ([_I, _I, _I, _P, _P, _P, _I, _F, _F, _P, _P], _I),
     "dpiso_laplace_f32": ([_I, _I, _I, _P, _P, _P, _I, _F, _F, _P, _P], _I),

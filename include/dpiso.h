@@ -146,6 +146,10 @@ int dpiso_bicgstab_ilu(int batch, const dpiso_bicg_tables *h_tab_u, const dpiso_
                        int nnz_v, const float *values, const float *rhs, const float *x0, float tol, int max_it,
                        float *x, int *stats, uint8_t *warn, float *workspace, void *stream);
 
+/* profiling hook: dev_counters = device buffer of 8 int64 SM-cycle counters accumulated by system 0 of every following
+ * solve ([0] setup, [1] ILU(0), [2] triangular sweeps, [4] SpMV / vector phases); NULL disables */
+int dpiso_bicgstab_set_timing(long long *dev_counters);
+
 /* ---- pressure matrix (calcPISOLaplaceMatrix) ----------------------------------------------------------
  * mode 0: k_faces [batch][n_v+n_u] is the scaling field flattened [v,u] (piso_cuda_pressure_solver.py:70)
  * mode 1: k_faces is a_diag [batch][n_u+n_v] ([u,v]); k = (1/(beta-a))*dx_factor is formed on the fly.

@@ -1,0 +1,36 @@
+"""Micro-benchmark of the batched BiCGStab kernel on the bench workload (periodic 128x128, batch 64): launch time and
+the in-kernel cycle breakdown of system 0 (dpiso_bicgstab_set_timing)."""
+import json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "differentiable-piso_b200")]
+import numpy as np
+import torch
+from diffpiso_b200 import ops, setups as SU, _native as N
+
+def main():
+    ny = nx = 128; B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+    dev = "cuda:0"
+    s = SU.periodic_box(ny, nx, visc=1e-3)
+    g = ops.Geometry.get(ny, nx, True, True, dev)
+    vel = torch.as_tensor(np.stack([SU.solenoidal_field(ny, nx, seed=100 + i) for i in range(B)])).to(dev)
+    ones = torch.ones((ny + 2) * (nx + 2), device=dev)
+    dm = torch.zeros(g.nf, dtype=torch.uint8, device=dev); ns = torch.zeros((ny + 2) * (nx + 2), dtype=torch.uint8, device=dev)
+    beta = float(np.float32(s["dy"] * s["dx"] / s["dt"]))
+    values, a_diag = ops.assemble(g, vel, dm, ones, ns, torch.tensor([1e-3], device=dev), s["dy"], s["dx"], beta)
+    rhs = vel * beta
+    neg = torch.neg(values)
+    out = {}
+    for tr in (False, True):
+        cnt = torch.zeros(8, dtype=torch.int64, device=dev)
+        x, st, w = ops.bicgstab_ilu(g, neg, rhs, vel, 1e-8, 10000, tr)
+        torch.cuda.synchronize()
+        N.lib.dpiso_bicgstab_set_timing(cnt.data_ptr())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); x, st, w = ops.bicgstab_ilu(g, neg, rhs, vel, 1e-8, 10000, tr); e1.record()
+        torch.cuda.synchronize()
+        N.lib.dpiso_bicgstab_set_timing(None)
+        c = cnt.cpu().numpy()
+        out["transpose" if tr else "forward"] = {"ms": e0.elapsed_time(e1), "iterations": st.cpu().numpy()[0, :, 0].tolist(),
+            "cycles_setup": int(c[0]), "cycles_ilu": int(c[1]), "cycles_sweeps": int(c[2]), "cycles_stream": int(c[4])}
+    print(json.dumps(out))
+main()
