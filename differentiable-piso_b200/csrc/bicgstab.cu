@@ -382,11 +382,17 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_kernel(const BicgPar
     float *x_g = prm.x + (size_t)sample * prm.n_face + face_off;
 
     float *ws = prm.workspace + (size_t)sys * prm.ws_floats;
-    float *a_val = ws;                       // [kMaxWa][n_max]  M(row, col)
-    float *lu = a_val + (size_t)kMaxWa * n_max;
-    float *a_rv = lu + (size_t)kMaxWa * n_max;   // [kMaxWa][n_max]  M(col, row) (0 where absent): ILU(0) pivot updates
-    float *b = a_rv + (size_t)kMaxWa * n_max;
-    float *x = b + n_max, *r = x + n_max, *rh = r + n_max, *p = rh + n_max, *v = p + n_max, *tt = v + n_max;
+    float *__restrict__ a_val = ws;                       // [kMaxWa][n_max]  M(row, col)
+    float *__restrict__ lu = a_val + (size_t)kMaxWa * n_max;
+    float *__restrict__ a_rv = lu + (size_t)kMaxWa * n_max;   // [kMaxWa][n_max]  M(col, row) (0 where absent): ILU(0) pivot updates
+    float *__restrict__ b = a_rv + (size_t)kMaxWa * n_max;
+    float *__restrict__ x = b + n_max;
+    float *__restrict__ r = x + n_max;
+    float *__restrict__ rh = r + n_max;
+    float *__restrict__ p = rh + n_max;
+    float *__restrict__ v = p + n_max;
+    float *__restrict__ tt = v + n_max;
+    const int *__restrict__ t_col = T.a_col;
     // compact L / U planes for the ring sweeps (16-byte aligned: n_max is padded to a multiple of 4 by the host)
     CompactPlanes cpl;
     {
@@ -407,6 +413,7 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_kernel(const BicgPar
 
     // ---- setup: permuted copies, NaN guard (":245-256") ------------------------------------------------------
     double nv = 0.0, nb = 0.0;
+#pragma unroll 8
     for (int i = tid; i < nnz_c; i += NT) { const double a = values_c[i]; nv += a * a; }
     for (int q = tid; q < n; q += NT) {
         const int orig = T.perm[q];
@@ -484,8 +491,17 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_kernel(const BicgPar
         }
     };
     auto spmv_row = [&](const float *vec, int q) {                   // CsrmvEx row: fma in ascending column order
+        float av[kMaxWa];
+        int ac[kMaxWa];
+#pragma unroll
+        for (int k = 0; k < kMaxWa; k++) {                           // all loads first (memory-level parallelism)
+            av[k] = k < wa ? a_val[k * n_max + q] : 0.0f;
+            ac[k] = k < wa ? t_col[k * n + q] : q;
+        }
         float acc = 0.0f;
-        for (int k = 0; k < wa; k++) acc = fmaf(a_val[k * n_max + q], vec[T.a_col[k * n + q]], acc);
+#pragma unroll
+        for (int k = 0; k < kMaxWa; k++)
+            if (k < wa) acc = fmaf(av[k], vec[ac[k]], acc);
         return acc;
     };
 
@@ -499,6 +515,7 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_kernel(const BicgPar
         for (int q = tid; q < n; q += NT) zs[q] = x[q];
         __syncthreads();
         double s0 = 0.0, s1 = 0.0;
+#pragma unroll 4
         for (int q = tid; q < n; q += NT) {
             const float rq = __fsub_rn(b[q], spmv_row(zs, q));
             r[q] = rq; s0 += (double)rq * rq;
@@ -515,6 +532,7 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_kernel(const BicgPar
             rho = rho_next;
             beta = __fmul_rn(__fdiv_rn(rho, rhop), __fdiv_rn(alpha, omega));
             __syncthreads();
+#pragma unroll 4
             for (int q = tid; q < n; q += NT) {                      // p = r + beta (p - omega v)  (":315-317")
                 float pq = fmaf(-omega, v[q], p[q]);
                 pq = __fmul_rn(beta, pq);
@@ -525,6 +543,7 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_kernel(const BicgPar
             __syncthreads();
             DPISO_TICK(2);
             s0 = 0.0; s1 = 0.0;
+#pragma unroll 4
             for (int q = tid; q < n; q += NT) {                      // v = A p_hat ; rh.v
                 const float vq = spmv_row(zs, q);
                 v[q] = vq; s0 += (double)rh[q] * vq;
@@ -532,6 +551,7 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_kernel(const BicgPar
             block_sum2(s0, s1, red);
             alpha = __fdiv_rn(rho, (float)s0);
             s0 = 0.0; s1 = 0.0;
+#pragma unroll 4
             for (int q = tid; q < n; q += NT) {                      // x += alpha p_hat ; r -= alpha v ; |r|
                 x[q] = fmaf(alpha, zs[q], x[q]);
                 const float rq = fmaf(-alpha, v[q], r[q]);
@@ -545,6 +565,7 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_kernel(const BicgPar
             __syncthreads();
             DPISO_TICK(2);
             s0 = 0.0; s1 = 0.0;
+#pragma unroll 4
             for (int q = tid; q < n; q += NT) {                      // t = A s_hat ; t.r ; t.t
                 const float tq = spmv_row(zs, q);
                 tt[q] = tq; s0 += (double)tq * r[q]; s1 += (double)tq * tq;
@@ -552,6 +573,7 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_kernel(const BicgPar
             block_sum2(s0, s1, red);
             omega = __fdiv_rn((float)s0, (float)s1);
             s0 = 0.0; s1 = 0.0;
+#pragma unroll 4
             for (int q = tid; q < n; q += NT) {                      // x += omega s_hat ; r -= omega t ; |r| ; r.rh
                 x[q] = fmaf(omega, zs[q], x[q]);
                 const float rq = fmaf(-omega, tt[q], r[q]);
