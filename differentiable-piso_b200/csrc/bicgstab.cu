@@ -331,16 +331,27 @@ __device__ __noinline__ void wavefront_ring(const BicgTab &T, int lp_cap, const 
         };
 #pragma unroll 1
         for (int s = 0; s < D; s++) issue(s);
+        // software pipeline: the row of the NEXT level is pulled from the ring into registers before the level barrier
+        int q = -1;
+        int4 c4 = make_int4(0, 0, 0, 0);
+        float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float e = 1.0f;
+        auto pull = [&](int s) {                                       // ring slot of step s -> registers
+            q = -1;
+            if (s < nl) {
+                const int d = MODE == 2 ? nl - 1 - s : s;
+                const int qq = lp[d] + t;
+                if (qq < lp[d + 1]) {
+                    const int slot = (s & (D - 1)) * P + t;
+                    q = qq; c4 = rc[slot]; v4 = rv[slot]; e = re[slot];
+                }
+            }
+        };
+        cp_async_wait<D - 1>();                                        // step 0 has landed
+        pull(0);
 #pragma unroll 1
         for (int s = 0; s < nl; s++) {
-            cp_async_wait<D - 1>();                                    // this thread's row of step s has landed
-            const int d = MODE == 2 ? nl - 1 - s : s;
-            const int q = lp[d] + t;
-            if (q < lp[d + 1]) {
-                const int slot = (s & (D - 1)) * P + t;
-                const int4 c4 = rc[slot];
-                const float4 v4 = rv[slot];
-                const float e = re[slot];
+            if (q >= 0) {
                 float acc = MODE == 1 ? e : zs[q];
                 acc = fmaf(-v4.x, zs[c4.x], acc);
                 acc = fmaf(-v4.y, zs[c4.y], acc);
@@ -349,6 +360,8 @@ __device__ __noinline__ void wavefront_ring(const BicgTab &T, int lp_cap, const 
                 zs[q] = MODE == 1 ? acc : __fdiv_rn(acc, e);
             }
             issue(s + D);                                              // refill the slot just consumed
+            cp_async_wait<D - 1>();                                    // step s+1 has landed (issued D levels ago)
+            pull(s + 1);
             named_bar(1, P);
         }
         cp_async_wait<0>();
