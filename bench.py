@@ -72,6 +72,21 @@ def _cpu_worker(args):
     return time.perf_counter() - t0
 
 
+def usable_cores():
+    """Host cores this process may actually use: scheduler affinity, capped by the cgroup CPU quota if one is set."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period))))
+    except (OSError, ValueError):
+        pass
+    return n
+
+
 def cpu_throughput(cores, steps_per_core, adjoint=True):
     """cell-updates/s of the oracle port: `cores` independent samples in parallel, `steps_per_core` steps each."""
     import multiprocessing as mp
@@ -91,7 +106,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     total = args.warmup + args.steps
     per_step = []
     # each "step" = every core advances one sample by one fwd+adjoint step (bounded sample of the 64-sample batch)

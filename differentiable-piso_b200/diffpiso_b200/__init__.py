@@ -3,6 +3,8 @@ surface.  Importing this package loads libdpiso.so (sm_100a kernels); there is n
 from . import _native
 from .grids import (CenteredGrid, StaggeredGrid, flatten_staggered_data, stack_staggered_components,
                     stagger_flattened_data, unstack_staggered_tensor)
+from .helpers import (arrange_rhs_term, custom_padded, explicit_H_csr, finite_volume_divergence,
+                      finite_volume_gradient_tensor)
 from .linear_solver import LinearSolver, LinearSolverCudaBicgstabILU, LinearSolverCudaMultiBicgstabILU
 from .ops import Geometry
 from .piso import SimulationParameters, advection_matrix_cuda, piso_step, pressure_extrapolation
@@ -11,4 +13,5 @@ from .pressure_solver import PisoPressureSolverCudaCustom, PoissonSolver
 __all__ = ["CenteredGrid", "StaggeredGrid", "flatten_staggered_data", "stagger_flattened_data",
            "stack_staggered_components", "unstack_staggered_tensor", "LinearSolver", "LinearSolverCudaBicgstabILU",
            "LinearSolverCudaMultiBicgstabILU", "PisoPressureSolverCudaCustom", "PoissonSolver", "SimulationParameters",
-           "piso_step", "advection_matrix_cuda", "pressure_extrapolation", "Geometry"]
+           "piso_step", "advection_matrix_cuda", "pressure_extrapolation", "Geometry", "custom_padded", "arrange_rhs_term",
+           "finite_volume_gradient_tensor", "finite_volume_divergence", "explicit_H_csr"]

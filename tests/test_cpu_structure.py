@@ -181,3 +181,23 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "piso_oracle" not in txt and "from oracle" not in txt, f
+
+
+@pytest.mark.parametrize("per_y,per_x", [(0, 0), (1, 1), (1, 0), (0, 1)])
+def test_custom_padded_matches_oracle(per_y, per_x):
+    """diffpiso_b200.custom_padded (torch indexing, runs on CPU tensors) == the oracle's restatement of
+    piso_helpers.py:35-55, including the dropped duplicate face on a component's own periodic axis."""
+    import torch
+    import diffpiso_b200 as dp
+    ny, nx = 5, 6
+    rng = np.random.RandomState(0)
+    u = rng.randn(ny, nx + 1).astype(np.float32)
+    v = rng.randn(ny + 1, nx).astype(np.float32)
+    st = dp.stack_staggered_components([torch.as_tensor(v)[None, ..., None], torch.as_tensor(u)[None, ..., None]])
+    vp, up = dp.custom_padded(dp.StaggeredGrid(st), 1, (per_y, per_x))
+    oup, ovp = O.pad_velocity(ny, nx, per_x, per_y, u, v)
+    assert np.array_equal(up[0].numpy(), oup) and np.array_equal(vp[0].numpy(), ovp)
+    flat = dp.flatten_staggered_data(st, coord_flip=True)[0].numpy()
+    assert np.array_equal(flat, np.concatenate([u.ravel(), v.ravel()]))
+    back = dp.stagger_flattened_data(torch.as_tensor(flat), (1, ny + 1, nx + 1, 2), coord_flip=True)
+    assert torch.equal(back, st)
