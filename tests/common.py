@@ -45,7 +45,11 @@ STRIP_SETUPS = {
     "sml32x128": lambda: SU.spatial_mixing_layer(ny=32, nx=128, box=(16.0, 64.0), dt=0.05, solver_precision=1e-6),
     "ldc_like64": lambda: SU.lid_driven_cavity(n=64, re=100.0, dt=0.01, cg_reset=1000, cg_max_it=5000),  # 65 x 64: general path, cluster 2
 }
+# a grid beyond the on-chip capacity of the solver kernels (67 584 cells): global-memory CG variant, BiCGStab with the
+# solve vector in global memory
+LARGE_SETUPS = {"periodic264x256": lambda: SU.periodic_box(264, 256, visc=1e-3)}
 ALL_SETUPS = dict(SMALL_SETUPS)
+ALL_SETUPS.update(LARGE_SETUPS)
 ALL_SETUPS.update(STRIP_SETUPS)
 
 

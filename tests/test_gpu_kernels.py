@@ -154,6 +154,24 @@ def test_pressure_cg_matches_oracle(name, fp64):
             assert rel_l2(x[i], x64) < 1e-1, (name, i, rel_l2(x[i], x64), int(its[i]), oit)
 
 
+def test_pressure_cg_large_grid_global_variant():
+    """A grid whose row blocks do not fit 16 CTAs (264 x 256 = 67 584 cells) takes the global-memory variant of the CG
+    kernel (config variant 6): same control flow, iteration count within the slack, solution within tolerance."""
+    from common import cg_iteration_slack
+    from diffpiso_b200 import ops, setups as SU
+    s = SU.periodic_box(264, 256, visc=1e-3)
+    g, m, a_diag, beta, dx_factor, div = _cg_problem(s, 9, 2)
+    lap = ops.laplace(g, m["active"], m["access"], _t(a_diag), 1, beta, dx_factor, fp64=True)
+    x, its = ops.pressure_cg(g, lap, _t(div), s["cg_tol"], s["cg_max_it"], s["cg_reset"], s["rank_deficient"])
+    assert ops.pressure_cg_config()["variant"] == 6
+    lap_h = lap.cpu().numpy()
+    for i in range(2):
+        ox, oit = O.pressure_cg(s["ny"], s["nx"], True, True, lap_h[i].ravel(), div[i].astype(np.float64), s["cg_tol"],
+                                s["cg_max_it"], s["cg_reset"], True)
+        assert abs(int(its[i]) - oit) <= cg_iteration_slack(s, oit), (int(its[i]), oit)
+        assert rel_l2(x[i].cpu().numpy(), ox.astype(np.float32)) < 3e-5
+
+
 def test_pressure_cg_zero_rhs_and_max_iterations():
     """Edge cases: zero right-hand side returns zeros (documented deviation D1 from the reference's 0/0) and the
     iteration cap is honoured."""

@@ -47,7 +47,7 @@ def run_step(s, sim, vel_flat, pres, forcing=None, full_output=False):
                         viscosity_field=visc_field, forcing_term=forcing, full_output=full_output)
 
 
-@pytest.mark.parametrize("name", list(SMALL_SETUPS) + ["periodic64", "tml64x128", "sml32x128"])
+@pytest.mark.parametrize("name", list(SMALL_SETUPS) + ["periodic64", "tml64x128", "sml32x128", "periodic264x256"])
 def test_piso_step_matches_oracle(name):
     """Three consecutive steps of a batch of 2 seeded samples; every intermediate of the first step and the state after
     each step within 1e-5 relative L2 of the oracle (north_star tolerance), solver iteration counts within +-1
