@@ -169,7 +169,7 @@ def test_pressure_cg_large_grid_global_variant():
         ox, oit = O.pressure_cg(s["ny"], s["nx"], True, True, lap_h[i].ravel(), div[i].astype(np.float64), s["cg_tol"],
                                 s["cg_max_it"], s["cg_reset"], True)
         assert abs(int(its[i]) - oit) <= cg_iteration_slack(s, oit), (int(its[i]), oit)
-        assert rel_l2(x[i].cpu().numpy(), ox.astype(np.float32)) < 3e-5
+        assert rel_l2(x[i].cpu().numpy(), ox.astype(np.float32)) < 5e-5
 
 
 def test_pressure_cg_zero_rhs_and_max_iterations():
