@@ -15,6 +15,8 @@
 //     ever returns to the host; convergence tests, the restart rule and the NaN warning follow the reference.
 // The transposed solve of the adjoint uses tables built for A^T (the reference transposes with csr2csc and
 // factorises again, ":113-134"); the kernels are identical.
+#include <cstdlib>
+
 #include "rows.cuh"
 
 namespace dpiso {
@@ -39,6 +41,7 @@ struct BicgParams {
     int lp_cap;            // ints reserved for the level_ptr copy in smem
     int compact;           // rows have <= 4 lower and <= 4 upper entries: compact triangular sweeps
     int ring_depth;        // levels in flight in the cp.async ring (16, 8 or 2)
+    int dbg;               // profiling experiments only (DPISO_BICG_DBG): 1 skip level barrier, 2 skip refill, 4 skip recurrence
     const float *values, *rhs, *x0;
     float *x;
     int *stats;
@@ -299,7 +302,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 
 template <int MODE, bool kZsSmem, int D>
 __device__ __noinline__ void wavefront_ring(const BicgTab &T, int lp_cap, const CompactPlanes cp, const float *in,
-                                            float *zs_global, int stage_rows) {
+                                            float *zs_global, int stage_rows, int dbg = 0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int *lp = (const int *)smem_raw;
     int *const stage0 = (int *)smem_raw + lp_cap;                      // ring lives in the stage-buffer region
@@ -316,42 +319,38 @@ __device__ __noinline__ void wavefront_ring(const BicgTab &T, int lp_cap, const 
         const int4 *gcol = MODE == 1 ? cp.lcol : cp.ucol;
         const float4 *gval = MODE == 1 ? cp.lval : cp.uval;
         const float *gext = MODE == 1 ? in : cp.udiag;
+        auto row_of = [&](int s) {                                     // this thread's row in sweep step s, or -1
+            if (s >= nl) return -1;
+            const int d = MODE == 2 ? nl - 1 - s : s;
+            const int q = lp[d] + t;
+            return q < lp[d + 1] ? q : -1;
+        };
         auto issue = [&](int s) {                                      // sweep step s -> ring slot s % D
-            if (s < nl) {
-                const int d = MODE == 2 ? nl - 1 - s : s;
-                const int q = lp[d] + t;
-                if (q < lp[d + 1]) {
-                    const int slot = (s & (D - 1)) * P + t;
-                    cp_async16(rc + slot, gcol + q);
-                    cp_async16(rv + slot, gval + q);
-                    cp_async4(re + slot, gext + q);
-                }
+            const int q = row_of(s);
+            if (q >= 0) {
+                const int slot = (s & (D - 1)) * P + t;
+                cp_async16(rc + slot, gcol + q);
+                cp_async16(rv + slot, gval + q);
+                cp_async4(re + slot, gext + q);
             }
             cp_async_commit();
         };
+        // D-1 steps in flight; at step s the slot consumed at step s-1 is refilled FIRST (its latency and the row lookup
+        // of the next step overlap the recurrence), then the dependent chain of the level runs:
+        //     LDS ring slot -> LDS zs[col] x4 -> 4 fma (-> div) -> STS -> bar.sync
 #pragma unroll 1
-        for (int s = 0; s < D; s++) issue(s);
-        // software pipeline: the row of the NEXT level is pulled from the ring into registers before the level barrier
-        int q = -1;
-        int4 c4 = make_int4(0, 0, 0, 0);
-        float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        float e = 1.0f;
-        auto pull = [&](int s) {                                       // ring slot of step s -> registers
-            q = -1;
-            if (s < nl) {
-                const int d = MODE == 2 ? nl - 1 - s : s;
-                const int qq = lp[d] + t;
-                if (qq < lp[d + 1]) {
-                    const int slot = (s & (D - 1)) * P + t;
-                    q = qq; c4 = rc[slot]; v4 = rv[slot]; e = re[slot];
-                }
-            }
-        };
-        cp_async_wait<D - 1>();                                        // step 0 has landed
-        pull(0);
+        for (int s = 0; s < D - 1; s++) issue(s);
+        int q = row_of(0);
 #pragma unroll 1
         for (int s = 0; s < nl; s++) {
-            if (q >= 0) {
+            if (!(dbg & 2)) issue(s + D - 1); else cp_async_commit();
+            const int q_next = row_of(s + 1);
+            cp_async_wait<D - 1>();                                    // this thread's row of step s has landed
+            if (q >= 0 && !(dbg & 4)) {
+                const int slot = (s & (D - 1)) * P + t;
+                const int4 c4 = rc[slot];
+                const float4 v4 = rv[slot];
+                const float e = re[slot];
                 float acc = MODE == 1 ? e : zs[q];
                 acc = fmaf(-v4.x, zs[c4.x], acc);
                 acc = fmaf(-v4.y, zs[c4.y], acc);
@@ -359,10 +358,8 @@ __device__ __noinline__ void wavefront_ring(const BicgTab &T, int lp_cap, const 
                 acc = fmaf(-v4.w, zs[c4.w], acc);
                 zs[q] = MODE == 1 ? acc : __fdiv_rn(acc, e);
             }
-            issue(s + D);                                              // refill the slot just consumed
-            cp_async_wait<D - 1>();                                    // step s+1 has landed (issued D levels ago)
-            pull(s + 1);
-            named_bar(1, P);
+            if (!(dbg & 1)) named_bar(1, P);
+            q = q_next;
         }
         cp_async_wait<0>();
     }
@@ -483,14 +480,14 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_kernel(const BicgPar
     auto precondition = [&](const float *src) {                      // zs = U^-1 L^-1 src   (csrsv2 x2, ":321-327")
         if (fast && zsm && prm.compact) {
             if (prm.ring_depth == 16) {
-                wavefront_ring<1, true, 16>(T, prm.lp_cap, cpl, src, zs_glob, prm.stage_rows);
-                wavefront_ring<2, true, 16>(T, prm.lp_cap, cpl, nullptr, zs_glob, prm.stage_rows);
+                wavefront_ring<1, true, 16>(T, prm.lp_cap, cpl, src, zs_glob, prm.stage_rows, prm.dbg);
+                wavefront_ring<2, true, 16>(T, prm.lp_cap, cpl, nullptr, zs_glob, prm.stage_rows, prm.dbg);
             } else if (prm.ring_depth == 8) {
-                wavefront_ring<1, true, 8>(T, prm.lp_cap, cpl, src, zs_glob, prm.stage_rows);
-                wavefront_ring<2, true, 8>(T, prm.lp_cap, cpl, nullptr, zs_glob, prm.stage_rows);
+                wavefront_ring<1, true, 8>(T, prm.lp_cap, cpl, src, zs_glob, prm.stage_rows, prm.dbg);
+                wavefront_ring<2, true, 8>(T, prm.lp_cap, cpl, nullptr, zs_glob, prm.stage_rows, prm.dbg);
             } else {
-                wavefront_ring<1, true, 2>(T, prm.lp_cap, cpl, src, zs_glob, prm.stage_rows);
-                wavefront_ring<2, true, 2>(T, prm.lp_cap, cpl, nullptr, zs_glob, prm.stage_rows);
+                wavefront_ring<1, true, 2>(T, prm.lp_cap, cpl, src, zs_glob, prm.stage_rows, prm.dbg);
+                wavefront_ring<2, true, 2>(T, prm.lp_cap, cpl, nullptr, zs_glob, prm.stage_rows, prm.dbg);
             }
         } else if (fast && zsm) {
             wavefront_staged<1, true>(T, prm.lp_cap, n_max, lu, nullptr, nullptr, src, zs_glob, prm.stage_rows);
@@ -656,6 +653,7 @@ int dpiso_bicgstab_ilu(int batch, const dpiso_bicg_tables *h_tab_u, const dpiso_
     prm.values = values; prm.rhs = rhs; prm.x0 = x0; prm.x = x; prm.stats = stats; prm.warn = warn;
     prm.workspace = workspace; prm.tol = tol; prm.max_it = max_it;
     prm.timing = g_bicg_timing;
+    { const char *e = getenv("DPISO_BICG_DBG"); prm.dbg = e ? atoi(e) : 0; }
     // shared memory plan: level_ptr copy + two stage buffers (staged wavefront) + the solve vector zs
     const size_t kBudget = 200 * 1024;
     const int max_level = h_tab_u->max_level > h_tab_v->max_level ? h_tab_u->max_level : h_tab_v->max_level;
