@@ -329,13 +329,15 @@ def run_ours(args):
         "e2e": {"value": cells * args.steps / (ms_e2e * 1e-3), "unit": "cell-updates/s",
                 "h2d_bytes_per_step": int(BATCH * (nf + nc) * 4), "d2h_bytes_per_step": int(2 * BATCH * (nf + nc) * 4)},
         "gpu_launches": n_launch,
-        "roofline": {"bound": "hbm", "kernel": "pressure_cg_kernel<double,float,4,...> (4 launches per fwd+adjoint step)",
+        "roofline": {"bound": "hbm", "kernel": "pressure_cg_kernel<double,float,%d threads,%d cells/thread> cluster %d (4 launches per fwd+adjoint step)" % (cfg["threads"], cfg["cells_per_thread"], cfg["cluster"]),
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                      "algorithmic_bytes_per_launch": bytes_per_launch, "mean_cg_iterations": mean_it,
                      "avg_launch_ms": cg_avg_ms, "cg_share_of_step": float(sum(cg_ms) / ms),
-                     "note": "state is register/smem resident: algorithmic HBM model of SURVEY 8(d) is exceeded by "
-                             "design; traffic = ncu-measured DRAM bytes per launch"},
+                     "note": "solver state is register/smem resident for the whole solve, so the algorithmic HBM model "
+                             "of SURVEY 8(d) (168 B/cell/iteration) is exceeded by design (frac > 1); traffic = "
+                             "ncu-measured DRAM bytes per launch (profiles/cg_dram_traffic.json); the kernel is bound "
+                             "by issue slots and reduction latency, see profiles/r01_summary.md"},
         "clocks": clocks, "finite": finite,
     }
     if args.cpu_baseline:

@@ -59,6 +59,6 @@ def test_oracle_pressure_solve_equals_reference_golden(path):
                           s["rank_deficient"])
     if prec == "f64":
         assert abs(it - int(g["iterations"])) <= cg_iteration_slack(s, it), (it, int(g["iterations"]))
-        assert rel_l2(x, g["x"]) < max(2e-5, 300 * tol)
+        assert rel_l2(x, g["x"]) < max(2e-5, 1000 * tol)
     else:
         assert rel_l2(x, g["x"]) < 5e-2

@@ -140,7 +140,7 @@ def test_pressure_cg_matches_oracle(name, fp64):
             assert abs(int(its[i]) - oit) <= cg_iteration_slack(s, oit), (name, i, int(its[i]), oit)
             # both sides stop on |r|_inf < tol at (possibly) different iterates: error in x ~ tol * cond
             slack = 2e-4 if s["cg_reset"] <= 10 else 3e-5      # restarted CG stops further from the fixed point
-            assert rel_l2(x[i], ox.astype(np.float32)) < max(slack, 300 * tol), (name, i)
+            assert rel_l2(x[i], ox.astype(np.float32)) < max(slack, 1000 * tol), (name, i)
             # x is returned in fp32 (the reference casts the fp64 result), which bounds the attainable residual
             bound = 10 * tol + 2e-6 * np.abs(x[i]).max() * np.abs(lap_h[i][:, 2]).max()
             assert cg_residual_inf(s, lap_h[i], x[i], div[i]) < bound

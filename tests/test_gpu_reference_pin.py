@@ -123,7 +123,7 @@ def test_oracle_pressure_solve_equals_reference_kernels(ref, name, fp64):
     if fp64:
         from common import cg_iteration_slack
         assert abs(it - oit) <= cg_iteration_slack(s, oit), (name, it, oit)
-        assert rel_l2(ox, x) < max(2e-5, 300 * tol), rel_l2(ox, x)
+        assert rel_l2(ox, x) < max(2e-5, 1000 * tol), rel_l2(ox, x)
     else:
         assert rel_l2(ox, x) < 5e-2, (rel_l2(ox, x), it, oit)
     np.savez_compressed(os.path.join(OUT, "pressure_%s_%s.npz" % (name, "f64" if fp64 else "f32")), k_vu=k_vu, div=div,
