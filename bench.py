@@ -186,7 +186,7 @@ def run_ours(args):
                                   s["accessible_mask"], bool_periodic=(True, True), no_slip_mask=s["no_slip_mask"],
                                   viscosity=float(s["visc"]), linear_solver=ls, pressure_solver=ps)
     vel_h, pres_h = initial_state(s, BATCH, 1234 + rank * BATCH)
-    box = (NY * s["dy"], NX * s["dx"])
+    dxy = (s["dy"], s["dx"])
     dvals = torch.zeros(1, nf, device=dev)
     rng = np.random.RandomState(99 + rank)
     w_u = torch.as_tensor(rng.randn(BATCH, nf).astype(np.float32)).to(dev)
@@ -197,8 +197,8 @@ def run_ours(args):
         """forward + adjoint of one PISO step; returns the new state and the input gradients"""
         vel = vel.detach().requires_grad_(True)
         pres = pres.detach().requires_grad_(True)
-        velocity = dp.StaggeredGrid(flat=vel, resolution=(NY, NX), box=box, extrapolation="periodic")
-        pressure = dp.CenteredGrid(pres.reshape(BATCH, NY, NX, 1), box=box, extrapolation="periodic")
+        velocity = dp.StaggeredGrid(flat=vel, resolution=(NY, NX), dx=dxy, extrapolation="periodic")
+        pressure = dp.CenteredGrid(pres.reshape(BATCH, NY, NX, 1), dx=dxy, extrapolation="periodic")
         v_new, p_new, warn = dp.piso_step(velocity, pressure, pressure, pressure, s["dt"], sim, dvals)
         loss = (v_new.flat * w_u).sum() + (p_new.data.reshape(BATCH, nc) * w_p).sum()
         gv, gp = torch.autograd.grad(loss, (vel, pres))
@@ -259,8 +259,8 @@ def run_ours(args):
     f0.record()
     with torch.no_grad():
         for _ in range(args.steps):
-            velocity = dp.StaggeredGrid(flat=vf, resolution=(NY, NX), box=box, extrapolation="periodic")
-            pressure = dp.CenteredGrid(pf.reshape(BATCH, NY, NX, 1), box=box, extrapolation="periodic")
+            velocity = dp.StaggeredGrid(flat=vf, resolution=(NY, NX), dx=dxy, extrapolation="periodic")
+            pressure = dp.CenteredGrid(pf.reshape(BATCH, NY, NX, 1), dx=dxy, extrapolation="periodic")
             v_new, p_new, _ = dp.piso_step(velocity, pressure, pressure, pressure, s["dt"], sim, dvals)
             vf, pf = v_new.flat, p_new.data.reshape(BATCH, nc)
     f1.record()

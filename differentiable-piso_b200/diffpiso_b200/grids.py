@@ -82,7 +82,44 @@ def extrapolation_codes(extrapolation):
     return codes
 
 
+_TORCH_PAD = {"boundary": "replicate", "constant": "constant", "periodic": "circular"}
+
+
+def pad_with_extrapolation(data, widths, extrapolation):
+    """Pad [B, ny, nx, C] along y and x by widths [[lo, hi], [lo, hi]], each side with its own PhiFlow extrapolation
+    ('boundary' -> replicate, 'constant' -> 0, 'periodic' -> wrap; grid.py:257-281, backend pad modes)."""
+    modes = _side_modes(extrapolation)
+    t = data
+    for axis in (0, 1):
+        dim = 1 + axis
+        n = t.shape[dim]
+        for side, width in enumerate(widths[axis]):
+            if width == 0:
+                continue
+            mode = modes[axis][side]
+            if mode not in _TORCH_PAD:
+                raise ValueError("unknown extrapolation %r" % (mode,))
+            if mode == "constant":
+                shape = list(t.shape)
+                shape[dim] = width
+                piece = t.new_zeros(shape)
+            elif mode == "boundary":
+                edge = t.narrow(dim, 0 if side == 0 else t.shape[dim] - 1, 1)
+                piece = edge.expand(*[width if d == dim else -1 for d in range(t.dim())])
+            else:
+                # wrap relative to the unpadded extent (lower side was possibly padded already)
+                off = widths[axis][0] if side == 1 else 0
+                start = (n - width) if side == 0 else off
+                piece = t.narrow(dim, start, width)
+            t = torch.cat([piece, t] if side == 0 else [t, piece], dim=dim)
+    return t
+
+
 class _Grid(object):
+    """As in PhiFlow the box size is an fp32 number (AABox stores fp32) and dx = size / resolution is formed from it in
+    fp64 (fp32 array / int64 array); every constant of the step derives from this dx (piso_tf.py:26,53,96-97), pinned
+    against the reference's Python by tests/golden/ref_python/step_*.npz.  A dx given explicitly is taken as is."""
+
     def _init_box(self, resolution, box, dx):
         res = np.asarray(resolution, dtype=np.float64)
         if dx is not None:
@@ -96,7 +133,7 @@ class _Grid(object):
             else:
                 size = np.asarray(box.size, dtype=np.float64) * np.ones(2)    # AABox-like
             self.box = size
-            self.dx = size / res
+            self.dx = size.astype(np.float32).astype(np.float64) / res
 
 
 class CenteredGrid(_Grid):
@@ -105,8 +142,8 @@ class CenteredGrid(_Grid):
 
     def __init__(self, data, box=None, extrapolation="boundary", dx=None, name=None):
         self.data = as_tensor(data)
-        if self.data.dim() != 4 or self.data.shape[-1] != 1:
-            raise ValueError("centred data must be [B, ny, nx, 1]")
+        if self.data.dim() != 4:
+            raise ValueError("centred data must be [B, ny, nx, C]")
         self.extrapolation = extrapolation
         self.name = name
         self._init_box(self.data.shape[1:3], box, dx)
@@ -116,11 +153,44 @@ class CenteredGrid(_Grid):
         return tuple(self.data.shape[1:3])
 
     def copied_with(self, data):
-        return CenteredGrid(data, box=self.box, extrapolation=self.extrapolation)
+        return CenteredGrid(data, box=self.box, dx=self.dx, extrapolation=self.extrapolation)
 
     def __add__(self, other):
         o = other.data if isinstance(other, CenteredGrid) else other
         return self.copied_with(self.data + o)
+
+    def padded(self, widths):
+        """PhiFlow/phi/physics/field/grid.py:188-194: pad the spatial axes with the grid's extrapolation."""
+        if isinstance(widths, int):
+            widths = [[widths, widths]] * 2
+        return CenteredGrid(pad_with_extrapolation(self.data, widths, self.extrapolation), dx=self.dx,
+                            extrapolation=self.extrapolation)
+
+    def gradient(self, physical_units=True, difference="central"):
+        """grid.py:218-223 / math/nd.py:186-216: finite-difference gradient of a scalar field, channels (d/dy, d/dx);
+        the closure network's pressure input (combined_training_integrated.py:401-405)."""
+        if self.data.shape[-1] != 1:
+            raise ValueError("gradient needs a scalar field")
+        if not np.allclose(self.dx, np.mean(self.dx)):
+            raise NotImplementedError("Only cubic cells supported.")
+        lo, hi, div = {"central": (1, 1, 2.0), "forward": (0, 1, 1.0), "backward": (1, 0, 1.0)}[difference.lower()]
+        t = pad_with_extrapolation(self.data, [[lo, hi], [lo, hi]], self.extrapolation)
+        ny, nx = self.data.shape[1:3]
+        gy = t[:, lo + hi:lo + hi + ny, lo:lo + nx] - t[:, 0:ny, lo:lo + nx]
+        gx = t[:, lo:lo + ny, lo + hi:lo + hi + nx] - t[:, lo:lo + ny, 0:nx]
+        scale = float(np.mean(self.dx)) * div if physical_units else div
+        return CenteredGrid(torch.cat([gy, gx], dim=-1) / scale, dx=self.dx, extrapolation=self.extrapolation)
+
+    def at_faces(self, component):
+        """`CenteredGrid.at(velocity.data[component])` (grid.py:108-130 -> linear resampling with this grid's
+        extrapolation): values on the v faces [B, ny+1, nx, C] (component 0) or the u faces [B, ny, nx+1, C]
+        (component 1) as the mean of the two adjacent cells; how the closure forcing reaches the faces
+        (combined_training_integrated.py:407-410)."""
+        w = [[1, 1], [0, 0]] if component == 0 else [[0, 0], [1, 1]]
+        t = pad_with_extrapolation(self.data, w, self.extrapolation)
+        if component == 0:
+            return 0.5 * (t[:, 1:] + t[:, :-1])
+        return 0.5 * (t[:, :, 1:] + t[:, :, :-1])
 
 
 class StaggeredGrid(_Grid):
@@ -164,5 +234,19 @@ class StaggeredGrid(_Grid):
         return self._flat
 
     def copied_with(self, data=None, flat=None):
-        return StaggeredGrid(data, box=self.box, extrapolation=self.extrapolation, flat=flat,
+        return StaggeredGrid(data, box=self.box, dx=self.dx, extrapolation=self.extrapolation, flat=flat,
                              resolution=self._resolution)
+
+    @property
+    def data(self):
+        """[v, u] component grids as in PhiFlow (`velocity.data[1].data` = u faces [B, ny, nx+1, 1])."""
+        v, u = unstack_staggered_tensor(self.staggered_tensor())
+        return [CenteredGrid(v, dx=self.dx, extrapolation=self.extrapolation),
+                CenteredGrid(u, dx=self.dx, extrapolation=self.extrapolation)]
+
+    def at_centers(self):
+        """staggered_grid.py:150-151: both components linearly resampled at the cell centres -> CenteredGrid with
+        data [B, ny, nx, 2] (channel 0 = v, 1 = u)."""
+        v, u = unstack_staggered_tensor(self.staggered_tensor())
+        c = torch.cat([0.5 * (v[:, 1:] + v[:, :-1]), 0.5 * (u[:, :, 1:] + u[:, :, :-1])], dim=-1)
+        return CenteredGrid(c, dx=self.dx, extrapolation=self.extrapolation)

@@ -56,6 +56,12 @@ def stagger_flat(flat, ny, nx, coord_flip=True):
     return stack_staggered(v.reshape(-1, ny + 1, nx), u.reshape(-1, ny, nx + 1))
 
 
+def spacing(length, n):
+    """dx of a PhiFlow Domain: the box size is stored in fp32, dx = size / resolution is formed in fp64
+    (PhiFlow/phi/physics/field/grid.py:87-89); every reference script gets its spacings this way."""
+    return float(np.float32(length)) / n
+
+
 def _base(ny, nx, dy, dx, dt, per_y, per_x):
     return dict(ny=ny, nx=nx, dy=float(dy), dx=float(dx), dt=float(dt), per_y=bool(per_y), per_x=bool(per_x))
 
@@ -87,7 +93,7 @@ def lid_driven_cavity(n=32, re=100.0, dt=0.01, bicg_tol=1e-8, bicg_max_it=100, c
                       cg_reset=10):
     """lid_driven_cavity_2d.py:10-47 (Domain([N+1, N]); the top cell row is a ghost lid row)."""
     ny, nx = n + 1, n
-    s = _base(ny, nx, 1.0 / n, 1.0 / n, dt, False, False)
+    s = _base(ny, nx, spacing(1.0 + 1.0 / n, ny), spacing(1.0, nx), dt, False, False)   # box[0:1+1/N, 0:1]
     dm_v = np.zeros((1, ny + 1, nx), np.float32)
     dm_v[:, 0] = 1
     dm_v[:, -2:] = 1
@@ -115,7 +121,7 @@ def lid_driven_cavity(n=32, re=100.0, dt=0.01, bicg_tol=1e-8, bicg_max_it=100, c
 def periodic_box(ny=128, nx=128, length=2 * math.pi, visc=1e-3, dt=None, cfl=0.5, umax=1.0, bicg_tol=1e-8,
                  bicg_max_it=10000, cg_tol=1e-8, cg_max_it=10000, cg_reset=1000, cg_fp64=True):
     """Fully periodic box (C2 / C5 of BASELINE.json).  All masks 1, no Dirichlet faces."""
-    dy, dx = length / ny, length / nx
+    dy, dx = spacing(length, ny), spacing(length, nx)
     if dt is None:
         dt = cfl * min(dy, dx) / umax
     s = _base(ny, nx, dy, dx, dt, True, True)
@@ -133,7 +139,7 @@ def temporal_mixing_layer(ny=128, nx=256, ly=None, lx=None, visc=2e-3, dt=0.05, 
     """Periodic in x, walls (v Dirichlet 0) in y -- masks of piso_helpers.py:136-166."""
     ly = float(ny) if ly is None else ly
     lx = float(nx) if lx is None else lx
-    s = _base(ny, nx, ly / ny, lx / nx, dt, False, True)
+    s = _base(ny, nx, spacing(ly, ny), spacing(lx, nx), dt, False, True)
     dm_v = np.zeros((1, ny + 1, nx), np.float32)
     dm_v[:, 0] = 1
     dm_v[:, -1] = 1
@@ -157,7 +163,7 @@ def spatial_mixing_layer(ny=128, nx=512, box=(64.0, 256.0), visc=0.002, sponge_r
     column 0, free outflow.  Viscosity is a per-face field with a linear sponge ramp.
     """
     ly, lx = box
-    s = _base(ny, nx, ly / ny, lx / nx, dt, False, False)
+    s = _base(ny, nx, spacing(ly, ny), spacing(lx, nx), dt, False, False)
     inlet = velocity_difference / 2 * np.tanh(sharpness * (np.linspace(0, ly, ny + 2) - ly / 2)) + average_velocity
     if perturbation is not None:
         inlet = inlet + perturbation

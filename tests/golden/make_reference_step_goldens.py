@@ -1,0 +1,140 @@
+"""Golden vectors of ONE PISO step, forward and backward, produced by the reference's own Python (see
+reference_runner.py for how it is executed without tensorflow).  Build container only:
+
+    python tests/golden/make_reference_step_goldens.py
+
+Writes tests/golden/ref_python/step_<setup>.npz: the seeded inputs, the 17 `full_output` results of
+`diffpiso.piso_tf.piso_step`, the arguments its Python handed to the three native ops, and the gradients of
+loss = <w_u, u_next> + <w_p, p_next> w.r.t. velocity, pressure, forcing term and Dirichlet values that the reference's
+registered gradients produce."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "differentiable-piso_b200"), HERE]
+
+from oracle import oracle as O                      # noqa: E402
+import reference_runner as RR                       # noqa: E402
+
+OUT = os.path.join(HERE, "ref_python")
+SETUPS = ["ldc8", "periodic16", "periodic24x20", "tml16x24", "sml16x48"]
+
+
+def _material(ns, code):
+    return {0: ns["OPEN"], 1: ns["CLOSED"], 2: ns["PERIODIC"]}[code]
+
+
+def reference_objects(ns, s):
+    """Domain, SimulationParameters and solver objects of the reference for one of our setup dicts."""
+    pbc = s["pbc"]
+    boundaries = ((_material(ns, pbc[0]), _material(ns, pbc[1])), (_material(ns, pbc[2]), _material(ns, pbc[3])))
+    ny, nx = s["ny"], s["nx"]
+    domain = ns["Domain"]([ny, nx], box=ns["box"][0:ny * s["dy"], 0:nx * s["dx"]], boundaries=boundaries)
+    ls = ns["LinearSolverCudaMultiBicgstabILU"](accuracy=s["bicg_tol"], max_iterations=s["bicg_max_it"], cast_to_double=False)
+    ps = ns["PisoPressureSolverCudaCustom"](dx=[], accuracy=s["cg_tol"], max_iterations=s["cg_max_it"],
+                                             residual_reset=s["cg_reset"], randomized_restarts=0,
+                                             cast_to_double=s.get("cg_fp64", True))
+    visc = s["visc"]
+    sim = ns["SimulationParameters"](dirichlet_mask=s["dirichlet_mask"].astype(bool),
+                                     dirichlet_values=s["dirichlet_values_staggered"],
+                                     active_mask=s["active_mask"], accessible_mask=s["accessible_mask"],
+                                     bool_periodic=(s["per_y"], s["per_x"]), no_slip_mask=s["no_slip_mask"],
+                                     viscosity=float(np.atleast_1d(visc)[0]), linear_solver=ls, pressure_solver=ps)
+    return domain, sim
+
+
+def run_reference_step(ns, log, s, vel_flat, pres, forcing_flat, w_u, w_p):
+    from diffpiso_b200 import setups as SU
+    ny, nx = s["ny"], s["nx"]
+    domain, sim = reference_objects(ns, s)
+    vel_t = RR.tf_tensor(SU.stagger_flat(vel_flat[None], ny, nx), True)
+    pres_t = RR.tf_tensor(pres.reshape(1, ny, nx, 1).copy(), True)
+    force_t = RR.tf_tensor(SU.stagger_flat(forcing_flat[None], ny, nx), True)
+    dvals_t = RR.tf_tensor(s["dirichlet_values_staggered"].copy(), True)
+    velocity = ns["StaggeredGrid"].sample(vel_t, domain=domain)
+    pressure = ns["CenteredGrid"](pres_t, box=domain.box, extrapolation=ns["pressure_extrapolation"](domain.boundaries))
+    # increments as in run_piso_steps (combined_training_integrated.py:419-420); their values are ignored (Q1)
+    # (there the grids get the default 'boundary' extrapolation, lid_driven_cavity_2d.py:55-56 passes the pressure's;
+    # the setup's `pbc_inc` says which one the case uses)
+    mode = {0: "boundary", 1: "constant", 2: "periodic"}
+    pi = s["pbc_inc"]
+    inc_ext = ((mode[pi[0]], mode[pi[1]]), (mode[pi[2]], mode[pi[3]]))
+    inc1 = ns["CenteredGrid"](torch.zeros_like(pres_t) + 5e-13, pressure.box, extrapolation=inc_ext)
+    inc2 = ns["CenteredGrid"](torch.zeros_like(pres_t) + 1e-12, pressure.box, extrapolation=inc_ext)
+    visc_field = None
+    if np.atleast_1d(s["visc"]).size > 1:
+        visc_field = RR.tf_tensor(np.asarray(s["visc"], np.float32))
+    log.calls.clear()
+    out = ns["piso_step"](velocity, pressure, inc1, inc2, s["dt"], sim, dvals_t, viscosity_field=visc_field,
+                          forcing_term=force_t, unrolling_step=0, full_output=True)
+    v_next = out[0].staggered_tensor()
+    p_next = out[1].data
+    fwd_calls = list(log.calls)
+    wu_t = RR.tf_tensor(SU.stagger_flat(w_u[None], ny, nx))
+    wp_t = RR.tf_tensor(w_p.reshape(1, ny, nx, 1))
+    loss = (v_next * wu_t).sum() + (p_next * wp_t).sum()
+    loss.backward()
+    bwd_calls = log.calls[len(fwd_calls):]
+
+    def flat(t):
+        return SU.flatten_staggered(t.detach().numpy())[0].astype(np.float32)
+
+    def tens(x):
+        return x.detach().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+    asm = [kw for n, kw in fwd_calls if n == "assemble"][0]
+    res = dict(
+        vel=vel_flat, pres=pres, forcing=forcing_flat, w_u=w_u, w_p=w_p,
+        vel_next=flat(v_next), pres_next=tens(p_next).ravel(), p1=tens(out[2].data).ravel(), p2=tens(out[3].data).ravel(),
+        values=tens(out[4]), col_ind=tens(out[5]), row_ptr=tens(out[6]), u_star=flat(out[7]), u_s2=flat(out[8]),
+        a_diag=tens(out[9]), rhs=tens(out[10]), div1=tens(out[13]).ravel(), lap1=tens(out[14]), lap2=tens(out[15]),
+        warn=tens(out[16]).astype(np.float32),
+        velocity_padded=asm["velocity_padded"], cell_area=asm["cell_area"], grid_spacing=asm["grid_spacing"],
+        beta=np.float64(asm["beta"]), dy=np.float64(domain.dx[0]), dx=np.float64(domain.dx[1]),
+        pressure_extrapolation=np.array(str(pressure.extrapolation)), velocity_extrapolation=np.array(str(velocity.extrapolation)),
+        k_faces=[kw for n, kw in fwd_calls if n == "pressure"][0]["k_faces"],
+        div2=[kw for n, kw in fwd_calls if n == "pressure"][1]["div"].ravel(),
+        cg_iterations=np.array([kw["iterations"][0] for n, kw in fwd_calls if n == "pressure"]),
+        bicg_iterations=np.array([st["iterations"] for n, kw in fwd_calls if n == "bicgstab" for st in kw["stats"]]),
+        g_vel=flat(vel_t.grad), g_pres=tens(pres_t.grad).ravel(), g_forcing=flat(force_t.grad), g_dvals=flat(dvals_t.grad),
+        bwd_ops=np.array([n + (":T" if kw.get("transpose") else "") for n, kw in bwd_calls]),
+        bwd_bicg_x0=[kw for n, kw in bwd_calls if n == "bicgstab"][0]["x0"],
+        bwd_bicg_rhs=[kw for n, kw in bwd_calls if n == "bicgstab"][0]["rhs"],
+        bwd_cg_rhs=np.stack([kw["div"].ravel() for n, kw in bwd_calls if n == "pressure"]),
+        bwd_cg_iterations=np.array([kw["iterations"][0] for n, kw in bwd_calls if n == "pressure"]),
+    )
+    return res
+
+
+def inputs_for(s, seed=50):
+    """Same recipe as tests/test_gpu_adjoint.py::test_piso_step_backward_matches_oracle (sample 0)."""
+    from common import random_fields
+    ny, nx = s["ny"], s["nx"]
+    nf, nc = ny * (nx + 1) + (ny + 1) * nx, ny * nx
+    rng = np.random.RandomState(5)
+    vel, pres = random_fields(s, seed)
+    forcing = (rng.randn(2, nf) * 0.01).astype(np.float32)[0]
+    w_u, w_p = rng.randn(2, nf).astype(np.float32)[0], rng.randn(2, nc).astype(np.float32)[0]
+    if s["rank_deficient"]:
+        act = s["active"].reshape(ny + 2, nx + 2)[1:-1, 1:-1].ravel() != 0
+        w_p[~act] = 0
+        w_p[act] -= w_p[act].mean()
+    return vel, pres, forcing, w_u, w_p
+
+
+def main():
+    from common import SMALL_SETUPS
+    os.makedirs(OUT, exist_ok=True)
+    ns, log = RR.load_reference(O)
+    for name in SETUPS:
+        s = SMALL_SETUPS[name]()
+        res = run_reference_step(ns, log, s, *inputs_for(s))
+        np.savez_compressed(os.path.join(OUT, "step_%s.npz" % name), **res)
+        print(name, "cg", res["cg_iterations"], "bicg", res["bicg_iterations"], "bwd", list(res["bwd_ops"]))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,114 @@
+"""CPU suite: the oracle against golden vectors produced by the REFERENCE'S OWN PYTHON executed in the build container
+(tests/golden/reference_runner.py: `diffpiso.piso_tf.piso_step`, the solver classes' `solve`, the helper functions and
+every registered `grad` closure run unmodified on PhiFlow's torch backend; only the three CUDA op libraries are replaced
+by callables with the ops' argument lists).  This pins
+
+* the Python glue of the step (padding, flattening orders, signs/scalings of predictor rhs and both correctors, H
+  application, pressure accumulation, the constants beta / cell_area / grid_spacing / dx_factor): BIT-EXACT,
+* the backward pass TF assembles from the registered gradients (op order, transposed predictor solve started from the
+  forward initial guess, the periodic-axis conventions Q19/Q20): gradients within solver tolerance,
+* the numpy helpers either side of the path (energy spectrum, training-sample file lists)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from common import SMALL_SETUPS, rel_l2
+from oracle import adjoint as A
+from oracle import oracle as O
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_python")
+STEP_SETUPS = ["ldc8", "periodic16", "periodic24x20", "tml16x24", "sml16x48"]
+
+
+def load_step(name):
+    return np.load(os.path.join(GOLD, "step_%s.npz" % name))
+
+
+@pytest.mark.parametrize("name", STEP_SETUPS)
+def test_constants_and_padding_equal_reference_python(name):
+    g, s = load_step(name), SMALL_SETUPS[name]()
+    ny, nx = s["ny"], s["nx"]
+    n_u = ny * (nx + 1)
+    assert s["dy"] == float(g["dy"]) and s["dx"] == float(g["dx"])                  # Domain.dx (fp32 box / resolution)
+    assert O.cell_areas(s["dy"], s["dx"]) == tuple(float(x) for x in g["cell_area"])    # piso_tf.py:97
+    assert [float(np.float32(s["dx"])), float(np.float32(s["dy"]))] == [float(x) for x in g["grid_spacing"]]
+    assert O.step_constants(s["dy"], s["dx"], s["dt"])["beta"] == float(np.float32(g["beta"]))      # piso_tf.py:26
+    up, vp = O.pad_velocity(ny, nx, s["per_x"], s["per_y"], g["vel"][:n_u].reshape(ny, nx + 1),
+                            g["vel"][n_u:].reshape(ny + 1, nx))
+    assert np.array_equal(np.concatenate([up.ravel(), vp.ravel()]), g["velocity_padded"])   # custom_padded + flatten
+    rp, ci = O.csr_structure(ny, nx, s["per_x"], s["per_y"])
+    assert np.array_equal(rp, g["row_ptr"]) and np.array_equal(ci, g["col_ind"])
+
+
+@pytest.mark.parametrize("name", STEP_SETUPS)
+def test_oracle_step_is_bit_identical_to_reference_python(name):
+    """Same inputs, same native-op substitutes: every intermediate of the step equals the reference's bit for bit."""
+    g, s = load_step(name), SMALL_SETUPS[name]()
+    vel_next, pres_next, st, ex = O.piso_step(s, g["vel"], g["pres"], forcing=g["forcing"], full_output=True)
+    for key in ("values", "a_diag", "rhs", "u_star", "div1", "p1", "u_s2", "div2", "p2"):
+        assert np.array_equal(np.asarray(ex[key]).ravel(), g[key].ravel()), key
+    assert np.array_equal(vel_next, g["vel_next"]) and np.array_equal(pres_next, g["pres_next"])
+    assert np.array_equal(np.asarray(ex["lap"]).ravel(), g["lap1"].ravel())
+    assert [st["cg1"], st["cg2"]] == g["cg_iterations"].tolist()
+    assert [st["bicg_u"][0], st["bicg_v"][0]] == g["bicg_iterations"].tolist()
+    assert float(g["warn"].max()) == 0.0
+
+
+@pytest.mark.parametrize("name", STEP_SETUPS)
+def test_oracle_adjoint_matches_reference_registered_gradients(name):
+    g, s = load_step(name), SMALL_SETUPS[name]()
+    # what TF's backward executes: two pressure solves (second corrector first), then the transposed predictor solve
+    assert g["bwd_ops"].tolist() == ["pressure", "pressure", "bicgstab:T"]
+    # ... which the reference starts from the FORWARD initial guess (linear_solver.py:164-167 passes flat_x again)
+    assert np.array_equal(g["bwd_bicg_x0"], g["vel"])
+    ref = A.piso_step_adjoint(s, g["vel"], g["pres"], g["w_u"], g["w_p"], forcing=g["forcing"])
+    tol = 1e-5
+    assert rel_l2(ref["g_vel"], g["g_vel"]) < tol
+    assert rel_l2(ref["g_pres"], g["g_pres"]) < tol
+    assert rel_l2(ref["g_forcing"], g["g_forcing"]) < tol
+    if s["dirichlet"].any():
+        # ldc8 runs the adjoint CG into its 1000-iteration cap (restart every 10): both sides stop unconverged
+        assert rel_l2(ref["g_dvals"], g["g_dvals"]) < (1e-4 if name == "ldc8" else tol)
+    else:
+        assert not g["g_dvals"].any() and not ref["g_dvals"].any()
+
+
+@pytest.mark.parametrize("tag", ["16x16", "12x20", "9x14"])
+def test_energy_spectrum_matches_reference_numpy(tag):
+    """diffpiso/evaluation_tools.py:92-113 executed from source vs diffpiso_b200.statistics.EK_spectrum_2D."""
+    from diffpiso_b200 import statistics as S
+    g = np.load(os.path.join(GOLD, "ek_spectrum_%s.npz" % tag))
+    k, e = S.EK_spectrum_2D(g["field"], None)
+    assert np.array_equal(k, g["k"])
+    assert np.allclose(e, g["e"], rtol=1e-5, atol=1e-12)
+
+
+def test_data_path_assembler_matches_reference():
+    """diffpiso/datamanagement.py:35-48 executed from source vs diffpiso_b200.datamanagement.data_path_assembler."""
+    from diffpiso_b200 import datamanagement as D
+    j = json.load(open(os.path.join(GOLD, "data_path_assembler.json")))
+    out = D.data_path_assembler(**j["args"])
+    assert json.loads(json.dumps(out)) == j["out"]
+
+
+def test_frame_files_round_trip(tmp_path):
+    """velocity_%06d.npz / pressure_%06d.npz with `arr_0` (spatial_mixing_layer.py:60-75) through save_frame,
+    load_frame and the training-sample loader of datamanagement.py:51-58."""
+    from diffpiso_b200 import datamanagement as D
+    rng = np.random.RandomState(0)
+    d = str(tmp_path) + "/"
+    frames = [(rng.randn(1, 5, 7, 2).astype(np.float32), rng.randn(1, 4, 6, 1).astype(np.float32)) for _ in range(6)]
+    for i, (v, p) in enumerate(frames):
+        D.save_frame(d, i, v, p)
+    assert sorted(os.listdir(d))[0] == "pressure_000000.npz"
+    v, p = D.load_frame(d, 3)
+    assert np.array_equal(v, frames[3][0]) and np.array_equal(p, frames[3][1])
+    files = D.data_path_assembler([d], ["velocity", "pressure"], [[float(i) for i in range(6)]], [0], [6], [2], dt_ratio=2)
+    assert len(files[0]) == 2 and files[0][1][-1].endswith("velocity_000005.npz")
+    vel, pres, ch = D.load_function(files[0][1], files[1][1], files[2][1])
+    assert vel.shape == (1, 3, 5, 7, 2) and pres.shape == (1, 3, 4, 6, 1) and ch.tolist() == [1.0]
+    assert np.array_equal(vel[0, 1], frames[3][0][0])
+    ds = D.FrameDataset(files, rank=1, world_size=2)
+    assert len(ds) == 1 and tuple(ds[0][0].shape) == (3, 5, 7, 2)

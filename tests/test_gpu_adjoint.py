@@ -101,14 +101,14 @@ def test_piso_step_backward_matches_oracle(name):
         act = s["active"].reshape(ny + 2, nx + 2)[1:-1, 1:-1].ravel() != 0
         w_p[:, ~act] = 0
         w_p[:, act] -= w_p[:, act].mean(axis=1, keepdims=True)
-    box = (ny * s["dy"], nx * s["dx"])
+    dxy = (s["dy"], s["dx"])
     tv = _t(vel).requires_grad_(True)
     tp = _t(pres).requires_grad_(True)
     tf = _t(forcing).requires_grad_(True)
     td = _t(s["dirichlet_values"])[None].clone().requires_grad_(True)
-    velocity = dp.StaggeredGrid(flat=tv, resolution=(ny, nx), box=box)
-    pressure = dp.CenteredGrid(tp.reshape(2, ny, nx, 1), box=box, extrapolation=extrap(s["pbc"]))
-    inc = dp.CenteredGrid(torch.zeros(2, ny, nx, 1, device=DEV), box=box, extrapolation=extrap(s["pbc_inc"]))
+    velocity = dp.StaggeredGrid(flat=tv, resolution=(ny, nx), dx=dxy)
+    pressure = dp.CenteredGrid(tp.reshape(2, ny, nx, 1), dx=dxy, extrapolation=extrap(s["pbc"]))
+    inc = dp.CenteredGrid(torch.zeros(2, ny, nx, 1, device=DEV), dx=dxy, extrapolation=extrap(s["pbc_inc"]))
     visc_field = _t(s["visc"]) if np.atleast_1d(s["visc"]).size > 1 else None
     v_new, p_new, warn = dp.piso_step(velocity, pressure, inc, inc, s["dt"], sim, td, viscosity_field=visc_field,
                                       forcing_term=tf)

@@ -19,13 +19,13 @@ def test_helper_operators_forward_and_backward(name):
     sim = build_sim(s)
     ny, nx = s["ny"], s["nx"]
     nf, nc = ny * (nx + 1) + (ny + 1) * nx, ny * nx
-    box = (ny * s["dy"], nx * s["dx"])
+    dxy = (s["dy"], s["dx"])
     rng = np.random.RandomState(3)
     per = (s["per_y"], s["per_x"])
     # finite_volume_gradient_tensor
     p = rng.randn(2, nc).astype(np.float32)
     tp = torch.as_tensor(p).to(DEV).requires_grad_(True)
-    cg = dp.CenteredGrid(tp.reshape(2, ny, nx, 1), box=box, extrapolation=extrap(s["pbc"]))
+    cg = dp.CenteredGrid(tp.reshape(2, ny, nx, 1), dx=dxy, extrapolation=extrap(s["pbc"]))
     g = dp.finite_volume_gradient_tensor(cg, sim)
     gflat = dp.flatten_staggered_data(g, coord_flip=True)
     w = rng.randn(2, nf).astype(np.float32)
@@ -36,7 +36,7 @@ def test_helper_operators_forward_and_backward(name):
     # finite_volume_divergence
     vel = rng.randn(2, nf).astype(np.float32)
     tv = torch.as_tensor(vel).to(DEV).requires_grad_(True)
-    sg = dp.StaggeredGrid(flat=tv, resolution=(ny, nx), box=box)
+    sg = dp.StaggeredGrid(flat=tv, resolution=(ny, nx), dx=dxy)
     d = dp.finite_volume_divergence(sg, per)
     wc = rng.randn(2, nc).astype(np.float32)
     (d.reshape(2, nc) * torch.as_tensor(wc).to(DEV)).sum().backward()
@@ -45,7 +45,7 @@ def test_helper_operators_forward_and_backward(name):
         assert np.array_equal(tv.grad[i].cpu().numpy(), A.fv_divergence_adj(ny, nx, s["per_x"], s["per_y"], s["dy"], s["dx"], wc[i]))
     # advection_matrix_cuda + explicit_H_csr
     v0 = np.stack([random_fields(s, 60 + i)[0] for i in range(2)])
-    vel0 = dp.StaggeredGrid(flat=torch.as_tensor(v0).to(DEV), resolution=(ny, nx), box=box)
+    vel0 = dp.StaggeredGrid(flat=torch.as_tensor(v0).to(DEV), resolution=(ny, nx), dx=dxy)
     c = O.step_constants(s["dy"], s["dx"], s["dt"])
     visc = torch.as_tensor(np.atleast_1d(s["visc"])).to(DEV)
     values, rp, ci, a_st, nnz, a_flat = dp.advection_matrix_cuda(vel0, sim, visc, c["beta"])
@@ -53,7 +53,7 @@ def test_helper_operators_forward_and_backward(name):
     assert np.array_equal(rp.cpu().numpy(), orp) and np.array_equal(ci.cpu().numpy(), oci)
     dvec = rng.randn(2, nf).astype(np.float32)
     td = torch.as_tensor(dvec).to(DEV).requires_grad_(True)
-    h = dp.explicit_H_csr(values, rp, ci, dp.StaggeredGrid(flat=td, resolution=(ny, nx), box=box), (2, ny + 1, nx + 1, 2),
+    h = dp.explicit_H_csr(values, rp, ci, dp.StaggeredGrid(flat=td, resolution=(ny, nx), dx=dxy), (2, ny + 1, nx + 1, 2),
                           a_st, c["beta"], per)
     hflat = dp.flatten_staggered_data(h, coord_flip=True)
     (hflat * torch.as_tensor(w).to(DEV)).sum().backward()

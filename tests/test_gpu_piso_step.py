@@ -36,10 +36,10 @@ def run_step(s, sim, vel_flat, pres, forcing=None, full_output=False):
     import diffpiso_b200 as dp
     b = vel_flat.shape[0]
     ny, nx = s["ny"], s["nx"]
-    box = (ny * s["dy"], nx * s["dx"])
-    velocity = dp.StaggeredGrid(flat=torch.as_tensor(vel_flat).to(DEV), resolution=(ny, nx), box=box)
-    pressure = dp.CenteredGrid(torch.as_tensor(pres).reshape(b, ny, nx, 1).to(DEV), box=box, extrapolation=extrap(s["pbc"]))
-    inc = dp.CenteredGrid(torch.zeros(b, ny, nx, 1, device=DEV), box=box, extrapolation=extrap(s["pbc_inc"]))
+    dxy = (s["dy"], s["dx"])
+    velocity = dp.StaggeredGrid(flat=torch.as_tensor(vel_flat).to(DEV), resolution=(ny, nx), dx=dxy)
+    pressure = dp.CenteredGrid(torch.as_tensor(pres).reshape(b, ny, nx, 1).to(DEV), dx=dxy, extrapolation=extrap(s["pbc"]))
+    inc = dp.CenteredGrid(torch.zeros(b, ny, nx, 1, device=DEV), dx=dxy, extrapolation=extrap(s["pbc_inc"]))
     visc_field = None
     if np.atleast_1d(s["visc"]).size > 1:
         visc_field = torch.as_tensor(s["visc"]).to(DEV)
