@@ -9,9 +9,18 @@ from .linear_solver import LinearSolver, LinearSolverCudaBicgstabILU, LinearSolv
 from .ops import Geometry
 from .piso import SimulationParameters, advection_matrix_cuda, piso_step, pressure_extrapolation
 from .pressure_solver import PisoPressureSolverCudaCustom, PoissonSolver
+from .masks import compute_mixingLayer_masks, temporal_mixing_layer_masks, update_dirichlet_values
+from .networks import fullyconv_network, initialise_fullyconv_network
+from .losses import L2_field_loss, multistep_averaging_loss, spectral_energy_loss, strain_rate_loss
+from .training import run_piso_steps, zero_gradient_op
+from .datamanagement import create_base_dir, data_path_assembler, load_function
 
 __all__ = ["CenteredGrid", "StaggeredGrid", "flatten_staggered_data", "stagger_flattened_data",
            "stack_staggered_components", "unstack_staggered_tensor", "LinearSolver", "LinearSolverCudaBicgstabILU",
            "LinearSolverCudaMultiBicgstabILU", "PisoPressureSolverCudaCustom", "PoissonSolver", "SimulationParameters",
            "piso_step", "advection_matrix_cuda", "pressure_extrapolation", "Geometry", "custom_padded", "arrange_rhs_term",
-           "finite_volume_gradient_tensor", "finite_volume_divergence", "explicit_H_csr"]
+           "finite_volume_gradient_tensor", "finite_volume_divergence", "explicit_H_csr",
+           "compute_mixingLayer_masks", "temporal_mixing_layer_masks", "update_dirichlet_values", "fullyconv_network",
+           "initialise_fullyconv_network", "L2_field_loss", "spectral_energy_loss", "strain_rate_loss",
+           "multistep_averaging_loss", "run_piso_steps", "zero_gradient_op", "create_base_dir", "data_path_assembler",
+           "load_function"]

@@ -1,0 +1,132 @@
+"""The caller of the PISO path in training and inference: `run_piso_steps` unrolls `step_count`
+steps, optionally with the closure network's forcing (diffpiso/combined_training_integrated.py:396-478), and the
+data-parallel pieces around it -- gradient all-reduce of the closure weights over NCCL (the only collective of the
+whole workload: samples are independent) and an Adam step (`training_run`, :71-76).
+
+Everything here is torch glue; each `piso_step` inside runs on the native kernels and brings its own adjoint."""
+import numpy as np
+import torch
+
+from .grids import CenteredGrid, StaggeredGrid, stack_staggered_components
+from .piso import piso_step
+
+
+class _ZeroGradient(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g * 0
+
+
+def zero_gradient_op(centered_data):
+    """combined_training_integrated.py:386-393: identity whose gradient is zero (used instead of stop_gradient on the
+    pressure so that the backward graph stays connected)."""
+    return _ZeroGradient.apply(centered_data)
+
+
+def closure_input(velocity, pressure, pressure_included=True):
+    """Network input [B, ny, nx, 2 or 4]: face velocities averaged to the centres (channel 0 = v, 1 = u) and, if
+    requested, the central-difference pressure gradient (d/dy, d/dx) (:401-405)."""
+    nn_in = velocity.at_centers().data
+    if pressure_included:
+        nn_in = torch.cat([nn_in, pressure.gradient().data], dim=-1)
+    return nn_in
+
+
+def closure_forcing(nn_out, velocity):
+    """Network output [B, ny, nx, 2] -> staggered forcing tensor: channel 0 resampled to the v faces, channel 1 to the
+    u faces, each as a CenteredGrid with the default 'boundary' extrapolation (:407-410)."""
+    fv = CenteredGrid(nn_out[..., 0:1], dx=velocity.dx).at_faces(0)
+    fu = CenteredGrid(nn_out[..., 1:2], dx=velocity.dx).at_faces(1)
+    return stack_staggered_components([fv, fu])
+
+
+def spatial_mixing_layer_network_wrapper(neural_network, input, fluid, physical_parameters, simulation_parameters,
+                                         loss_buffer_width, buffer_width):
+    """spatial_mixing_layer_differentiable_training.py:6-10: the network sees the region upstream of the sponge layer
+    only; its output is zero-padded back to the full width."""
+    sponge_start = int(simulation_parameters["HRres"][1] * simulation_parameters["sponge_ratio"]) // simulation_parameters["dx_ratio"]
+    out = neural_network(input[:, :, :sponge_start, :])
+    return torch.nn.functional.pad(out, (0, 0, 0, int(fluid.resolution[1]) - sponge_start))
+
+
+def run_piso_steps(velocity, pressure, domain, physical_parameters, simulation_parameters, training_dict, neural_network,
+                   neural_network_wrapper, sim_physics, viscosity_field, bcx, bc_placeholders,
+                   dirichlet_placeholder_update=None, loss_buffer_width=None):
+    """combined_training_integrated.py:396-478, same arguments and the same 9-tuple
+    (velocity_all_steps, pressure_all_steps, nn_all_steps, velnew, pnew, NN_out, warn, velocity_all_arrays,
+    pressure_all_arrays).  `domain` only needs `.resolution`; `bc_placeholders` is the per-step inflow perturbation
+    [step_count, 1, ny+2, 1, 1] (a tensor instead of a TF placeholder); every sample of the batch is unrolled at once."""
+    step_count = training_dict["step_count"] if training_dict is not None else 1
+    dt = simulation_parameters["dt"] * simulation_parameters["dt_ratio"]
+    dirichlet_values = sim_physics.dirichlet_values
+    device = velocity.flat.device
+    nn_all_steps, nn_out = [], []
+    velocity_all_steps, pressure_all_steps, velocity_all_arrays, pressure_all_arrays = [], [], [], []
+    warn = [None] * step_count
+    if neural_network is not None:
+        buffer_width = [[i // simulation_parameters["dx_ratio"] for i in j] for j in training_dict["HR_buffer_width"]]
+    velnew, pnew = velocity, pressure
+    for i in range(step_count):
+        if i > 0:
+            if i % training_dict["loss_influence_range"] == 0:            # :436-438
+                velnew = StaggeredGrid(velnew.staggered_tensor().detach(), dx=velnew.dx, extrapolation=velnew.extrapolation)
+                pnew = CenteredGrid(zero_gradient_op(pnew.data), dx=pnew.dx, extrapolation=pnew.extrapolation)
+            if dirichlet_placeholder_update is not None:                  # :440-441
+                bc = torch.as_tensor(np.asarray(bcx), dtype=bc_placeholders[i].dtype, device=device) + bc_placeholders[i]
+                dirichlet_values = dirichlet_placeholder_update(sim_physics.dirichlet_values, (([], []), (bc, [])))
+        residual_force = None
+        if neural_network is not None:
+            nn_in = closure_input(velnew, pnew, training_dict["pressure_included"])
+            nn_out = neural_network_wrapper(neural_network, nn_in, domain, physical_parameters, simulation_parameters,
+                                            loss_buffer_width, buffer_width)
+            residual_force = closure_forcing(nn_out, velocity)
+            nn_all_steps.append(nn_out)
+        # the increments only carry box / extrapolation (their values are ignored by the solver); the
+        # reference builds them without an extrapolation argument, i.e. 'boundary' (:419-420)
+        inc1 = CenteredGrid(torch.zeros_like(pressure.data) + 5e-13, dx=pressure.dx)
+        inc2 = CenteredGrid(torch.zeros_like(pressure.data) + 1e-12, dx=pressure.dx)
+        vel_piso, p_piso, warn[i] = piso_step(velnew, pnew, inc1, inc2, dt, sim_physics, dirichlet_values,
+                                              viscosity_field=viscosity_field, forcing_term=residual_force,
+                                              unrolling_step=i)
+        velocity_all_steps.append(vel_piso)
+        pressure_all_steps.append(p_piso)
+        velocity_all_arrays.append(vel_piso.staggered_tensor())
+        pressure_all_arrays.append(p_piso.data)
+        velnew = StaggeredGrid(velocity_all_arrays[i], dx=vel_piso.dx, extrapolation=vel_piso.extrapolation)
+        pnew = CenteredGrid(pressure_all_arrays[i], dx=p_piso.dx, extrapolation=p_piso.extrapolation)
+    return (velocity_all_steps, pressure_all_steps, nn_all_steps, velnew, pnew, nn_out, warn, velocity_all_arrays,
+            pressure_all_arrays)
+
+
+def allreduce_gradients(parameters, world_size=None, average=True):
+    """Sum (or mean) of the closure-network gradients over the ranks: ONE flat NCCL all-reduce per training iteration
+    (81 856 parameters = 0.33 MB; latency-bound, so a single bucket).  No-op without an initialised process group."""
+    import torch.distributed as dist
+    params = [p for p in parameters if p.grad is not None]
+    if not (dist.is_available() and dist.is_initialized()) or not params:
+        return
+    world_size = dist.get_world_size() if world_size is None else world_size
+    flat = torch.cat([p.grad.reshape(-1) for p in params])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    if average:
+        flat /= world_size
+    off = 0
+    for p in params:
+        n = p.grad.numel()
+        p.grad.copy_(flat[off:off + n].view_as(p.grad))
+        off += n
+
+
+def training_iteration(optimizer, weights, loss_fn):
+    """One optimisation step as in `training_run` (:61-76, :300-330): loss -> gradients w.r.t. the closure weights
+    through the unrolled PISO steps -> all-reduce over the data-parallel ranks -> Adam."""
+    optimizer.zero_grad(set_to_none=True)
+    loss = loss_fn()
+    loss.backward()
+    allreduce_gradients(weights)
+    optimizer.step()
+    return loss.detach()

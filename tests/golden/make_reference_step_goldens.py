@@ -125,10 +125,102 @@ def inputs_for(s, seed=50):
     return vel, pres, forcing, w_u, w_p
 
 
+def mask_goldens(ns):
+    """compute_mixingLayer_masks / temporal_mixing_layer_masks / update_dirichlet_values (piso_helpers.py:58-166)."""
+    ny, nx = 6, 9
+    shape = (1, ny + 1, nx + 1, 2)
+    rng = np.random.RandomState(3)
+    bcy, bcx = rng.randn(1, 1, nx + 2, 1), rng.randn(1, ny + 2, 1, 1)
+    dv = rng.randn(*shape).astype(np.float32)
+    arr = ((bcy, bcy * 2), (bcx, bcx * 3))
+    out = dict(bcy=bcy, bcx=bcx, dv=dv, shape=np.array(shape))
+    cases = [((True, True), (True, False)), ((False, True), (True, True)), ((True, False), (False, False))]
+    out["mixing_cases"] = np.array(cases)
+    for k, bb in enumerate(cases):
+        for j, a in enumerate(ns["compute_mixingLayer_masks"](shape, bb, arr)):
+            out["mixing%d_%d" % (k, j)] = np.asarray(a)
+    r = ns["temporal_mixing_layer_masks"](shape, ((True, True), (False, False)), arr)
+    for j, a in enumerate((r[0], r[1], r[2][0], r[2][1], r[3], r[4])):
+        out["temporal_%d" % j] = np.asarray(a)
+    upd = [((False, False), (True, False)), ((True, True), (True, True)), ((False, True), (False, False))]
+    out["update_cases"] = np.array(upd)
+    for k, ub in enumerate(upd):
+        out["update%d" % k] = np.asarray(ns["update_dirichlet_values"](dv, ub, arr))
+    np.savez_compressed(os.path.join(OUT, "masks.npz"), **out)
+
+
+def closure_weights(seed=11, scale=0.05):
+    """Small seeded closure weights in TF's HWIO layout (networks.py:57-65 shapes)."""
+    rng = np.random.RandomState(seed)
+    chans = [4, 16, 16, 32, 64, 64, 64, 2]
+    ks = [7, 5, 5, 3, 3, 1, 1]
+    return [(rng.randn(k, k, chans[i], chans[i + 1]) * scale / k).astype(np.float32) for i, k in enumerate(ks)]
+
+
+def network_goldens(ns):
+    """fullyconv_network (networks.py:3-52): SAME, and VALID with restore_shape and a buffer (the training default)."""
+    rng = np.random.RandomState(2)
+    w = closure_weights()
+    x = rng.randn(2, 30, 44, 4).astype(np.float32)
+    tw = [RR.tf_tensor(k) for k in w]
+    same = ns["fullyconv_network"](RR.tf_tensor(x), tw, None, "SAME", False)
+    valid = ns["fullyconv_network"](RR.tf_tensor(x), tw, [[1, 2], [0, 3]], "VALID", True)
+    np.savez_compressed(os.path.join(OUT, "network.npz"), x=x, same=same.detach().numpy(), valid=valid.detach().numpy(),
+                        **{"w%d" % i: k for i, k in enumerate(w)})
+
+
+def unroll_goldens(ns, log, name="sml16x48", steps=3):
+    """run_piso_steps (combined_training_integrated.py:396-478) with the closure network, the per-step inflow
+    perturbation and a stop-gradient window of 2 steps; loss = sum_s <w_s, velocity_s>; gradients w.r.t. the closure
+    weights and the initial state."""
+    from common import SMALL_SETUPS, random_fields
+    from diffpiso_b200 import setups as SU
+    s = SMALL_SETUPS[name]()
+    ny, nx = s["ny"], s["nx"]
+    domain, sim = reference_objects(ns, s)
+    rng = np.random.RandomState(21)
+    vel, pres = random_fields(s, 60)
+    w = closure_weights()
+    tw = [RR.tf_tensor(k, True) for k in w]
+    bcx = s["inlet_profile"].reshape(1, ny + 2, 1, 1).astype(np.float32)
+    bc_pert = (rng.randn(steps, 1, ny + 2, 1, 1) * 0.01).astype(np.float32)
+    sim.dirichlet_values = ns["update_dirichlet_values"](s["dirichlet_values_staggered"], ((False, False), (True, False)),
+                                                       (([], []), (bcx + bc_pert[0], [])))
+    vel_t = RR.tf_tensor(SU.stagger_flat(vel[None], ny, nx), True)
+    pres_t = RR.tf_tensor(pres.reshape(1, ny, nx, 1).copy(), True)
+    velocity = ns["StaggeredGrid"].sample(vel_t, domain=domain)
+    pressure = ns["CenteredGrid"](pres_t, box=domain.box, extrapolation=ns["pressure_extrapolation"](domain.boundaries))
+    simulation_parameters = dict(dx_ratio=1, dt=s["dt"], dt_ratio=1, HRres=[ny, nx], sponge_ratio=0.875)
+    training_dict = dict(step_count=steps, HR_buffer_width=[[0, 0], [0, 0]], pressure_included=True, loss_influence_range=2)
+    network = lambda x: ns["fullyconv_network"](x, tw, [[0, 0], [0, 0]], "SAME", False)
+    visc_field = RR.tf_tensor(np.asarray(s["visc"], np.float32))
+    update = lambda dv, pl: ns["update_dirichlet_values"](dv, ((False, False), (True, False)), pl)
+    log.calls.clear()
+    out = ns["run_piso_steps"](velocity, pressure, domain, {}, simulation_parameters, training_dict, network,
+                               ns["neural_network_wrapper"], sim, visc_field, bcx, RR.tf_tensor(bc_pert), update, None)
+    w_loss = rng.randn(steps, 1, ny + 1, nx + 1, 2).astype(np.float32)
+    loss = sum((out[7][k] * RR.tf_tensor(w_loss[k])).sum() for k in range(steps))
+    loss.backward()
+    res = dict(vel=vel, pres=pres, bcx=bcx, bc_pert=bc_pert, w_loss=w_loss, loss=np.float64(loss.detach().numpy()),
+               velocities=np.stack([t.detach().numpy() for t in out[7]]),
+               pressures=np.stack([t.detach().numpy() for t in out[8]]),
+               nn_out=np.stack([t.detach().numpy() for t in out[2]]),
+               g_vel=vel_t.grad.numpy(), g_pres=pres_t.grad.numpy(),
+               ops=np.array([n + (":T" if kw.get("transpose") else "") for n, kw in log.calls]))
+    for i, k in enumerate(w):
+        res["w%d" % i] = k
+        res["g_w%d" % i] = tw[i].grad.numpy()
+    np.savez_compressed(os.path.join(OUT, "unroll_%s.npz" % name), **res)
+    print("unroll", name, "loss", float(loss), "ops", len(log.calls), "|g_w0|", float(np.abs(res["g_w0"]).sum()))
+
+
 def main():
     from common import SMALL_SETUPS
     os.makedirs(OUT, exist_ok=True)
     ns, log = RR.load_reference(O)
+    mask_goldens(ns)
+    network_goldens(ns)
+    unroll_goldens(ns, log)
     for name in SETUPS:
         s = SMALL_SETUPS[name]()
         res = run_reference_step(ns, log, s, *inputs_for(s))

@@ -92,8 +92,23 @@ def _plain(t):
     return t.as_subclass(torch.Tensor) if isinstance(t, _TfTensor) else t
 
 
+class _TfNn(object):
+    @staticmethod
+    def conv2d(x, w, strides, padding):
+        """NHWC input, HWIO filter, stride 1, 'SAME' (odd kernels: symmetric zero padding) or 'VALID'."""
+        assert list(strides) == [1, 1, 1, 1] and padding in ("SAME", "VALID")
+        pad = (w.shape[0] // 2, w.shape[1] // 2) if padding == "SAME" else 0
+        y = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), padding=pad)
+        return y.permute(0, 2, 3, 1)
+
+    @staticmethod
+    def leaky_relu(x, alpha=0.2):
+        return torch.nn.functional.leaky_relu(x, alpha)
+
+
 class TfShim(object):
     float32, float64, int32, bool = torch.float32, torch.float64, torch.int32, torch.bool
+    nn = _TfNn()
 
     @staticmethod
     def _shape(shape):
@@ -353,6 +368,8 @@ def load_reference(oracle):
         (d + "piso_cuda_pressure_solver.py", {"PisoPressureSolverCudaCustom"}),
         (d + "piso_tf.py", {"piso_step", "advection_matrix_cuda", "pressure_extrapolation", "SimulationParameters"}),
         (d + "combined_training_integrated.py", {"zero_gradient_op", "run_piso_steps"}),
+        (d + "networks.py", {"fullyconv_network"}),
+        (REF + "/spatial_mixing_layer_differentiable_training.py", {"neural_network_wrapper"}),
     ]
     for path, names in wanted:
         for node in _definitions(path, names):

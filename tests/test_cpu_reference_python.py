@@ -112,3 +112,65 @@ def test_frame_files_round_trip(tmp_path):
     assert np.array_equal(vel[0, 1], frames[3][0][0])
     ds = D.FrameDataset(files, rank=1, world_size=2)
     assert len(ds) == 1 and tuple(ds[0][0].shape) == (3, 5, 7, 2)
+
+
+def test_mask_builders_match_reference():
+    """compute_mixingLayer_masks / temporal_mixing_layer_masks / update_dirichlet_values (piso_helpers.py:58-166)."""
+    import torch
+    from diffpiso_b200 import masks as M
+    g = np.load(os.path.join(GOLD, "masks.npz"))
+    shape = tuple(int(k) for k in g["shape"])
+    arr = ((g["bcy"], g["bcy"] * 2), (g["bcx"], g["bcx"] * 3))
+    for k, bb in enumerate(g["mixing_cases"]):
+        bb = tuple(tuple(bool(x) for x in row) for row in bb)
+        for j, a in enumerate(M.compute_mixingLayer_masks(shape, bb, arr)):
+            ref = g["mixing%d_%d" % (k, j)]
+            assert a.shape == ref.shape and np.array_equal(a, ref), (bb, j)
+    r = M.temporal_mixing_layer_masks(shape, ((True, True), (False, False)), arr)
+    for j, a in enumerate((r[0], r[1], r[2][0], r[2][1], r[3], r[4])):
+        assert np.array_equal(a, g["temporal_%d" % j]), j
+    for k, ub in enumerate(g["update_cases"]):
+        ub = tuple(tuple(bool(x) for x in row) for row in ub)
+        assert np.array_equal(M.update_dirichlet_values(g["dv"], ub, arr), g["update%d" % k])
+        t = M.update_dirichlet_values(torch.from_numpy(g["dv"]), ub, arr)                  # in-graph variant
+        assert np.array_equal(t.numpy(), g["update%d" % k].astype(np.float32))
+
+
+def _weights(g):
+    import torch
+    return [torch.from_numpy(g["w%d" % i]) for i in range(7)]
+
+
+def test_closure_network_matches_reference():
+    """diffpiso/networks.py:3-52 executed from source (tf.nn.conv2d -> torch conv) vs diffpiso_b200.networks."""
+    import torch
+    from diffpiso_b200 import networks as N
+    g = np.load(os.path.join(GOLD, "network.npz"))
+    x, w = torch.from_numpy(g["x"]), _weights(g)
+    same = N.fullyconv_network(x, w, None, "SAME", False)
+    valid = N.fullyconv_network(x, w, [[1, 2], [0, 3]], "VALID", True)
+    assert same.shape == g["same"].shape and valid.shape == g["valid"].shape
+    assert rel_l2(same.numpy(), g["same"]) < 1e-6 and rel_l2(valid.numpy(), g["valid"]) < 1e-6
+    assert np.array_equal(valid.numpy() == 0, g["valid"] == 0)          # same zero frame
+
+
+def test_closure_coupling_of_first_unrolled_step_matches_reference():
+    """Network input (face->centre averages + central pressure gradient with the pressure's mixed extrapolation) and the
+    sponge-cropping wrapper, as run_piso_steps evaluates them for step 0 (combined_training_integrated.py:399-410)."""
+    import torch
+    from diffpiso_b200 import networks as N, setups as SU, training as T
+    from diffpiso_b200.grids import CenteredGrid, StaggeredGrid
+    from test_gpu_piso_step import extrap
+    g = np.load(os.path.join(GOLD, "unroll_sml16x48.npz"))
+    s = SMALL_SETUPS["sml16x48"]()
+    ny, nx = s["ny"], s["nx"]
+    velocity = StaggeredGrid(torch.from_numpy(SU.stagger_flat(g["vel"][None], ny, nx)), dx=(s["dy"], s["dx"]))
+    pressure = CenteredGrid(torch.from_numpy(g["pres"].reshape(1, ny, nx, 1)), dx=(s["dy"], s["dx"]),
+                            extrapolation=extrap(s["pbc"]))
+    w = _weights(g)
+    nn_in = T.closure_input(velocity, pressure, True)
+    sim_par = dict(dx_ratio=1, HRres=[ny, nx], sponge_ratio=0.875)
+    out = T.spatial_mixing_layer_network_wrapper(lambda x: N.fullyconv_network(x, w, [[0, 0], [0, 0]], "SAME", False),
+                                                 nn_in, velocity, {}, sim_par, None, [[0, 0], [0, 0]])
+    assert rel_l2(out.numpy(), g["nn_out"][0]) < 1e-6
+    assert not out[:, :, 42:].any()

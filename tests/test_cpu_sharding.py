@@ -52,3 +52,47 @@ def test_two_rank_gloo_sharding_and_timing():
     assert [r[1] for r in res] == [[7, 6], [7, 6]]            # every rank sees the same whole-job counts
     assert [r[2] for r in res] == [[11.0, 5.0], [11.0, 5.0]]  # max over ranks
     assert [r[3] for r in res] == [0.0, 21.0] and [r[4] for r in res] == [7, 6]
+
+
+def _train_worker(rank, world, port, q):
+    """Two ranks, each with its own shard of samples: after allreduce_gradients + Adam both hold identical closure
+    weights, equal to a single-process run over the whole batch."""
+    from diffpiso_b200 import networks as N, training as T
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    gen = torch.Generator().manual_seed(3)
+    net, w, _ = N.initialise_fullyconv_network(None, "SAME", generator=gen)
+    x = torch.randn(4, 12, 14, 4, generator=torch.Generator().manual_seed(5))
+    mine = sharding.local_batch(x)
+    opt = torch.optim.Adam(w, lr=1e-3)
+    loss = T.training_iteration(opt, w, lambda: (net(mine) ** 2).sum() / x.shape[0] * world)
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, float(loss), [t.detach().numpy().copy() for t in w]))
+
+
+def test_two_rank_gloo_closure_gradient_allreduce():
+    from diffpiso_b200 import networks as N, training as T
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=180) for _ in procs), key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for a, b in zip(res[0][2], res[1][2]):
+        assert (a == b).all()
+    # single process over the whole batch (mean over ranks of per-rank losses scaled by world == whole-batch loss)
+    gen = torch.Generator().manual_seed(3)
+    net, w, _ = N.initialise_fullyconv_network(None, "SAME", generator=gen)
+    x = torch.randn(4, 12, 14, 4, generator=torch.Generator().manual_seed(5))
+    opt = torch.optim.Adam(w, lr=1e-3)
+    T.training_iteration(opt, w, lambda: (net(x) ** 2).sum() / x.shape[0])
+    for a, b in zip(res[0][2], w):
+        assert torch.allclose(torch.from_numpy(a), b.detach(), rtol=1e-4, atol=1e-6)

@@ -47,6 +47,14 @@ def run_step(s, sim, vel_flat, pres, forcing=None, full_output=False):
                         viscosity_field=visc_field, forcing_term=forcing, full_output=full_output)
 
 
+def _gauge(s, p):
+    """Rank-deficient pressure systems fix the constant mode only through the solver's shift s * sum(p)
+    (pressure_solve_op.cu.cc:444-453), i.e. through sum(rhs) ~ rounding noise: compare with the mean removed (the
+    mean itself is checked separately against the field's magnitude)."""
+    p = np.asarray(p, np.float64)
+    return p - p.mean() if s["rank_deficient"] else p
+
+
 @pytest.mark.parametrize("name", list(SMALL_SETUPS) + ["periodic64", "tml64x128", "sml32x128", "periodic264x256"])
 def test_piso_step_matches_oracle(name):
     """Three consecutive steps of a batch of 2 seeded samples; every intermediate of the first step and the state after
@@ -72,13 +80,14 @@ def test_piso_step_matches_oracle(name):
                 assert np.array_equal(out[10][i].cpu().numpy(), ex["rhs"])                      # implicit rhs
                 assert rel_l2(out[7][i].cpu().numpy()[:-1, :, 1].ravel(), ex["u_star"][:g_nu]) < 1e-5
                 assert rel_l2(out[13][i].cpu().numpy().ravel(), ex["div1"]) < 1e-4             # differences of u*
-                assert rel_l2(out[2].data[i].cpu().numpy().ravel(), ex["p1"]) < 1e-4
+                assert rel_l2(_gauge(s, out[2].data[i].cpu().numpy().ravel()), _gauge(s, ex["p1"])) < 1e-4
             assert abs(int(bicg[i, 0, 0]) - st["bicg_u"][0]) <= 1 and abs(int(bicg[i, 1, 0]) - st["bicg_v"][0]) <= 1
             # north_star: 1e-5 relative L2 per step at the paper's 1e-8 solver tolerance; setups that run the solvers at
             # 1e-6 (training tolerance) can only agree to ~tol * cond, on either side of the comparison
             vtol, ptol = (1e-5, 1e-4) if s["cg_tol"] <= 1e-8 else (5e-5, 5e-4)
             assert rel_l2(v_new[i], ov) < vtol, (name, step, i, rel_l2(v_new[i], ov))
-            assert rel_l2(p_new[i], op) < ptol, (name, step, i, rel_l2(p_new[i], op))
+            assert rel_l2(_gauge(s, p_new[i]), _gauge(s, op)) < ptol, (name, step, i, rel_l2(p_new[i], op))
+            assert abs(float(np.mean(p_new[i]) - np.mean(op))) < 1e-3 * float(np.abs(op).max())
             ovel[i], opres[i] = ov, op
         vel, pres = v_new, p_new
 
