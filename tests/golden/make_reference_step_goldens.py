@@ -214,12 +214,39 @@ def unroll_goldens(ns, log, name="sml16x48", steps=3):
     print("unroll", name, "loss", float(loss), "ops", len(log.calls), "|g_w0|", float(np.abs(res["g_w0"]).sum()))
 
 
+def loss_goldens(ns):
+    """The four training objectives (diffpiso/losses.py:6-148) on seeded fields, summed and per-step variants."""
+    rng = np.random.RandomState(8)
+    steps, ny, nx = 4, 12, 20
+    fields = rng.randn(steps, 1, ny + 1, nx + 1, 2).astype(np.float32)
+    fields[:, :, -1, :, 1] = 0
+    fields[:, :, :, -1, 0] = 0
+    gt = (fields + 0.1 * rng.randn(*fields.shape)).astype(np.float32).transpose(1, 0, 2, 3, 4).copy()
+    gt[:, :, -1, :, 1] = 0
+    gt[:, :, :, -1, 0] = 0
+    box = ns["box"][0:ny * 0.5, 0:nx * 0.5]
+    grids = [ns["StaggeredGrid"](RR.tf_tensor(fields[k]), box) for k in range(steps)]
+    gt_t = RR.tf_tensor(gt)
+    bw = [[1, 2], [0, 3]]
+    out = dict(fields=fields, gt=gt, buffer_width=np.array(bw), dx=np.float64(0.5), sponge_start=np.int64(17))
+    for fn_name, factor in (("L2_field_loss", 50), ("spectral_energy_loss", 0.5), ("strain_rate_loss", 2),
+                            ("multistep_averaging_loss", 0.5)):
+        fn = ns[fn_name]
+        total, contrib = fn(0, [grids], [gt_t], steps, bw, factor, 17, sum_steps=True, loss_influence_range=2)
+        out[fn_name + "_sum"] = np.float64(float(total))
+        per, contrib = fn([0.0] * steps, [grids], [gt_t], steps, bw, factor, 17, sum_steps=False, loss_influence_range=2)
+        out[fn_name + "_steps"] = np.array([float(x) for x in per])
+    np.savez_compressed(os.path.join(OUT, "losses.npz"), **out)
+    print("losses", {k: v for k, v in out.items() if k.endswith("_sum")})
+
+
 def main():
     from common import SMALL_SETUPS
     os.makedirs(OUT, exist_ok=True)
     ns, log = RR.load_reference(O)
     mask_goldens(ns)
     network_goldens(ns)
+    loss_goldens(ns)
     unroll_goldens(ns, log)
     for name in SETUPS:
         s = SMALL_SETUPS[name]()

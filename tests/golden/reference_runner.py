@@ -57,6 +57,9 @@ class _TfTensor(torch.Tensor):
     def shape(self):
         return _Shape(super().shape)
 
+    def set_shape(self, shape):          # static-shape hint in TF, nothing to do
+        assert list(self.shape) == list(shape)
+
     @classmethod
     def __torch_function__(cls, func, types, args=(), kwargs=None):
         ref = next((a for a in args if isinstance(a, torch.Tensor)), None)
@@ -94,6 +97,10 @@ def _plain(t):
 
 class _TfNn(object):
     @staticmethod
+    def l2_loss(x):
+        return (x ** 2).sum() / 2
+
+    @staticmethod
     def conv2d(x, w, strides, padding):
         """NHWC input, HWIO filter, stride 1, 'SAME' (odd kernels: symmetric zero padding) or 'VALID'."""
         assert list(strides) == [1, 1, 1, 1] and padding in ("SAME", "VALID")
@@ -106,9 +113,63 @@ class _TfNn(object):
         return torch.nn.functional.leaky_relu(x, alpha)
 
 
+class _TfMath(object):
+    @staticmethod
+    def segment_sum(data, segment_ids):
+        ids = segment_ids.long()
+        out = torch.zeros(int(ids.max()) + 1, dtype=data.dtype)
+        return out.index_add(0, ids, data)
+
+
+def _stack_nested(x):
+    if isinstance(x, (list, tuple)):
+        parts = [_stack_nested(k) for k in x]
+        parts = [p if isinstance(p, torch.Tensor) else torch.as_tensor(p) for p in parts]
+        return torch.stack([p.to(torch.float32) if not p.is_floating_point() else p for p in parts])
+    return x
+
+
 class TfShim(object):
-    float32, float64, int32, bool = torch.float32, torch.float64, torch.int32, torch.bool
+    float32, float64, int32, bool, complex64 = torch.float32, torch.float64, torch.int32, torch.bool, torch.complex64
     nn = _TfNn()
+    math = _TfMath()
+
+    def reduce_sum(self, x, axis=None):
+        x = _stack_nested(x)
+        return x.sum() if axis is None else x.sum(dim=tuple(int(a) for a in np.atleast_1d(axis)))
+
+    def convert_to_tensor(self, x):
+        return _stack_nested(x)
+
+    def fft2d(self, x):
+        return torch.fft.fft2(x)
+
+    def conj(self, x):
+        return torch.conj(x)
+
+    def abs(self, x):
+        return torch.abs(x)
+
+    def log(self, x):
+        return torch.log(x)
+
+    def sqrt(self, x):
+        return torch.sqrt(x)
+
+    def round(self, x):
+        return torch.round(x)
+
+    def matmul(self, a, b):
+        return torch.matmul(a, b)
+
+    def expand_dims(self, x, axis):
+        return torch.unsqueeze(x, axis)
+
+    def reshape(self, x, shape):
+        return torch.reshape(x, tuple(int(k) for k in shape))
+
+    def argsort(self, x):
+        return torch.argsort(x, stable=True)
 
     @staticmethod
     def _shape(shape):
@@ -150,8 +211,8 @@ class TfShim(object):
     def gather(self, params, indices):
         return params[torch.as_tensor(indices).long()]
 
-    def range(self, n):
-        return torch.arange(int(n), dtype=torch.int32)
+    def range(self, n, dtype=torch.int32):
+        return torch.arange(int(n), dtype=dtype).as_subclass(_TfTensor)
 
     def searchsorted(self, sorted_sequence, values, side="left"):
         return torch.searchsorted(sorted_sequence.contiguous(), values.contiguous(), right=(side == "right")).to(torch.int32)
@@ -369,6 +430,8 @@ def load_reference(oracle):
         (d + "piso_tf.py", {"piso_step", "advection_matrix_cuda", "pressure_extrapolation", "SimulationParameters"}),
         (d + "combined_training_integrated.py", {"zero_gradient_op", "run_piso_steps"}),
         (d + "networks.py", {"fullyconv_network"}),
+        (d + "evaluation_tools.py", {"tf_fftshift", "EK_spectrum_2D_tf", "EK_spectrum_1D_tf"}),
+        (d + "losses.py", None),
         (REF + "/spatial_mixing_layer_differentiable_training.py", {"neural_network_wrapper"}),
     ]
     for path, names in wanted:

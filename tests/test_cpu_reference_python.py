@@ -174,3 +174,21 @@ def test_closure_coupling_of_first_unrolled_step_matches_reference():
                                                  nn_in, velocity, {}, sim_par, None, [[0, 0], [0, 0]])
     assert rel_l2(out.numpy(), g["nn_out"][0]) < 1e-6
     assert not out[:, :, 42:].any()
+
+
+@pytest.mark.parametrize("name,factor", [("L2_field_loss", 50), ("spectral_energy_loss", 0.5), ("strain_rate_loss", 2),
+                                         ("multistep_averaging_loss", 0.5)])
+def test_losses_match_reference(name, factor):
+    """diffpiso/losses.py executed from source (summed and per-step variants, cropped window, sponge cut) vs
+    diffpiso_b200.losses."""
+    import torch
+    from diffpiso_b200 import StaggeredGrid, losses as L
+    g = np.load(os.path.join(GOLD, "losses.npz"))
+    steps = g["fields"].shape[0]
+    grids = [StaggeredGrid(torch.from_numpy(g["fields"][k]), dx=float(g["dx"])) for k in range(steps)]
+    gt, bw, sponge = torch.from_numpy(g["gt"]), g["buffer_width"].tolist(), int(g["sponge_start"])
+    fn = getattr(L, name)
+    total, _ = fn(0, [grids], [gt], steps, bw, factor, sponge, sum_steps=True, loss_influence_range=2)
+    per, _ = fn([0.0] * steps, [grids], [gt], steps, bw, factor, sponge, sum_steps=False, loss_influence_range=2)
+    assert np.isclose(float(total), float(g[name + "_sum"]), rtol=2e-5)
+    assert np.allclose([float(x) for x in per], g[name + "_steps"], rtol=2e-5)
