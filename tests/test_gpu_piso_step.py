@@ -167,3 +167,35 @@ def test_cpu_tensors_fail_loudly():
     pressure = dp.CenteredGrid(torch.as_tensor(pres).reshape(1, s["ny"], s["nx"], 1))
     with pytest.raises(dp._native.DpisoError):
         dp.piso_step(velocity, pressure, pressure, pressure, 0.01, sim, torch.as_tensor(s["dirichlet_values"])[None])
+
+
+def test_long_rollout_turbulence_statistics_within_one_percent():
+    """north_star: "long-rollout turbulence statistics within 1 %".  Decaying 2-D turbulence, periodic 64^2, nu = 1e-3,
+    CFL 0.5, 200 steps (about ten time units) on the GPU and with the oracle from the same seeded state: kinetic
+    energy, enstrophy and the shell-summed energy spectrum E(k), k = 1..16 (evaluation_tools.py:92-113) agree within
+    1 %; the fields themselves still agree to 1e-3 after 200 steps."""
+    import diffpiso_b200 as dp
+    from diffpiso_b200 import setups as SU, statistics as S
+    s = SU.periodic_box(64, 64, visc=1e-3)
+    sim = build_sim(s)
+    ny = nx = 64
+    vel0, pres0 = random_fields(s, 77)
+    vel, pres = np.stack([vel0, random_fields(s, 78)[0]]), np.stack([pres0, pres0])
+    ov, op = vel0.copy(), pres0.copy()
+    for _ in range(200):
+        out = run_step(s, sim, vel, pres)
+        vel, pres = out[0].flat.cpu().numpy(), out[1].data.reshape(2, -1).cpu().numpy()
+        ov, op, _ = O.piso_step(s, ov, op)
+
+    def stats(flat):
+        g = dp.StaggeredGrid(flat=torch.as_tensor(flat[None]), resolution=(ny, nx), dx=(s["dy"], s["dx"]),
+                             extrapolation="periodic")
+        k, e = S.EK_spectrum_2D(g.at_centers().data[0], None)
+        return float(S.kinetic_energy(g)[0]), float(S.enstrophy(g)[0]), e[1:17]
+    ke_g, en_g, e_g = stats(vel[0])
+    ke_o, en_o, e_o = stats(ov)
+    ke_0, en_0, _ = stats(vel0)
+    assert ke_o < 0.95 * ke_0 and en_o < 0.9 * en_0                      # the flow did evolve
+    assert abs(ke_g / ke_o - 1) < 0.01 and abs(en_g / en_o - 1) < 0.01
+    assert np.abs(e_g / e_o - 1).max() < 0.01
+    assert rel_l2(vel[0], ov) < 1e-3
