@@ -154,16 +154,22 @@ def test_pressure_cg_matches_oracle(name, fp64):
             assert rel_l2(x[i], x64) < 1e-1, (name, i, rel_l2(x[i], x64), int(its[i]), oit)
 
 
-def test_pressure_cg_large_grid_global_variant():
-    """A grid whose row blocks do not fit 16 CTAs (264 x 256 = 67 584 cells) takes the global-memory variant of the CG
-    kernel (config variant 6): same control flow, iteration count within the slack, solution within tolerance."""
+@pytest.mark.parametrize("variant", [7, 6])
+def test_pressure_cg_large_grid_global_variant(variant):
+    """A grid whose row blocks do not fit 16 CTAs (264 x 256 = 67 584 cells) takes a global-memory variant of the CG
+    kernel: 7 = cooperative launch, nSM / batch CTAs per sample with a global-memory group barrier (default), 6 =
+    cluster of 16 CTAs per sample.  Same control flow, iteration count within the slack, solution within tolerance."""
     from common import cg_iteration_slack
-    from diffpiso_b200 import ops, setups as SU
+    from diffpiso_b200 import _native as N, ops, setups as SU
     s = SU.periodic_box(264, 256, visc=1e-3)
     g, m, a_diag, beta, dx_factor, div = _cg_problem(s, 9, 2)
     lap = ops.laplace(g, m["active"], m["access"], _t(a_diag), 1, beta, dx_factor, fp64=True)
-    x, its = ops.pressure_cg(g, lap, _t(div), s["cg_tol"], s["cg_max_it"], s["cg_reset"], s["rank_deficient"])
-    assert ops.pressure_cg_config()["variant"] == 6
+    N.lib.dpiso_pressure_cg_set_tuning(0, variant if variant == 6 else -1)
+    try:
+        x, its = ops.pressure_cg(g, lap, _t(div), s["cg_tol"], s["cg_max_it"], s["cg_reset"], s["rank_deficient"])
+        assert ops.pressure_cg_config()["variant"] == variant
+    finally:
+        N.lib.dpiso_pressure_cg_set_tuning(0, -1)
     lap_h = lap.cpu().numpy()
     for i in range(2):
         ox, oit = O.pressure_cg(s["ny"], s["nx"], True, True, lap_h[i].ravel(), div[i].astype(np.float64), s["cg_tol"],
