@@ -235,6 +235,17 @@ def run_ours(args):
         cg_events.append((e0, e1, out[1]))
         return out
     ops.pressure_cg = timed_cg
+    bicg_events = []
+    orig_bicg = ops.bicgstab_ilu
+
+    def timed_bicg(*a, **k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = orig_bicg(*a, **k)
+        e1.record()
+        bicg_events.append((e0, e1, out[1]))
+        return out
+    ops.bicgstab_ilu = timed_bicg
 
     vel, pres = torch.as_tensor(vel_h).to(dev), torch.as_tensor(pres_h).to(dev)
     for _ in range(args.warmup):
@@ -248,6 +259,7 @@ def run_ours(args):
 
     # ---- device-resident timing --------------------------------------------------------------------------------
     cg_events.clear()
+    bicg_events.clear()
     launches["n"] = 0
     sampler = ClockSampler(local) if rank == 0 else None
     barrier()
@@ -262,6 +274,8 @@ def run_ours(args):
     clocks = sampler.stop() if sampler else None
     cg_ms = [a.elapsed_time(b) for a, b, _ in cg_events]
     cg_its = np.concatenate([it.cpu().numpy() for _, _, it in cg_events]).astype(np.float64)
+    bicg_ms = [a.elapsed_time(b) for a, b, _ in bicg_events]
+    bicg_its = np.concatenate([st.cpu().numpy()[:, :, 0].ravel() for _, _, st in bicg_events]).astype(np.float64)
     finite = bool(torch.isfinite(vel).all() and torch.isfinite(gv).all())
 
     # ---- forward-only rollout (reported beside the headline) -------------------------------------------------------
@@ -353,6 +367,21 @@ def run_ours(args):
     except Exception:
         pass
     cfg = ops.pressure_cg_config()
+    # second kernel: BiCGStab+ILU0 (setup 36 + ILU 40 + 224 per iteration, bytes per row)
+    bicg_it = float(bicg_its.mean())
+    bicg_bytes = BATCH * nf * (36.0 + 40.0 + 224.0 * bicg_it)
+    bicg_avg_ms = float(np.mean(bicg_ms))
+    bicg_traffic = None
+    try:
+        bicg_traffic = json.load(open(os.path.join(ROOT, "profiles", "bicg_dram_traffic.json")))["bytes_per_launch"]
+    except Exception:
+        pass
+    # whole step against the step model of SURVEY 8(d) (forward: assembly 56 + ILU 80 + glue 120 + 2 Laplace 96 +
+    # 448 it_bicg + 168 (it_cg1 + it_cg2) bytes per cell; backward the same without the assembly, plus ILU again because
+    # the adjoint re-factorises)
+    n_cg = len(cg_ms) // args.steps
+    step_bytes = BATCH * nc * (56 + 2 * 80 + 2 * 120 + 4 * 48 + 448 * 2 * bicg_it + 168 * mean_it * n_cg)
+    step_achieved = step_bytes / (ms / args.steps * 1e-3) / 1e9
     line = {
         "metric": "piso_cell_updates_per_s_fwd_adjoint", "value": value, "unit": "cell-updates/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -375,6 +404,15 @@ def run_ours(args):
                              "of SURVEY 8(d) (168 B/cell/iteration) is exceeded by design (frac > 1); traffic = "
                              "ncu-measured DRAM bytes per launch (profiles/cg_dram_traffic.json); the kernel is bound "
                              "by issue slots and reduction latency, see profiles/r01_summary.md"},
+        "roofline_bicgstab": {"bound": "hbm", "kernel": "bicgstab_kernel (one 512-thread CTA per system, 2 launches per step)",
+                              "achieved": bicg_bytes / (bicg_avg_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                              "frac": bicg_bytes / (bicg_avg_ms * 1e-3) / 1e9 / peak, "traffic": bicg_traffic,
+                              "mean_iterations": bicg_it, "avg_launch_ms": bicg_avg_ms,
+                              "share_of_step": float(sum(bicg_ms) / ms),
+                              "note": "latency-bound: 13 triangular sweeps x 255 dependent wavefront levels per solve"},
+        "roofline_step": {"bound": "hbm", "achieved": step_achieved, "peak": peak, "unit": "GB/s", "frac": step_achieved / peak,
+                          "algorithmic_bytes_per_step": step_bytes,
+                          "note": "SURVEY 8(d) step model with the iteration counts of this run"},
         "clocks": clocks, "finite": finite,
     }
     if args.cpu_baseline:

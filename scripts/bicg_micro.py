@@ -8,11 +8,13 @@ import torch
 from diffpiso_b200 import ops, setups as SU, _native as N
 
 def main():
-    ny = nx = 128; B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+    B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+    ny = nx = int(sys.argv[2]) if len(sys.argv) > 2 else 128
     dev = "cuda:0"
     s = SU.periodic_box(ny, nx, visc=1e-3)
     g = ops.Geometry.get(ny, nx, True, True, dev)
-    vel = torch.as_tensor(np.stack([SU.solenoidal_field(ny, nx, seed=100 + i) for i in range(B)])).to(dev)
+    base = SU.solenoidal_field(ny, nx, seed=100)
+    vel = torch.as_tensor(np.stack([base if ny > 256 else SU.solenoidal_field(ny, nx, seed=100 + i) for i in range(B)])).to(dev)
     ones = torch.ones((ny + 2) * (nx + 2), device=dev)
     dm = torch.zeros(g.nf, dtype=torch.uint8, device=dev); ns = torch.zeros((ny + 2) * (nx + 2), dtype=torch.uint8, device=dev)
     beta = float(np.float32(s["dy"] * s["dx"] / s["dt"]))
