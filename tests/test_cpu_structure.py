@@ -171,6 +171,15 @@ def test_cabi_argument_errors_without_gpu():
     assert (n[0], n[1], z[0], z[1]) == O.sizes(33, 32, 0, 0)
     assert N.lib.dpiso_sizes(128, 128, 1, 1, n, z) == 0
     assert (n[0], n[1], z[0], z[1]) == (16512, 16512, 82560, 82560)
+    # solver entry points: empty batch, null pointers, bad cadence -> EINVAL before anything is launched
+    null = None
+    assert N.lib.dpiso_pressure_cg_f64(0, 16, 16, 1, 1, null, null, 1e-8, 10, 10, 1, null, null, null, null) == -1
+    assert b"bad sizes" in N.lib.dpiso_last_error()
+    assert N.lib.dpiso_pressure_cg_f64(1, 16, 16, 1, 1, null, null, 1e-8, 10, 10, 1, null, null, null, null) == -1
+    assert b"null pointer" in N.lib.dpiso_last_error()
+    assert N.lib.dpiso_bicgstab_ilu(0, null, null, 0, 0, null, null, null, 1e-8, 10, null, null, null, null, null) == -1
+    assert N.lib.dpiso_assemble(0, 16, 16, 0, 0, 1.0, 1.0, 1.0, 1.0, 1.0, null, null, null, null, null, 0, null, null, null) == -1
+    assert b"batch must be >= 1" in N.lib.dpiso_last_error()
 
 
 def test_product_never_imports_oracle():
