@@ -12,7 +12,7 @@ from .pressure_solver import PisoPressureSolverCudaCustom, PoissonSolver
 from .masks import compute_mixingLayer_masks, temporal_mixing_layer_masks, update_dirichlet_values
 from .networks import fullyconv_network, initialise_fullyconv_network
 from .losses import L2_field_loss, multistep_averaging_loss, spectral_energy_loss, strain_rate_loss
-from .training import run_piso_steps, zero_gradient_op
+from .training import boundary_perturbation_fun, inference_rollout, run_piso_steps, zero_gradient_op
 from .datamanagement import create_base_dir, data_path_assembler, load_function
 
 __all__ = ["CenteredGrid", "StaggeredGrid", "flatten_staggered_data", "stagger_flattened_data",
@@ -22,5 +22,6 @@ __all__ = ["CenteredGrid", "StaggeredGrid", "flatten_staggered_data", "stagger_f
            "finite_volume_gradient_tensor", "finite_volume_divergence", "explicit_H_csr",
            "compute_mixingLayer_masks", "temporal_mixing_layer_masks", "update_dirichlet_values", "fullyconv_network",
            "initialise_fullyconv_network", "L2_field_loss", "spectral_energy_loss", "strain_rate_loss",
-           "multistep_averaging_loss", "run_piso_steps", "zero_gradient_op", "create_base_dir", "data_path_assembler",
+           "multistep_averaging_loss", "run_piso_steps", "zero_gradient_op", "inference_rollout",
+           "boundary_perturbation_fun", "create_base_dir", "data_path_assembler",
            "load_function"]

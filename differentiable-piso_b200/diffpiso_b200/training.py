@@ -130,3 +130,57 @@ def training_iteration(optimizer, weights, loss_fn):
     allreduce_gradients(weights)
     optimizer.step()
     return loss.detach()
+
+
+def boundary_perturbation_fun(domain, average_velocity, shape, time, perturbation_amplitudes):
+    """combined_training_integrated.py:7-14 (after J. Ko et al.): time-dependent perturbation of the inflow profile of
+    the spatial mixing layer, one value per row of the padded grid.  `domain` needs `.resolution` and the box height
+    (`.box` = (ly, lx) or an object with `.size`)."""
+    ny = int(domain.resolution[0])
+    box = domain.box
+    ly = float(np.asarray(box.size if hasattr(box, "size") and not isinstance(box, np.ndarray) else box).ravel()[0])
+    y_disc = np.linspace(0, ly, ny + 2) - ly / 2
+    eps = [perturbation_amplitudes[0] * average_velocity, perturbation_amplitudes[1] * average_velocity]
+    n = [.4 * np.pi, .3 * np.pi]
+    omeg = [.22, .11]
+    u_perturb = np.sum([eps[i] * np.cos(n[i] * y_disc) * (1 - np.tanh(y_disc / 2) ** 2) * np.sin(omeg[i] * time)
+                        for i in range(len(eps))], axis=0)
+    return np.reshape(u_perturb, shape)
+
+
+def inference_rollout(velocity, pressure, timesteps, domain, physical_parameters, simulation_parameters, sim_physics,
+                      viscosity_field, bcx=None, perturbation_fun=None, dirichlet_placeholder_update=None,
+                      neural_network=None, neural_network_wrapper=None, training_dict=None, save_dir=None,
+                      on_step=None):
+    """Forward roll-out as in spatial_mixing_layer_differentiable_inference.py:100-165 (and the data generator
+    spatial_mixing_layer.py:52-92): `timesteps - 1` PISO steps, the inflow perturbation re-evaluated every step, the
+    closure network's forcing if a network is given; frames are written as velocity_/pressure_/nn_forcing_%06d.npz
+    (batch 1) when `save_dir` is set.  Unlike the reference the state stays on the GPU between steps.
+    -> (velocity, pressure) grids after the last step."""
+    from .datamanagement import frame_path, save_frame
+    device = velocity.flat.device
+    td = dict(step_count=1, HR_buffer_width=[[0, 0], [0, 0]], pressure_included=True, loss_influence_range=1)
+    if training_dict is not None:
+        td.update({k: training_dict[k] for k in ("HR_buffer_width", "pressure_included") if k in training_dict})
+    if save_dir is not None:
+        save_frame(save_dir, 0, velocity, pressure)
+    dt = simulation_parameters["dt"] * simulation_parameters["dt_ratio"]
+    base_values = sim_physics.dirichlet_values
+    with torch.no_grad():
+        for i in range(1, timesteps):
+            if perturbation_fun is not None and dirichlet_placeholder_update is not None:
+                ny = int(velocity.resolution[0])
+                pert = torch.as_tensor(np.asarray(perturbation_fun((1, ny + 2, 1, 1), dt * i), np.float32), device=device)
+                bc = torch.as_tensor(np.asarray(bcx, np.float32), device=device) + pert
+                sim_physics.dirichlet_values = dirichlet_placeholder_update(base_values, (([], []), (bc, [])))
+            out = run_piso_steps(velocity, pressure, domain, physical_parameters, simulation_parameters, td, neural_network,
+                                 neural_network_wrapper, sim_physics, viscosity_field, bcx, None, None, None)
+            velocity, pressure = out[3], out[4]
+            if save_dir is not None:
+                save_frame(save_dir, i, velocity, pressure)
+                if neural_network is not None:
+                    np.savez(frame_path(save_dir, "nn_forcing", i), out[5].detach().cpu().numpy())
+            if on_step is not None:
+                on_step(i, velocity, pressure)
+    sim_physics.dirichlet_values = base_values
+    return velocity, pressure

@@ -202,3 +202,41 @@ def test_long_rollout_turbulence_statistics_within_one_percent():
     assert abs(ke_g / ke_o - 1) < 0.01 and abs(en_g / en_o - 1) < 0.01
     assert np.abs(e_g / e_o - 1).max() < 0.01
     assert rel_l2(vel[0], ov) < 1e-3
+
+
+def test_inference_rollout_with_inflow_perturbation_matches_oracle(tmp_path):
+    """spatial mixing layer 16x48: 6 frames of `inference_rollout` (inflow profile perturbed every step,
+    spatial_mixing_layer_differentiable_inference.py:118-133), frames written in the reference's npz format; the final
+    state equals an oracle roll-out fed with the same per-step Dirichlet values."""
+    import diffpiso_b200 as dp
+    from diffpiso_b200 import datamanagement as D, masks as M, setups as SU, training as T
+    s = SMALL_SETUPS["sml16x48"]()
+    sim = build_sim(s)
+    sim.dirichlet_values = torch.as_tensor(s["dirichlet_values_staggered"]).to(DEV)
+    ny, nx = s["ny"], s["nx"]
+    vel0, pres0 = random_fields(s, 91)
+    velocity = dp.StaggeredGrid(flat=torch.as_tensor(vel0[None]).to(DEV), resolution=(ny, nx), dx=(s["dy"], s["dx"]))
+    pressure = dp.CenteredGrid(torch.as_tensor(pres0).reshape(1, ny, nx, 1).to(DEV), dx=(s["dy"], s["dx"]),
+                               extrapolation=extrap(s["pbc"]))
+
+    class Dom(object):
+        resolution = (ny, nx)
+        box = (ny * s["dy"], nx * s["dx"])
+    bcx = s["inlet_profile"].reshape(1, ny + 2, 1, 1)
+    pert = lambda shape, t: T.boundary_perturbation_fun(Dom, 1.0, shape, t, (0.05, 0.05))
+    update = lambda dv, pl: M.update_dirichlet_values(dv, ((False, False), (True, False)), pl)
+    sim_par = dict(dt=s["dt"], dt_ratio=1, dx_ratio=1)
+    d = str(tmp_path)
+    v_end, p_end = T.inference_rollout(velocity, pressure, 6, Dom, {}, sim_par, sim,
+                                       torch.as_tensor(np.asarray(s["visc"], np.float32)).to(DEV), bcx=bcx,
+                                       perturbation_fun=pert, dirichlet_placeholder_update=update, save_dir=d)
+    assert sorted(f for f in __import__("os").listdir(d))[-1] == "velocity_000005.npz"
+    fv, fp = D.load_frame(d, 5)
+    assert fv.shape == (1, ny + 1, nx + 1, 2) and np.array_equal(fv, v_end.staggered_tensor().cpu().numpy())
+    ov, op = vel0, pres0
+    for i in range(1, 6):
+        bc = (bcx + pert((1, ny + 2, 1, 1), s["dt"] * i)).astype(np.float32)
+        dv = M.update_dirichlet_values(s["dirichlet_values_staggered"], ((False, False), (True, False)), (([], []), (bc, [])))
+        ov, op, _ = O.piso_step(s, ov, op, dirichlet_values=SU.flatten_staggered(dv.astype(np.float32))[0])
+    assert rel_l2(v_end.flat[0].cpu().numpy(), ov) < 5e-5
+    assert rel_l2(p_end.data.cpu().numpy().ravel(), op) < 5e-4
