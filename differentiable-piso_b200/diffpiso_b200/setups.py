@@ -118,6 +118,32 @@ def lid_driven_cavity(n=32, re=100.0, dt=0.01, bicg_tol=1e-8, bicg_max_it=100, c
     return _finish(s, stack_staggered(dm_v, dm_u), stack_staggered(dv_v, dv_u), active, access, noslip)
 
 
+def obstacle_channel(ny=16, nx=24, block=(6, 10, 8, 13), ly=None, lx=None, visc=1e-2, dt=0.02, solver_precision=1e-8,
+                     cg_reset=1000):
+    """Closed box with a solid rectangular obstacle (cells [y0, y1) x [x0, x1)) -- no reference script builds one, but
+    the kernels' mask logic (solid neighbours in the Laplace rows laplace_op.cu.cc:125-174, the `tBB` / no-slip terms of
+    the momentum rows central_difference_csr_op.cu.cc:252-288) is only exercised by interior solid cells.  Masks follow
+    the conventions of lid_driven_cavity_2d.py:19-43: active = accessible = 1 in fluid cells, Dirichlet (value 0) on
+    every face that touches a solid cell or the wall, no-slip flag on solid cells."""
+    ly = float(ny) / 8 if ly is None else ly
+    lx = float(nx) / 8 if lx is None else lx
+    s = _base(ny, nx, spacing(ly, ny), spacing(lx, nx), dt, False, False)
+    y0, y1, x0, x1 = block
+    fluid = np.ones((ny, nx), np.float32)
+    fluid[y0:y1, x0:x1] = 0
+    padded = np.pad(fluid, ((1, 1), (1, 1)))                         # solid ring = walls
+    # u face (y, x) sits between padded cells (y+1, x) and (y+1, x+1); v face (y, x) between (y, x+1) and (y+1, x+1)
+    dm_u = 1.0 - np.minimum(padded[1:-1, :-1], padded[1:-1, 1:])
+    dm_v = 1.0 - np.minimum(padded[:-1, 1:-1], padded[1:, 1:-1])
+    mask = padded[None, :, :, None].astype(np.float32)
+    noslip = (padded == 0)[None, :, :, None]
+    s.update(pbc=[ZERO] * 4, pbc_inc=[ZERO] * 4, visc=np.float32(visc), rank_deficient=rank_deficient_from_masks(mask, mask),
+             bicg_tol=solver_precision, bicg_max_it=1000, cg_tol=solver_precision, cg_max_it=5000, cg_reset=cg_reset,
+             cg_fp64=True, name="obstacle_channel_%dx%d" % (ny, nx))
+    return _finish(s, stack_staggered(dm_v[None].astype(np.float32), dm_u[None].astype(np.float32)),
+                   np.zeros((1, ny + 1, nx + 1, 2), np.float32), mask, mask.copy(), noslip)
+
+
 def periodic_box(ny=128, nx=128, length=2 * math.pi, visc=1e-3, dt=None, cfl=0.5, umax=1.0, bicg_tol=1e-8,
                  bicg_max_it=10000, cg_tol=1e-8, cg_max_it=10000, cg_reset=1000, cg_fp64=True):
     """Fully periodic box (C2 / C5 of BASELINE.json).  All masks 1, no Dirichlet faces."""

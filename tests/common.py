@@ -35,6 +35,7 @@ SMALL_SETUPS = {
     "periodic32": lambda: SU.periodic_box(32, 32, visc=1e-3),
     "tml16x24": lambda: SU.temporal_mixing_layer(ny=16, nx=24, visc=2e-3, dt=0.05),
     "sml16x48": lambda: SU.spatial_mixing_layer(ny=16, nx=48, box=(8.0, 24.0), dt=0.05, solver_precision=1e-6),
+    "obstacle16x24": lambda: SU.obstacle_channel(ny=16, nx=24),
 }
 # grids that take the strip-layout fast path of the pressure CG (rows per CTA = 8*G, G*nx threads in {256, 512})
 STRIP_SETUPS = {

@@ -21,7 +21,13 @@ from oracle import oracle as O                      # noqa: E402
 import reference_runner as RR                       # noqa: E402
 
 OUT = os.path.join(HERE, "ref_python")
-SETUPS = ["ldc8", "periodic16", "periodic24x20", "tml16x24", "sml16x48"]
+# The pressure solver stops on an ABSOLUTE residual (1e-8).  With O(1) loss weights the adjoint right-hand sides are
+# O(10..100) and their fp32 rounding leaves a non-zero mean of ~1e-5 over the fluid cells, which a rank-deficient system
+# can never reduce below the tolerance: the reference's own adjoint CG then runs into max_iterations and returns
+# garbage (seen for ldc8's Dirichlet gradient and the obstacle case).  Gradients are linear in the weights, so the
+# obstacle case uses small ones.
+WEIGHT_SCALE = {"obstacle16x24": 1e-3}
+SETUPS = ["ldc8", "periodic16", "periodic24x20", "tml16x24", "sml16x48", "obstacle16x24"]
 
 
 def _material(ns, code):
@@ -250,7 +256,9 @@ def main():
     unroll_goldens(ns, log)
     for name in SETUPS:
         s = SMALL_SETUPS[name]()
-        res = run_reference_step(ns, log, s, *inputs_for(s))
+        vel, pres, forcing, w_u, w_p = inputs_for(s)
+        k = np.float32(WEIGHT_SCALE.get(name, 1.0))
+        res = run_reference_step(ns, log, s, vel, pres, forcing, w_u * k, w_p * k)
         np.savez_compressed(os.path.join(OUT, "step_%s.npz" % name), **res)
         print(name, "cg", res["cg_iterations"], "bicg", res["bicg_iterations"], "bwd", list(res["bwd_ops"]))
 

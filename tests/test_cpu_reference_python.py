@@ -19,7 +19,7 @@ from oracle import adjoint as A
 from oracle import oracle as O
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_python")
-STEP_SETUPS = ["ldc8", "periodic16", "periodic24x20", "tml16x24", "sml16x48"]
+STEP_SETUPS = ["ldc8", "periodic16", "periodic24x20", "tml16x24", "sml16x48", "obstacle16x24"]
 
 
 def load_step(name):

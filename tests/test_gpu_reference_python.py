@@ -19,7 +19,7 @@ def _t(a, grad=False):
     return t.requires_grad_(True) if grad else t
 
 
-@pytest.mark.parametrize("name", ["ldc8", "periodic16", "periodic24x20", "tml16x24", "sml16x48"])
+@pytest.mark.parametrize("name", ["ldc8", "periodic16", "periodic24x20", "tml16x24", "sml16x48", "obstacle16x24"])
 def test_piso_step_forward_backward_matches_reference_python(name):
     """Integer/assembly outputs bit-exact; fields within the north_star 1e-5 relative L2; iteration counts +-1
     (BiCGStab) / quantisation slack (CG); gradients within 1e-4 (three nested iterative solves)."""
