@@ -17,7 +17,7 @@ def _t(a, dtype=torch.float32):
     return torch.as_tensor(np.ascontiguousarray(a)).to(dtype).to(DEV)
 
 
-@pytest.mark.parametrize("name", ["ldc8", "periodic16", "periodic24x20", "tml16x24", "sml16x48"])
+@pytest.mark.parametrize("name", ["ldc8", "periodic16", "periodic24x20", "tml16x24", "sml16x48", "obstacle16x24"])
 def test_pointwise_adjoint_kernels(name):
     from diffpiso_b200 import ops
     s = SMALL_SETUPS[name]()
@@ -62,7 +62,7 @@ def test_pointwise_adjoint_kernels(name):
     assert abs((hd * gs).sum() - (d.astype(np.float64) * ht).sum()) < 1e-4 * abs((hd * gs).sum()) + 1e-6
 
 
-@pytest.mark.parametrize("name", ["ldc8", "sml16x48"])
+@pytest.mark.parametrize("name", ["ldc8", "sml16x48", "obstacle16x24"])
 def test_nonperiodic_adjoints_are_exact_transposes(name):
     """<G p, s> == <p, G^T s> and <D v, g> == <v, D^T g> on grids without periodic axes."""
     from diffpiso_b200 import ops

@@ -64,7 +64,7 @@ def test_assemble_matches_oracle(name):
         assert np.array_equal(a_diag[i].cpu().numpy(), oa)
 
 
-@pytest.mark.parametrize("name", ["ldc8", "periodic16", "tml16x24", "sml16x48"])
+@pytest.mark.parametrize("name", ["ldc8", "periodic16", "tml16x24", "sml16x48", "obstacle16x24"])
 def test_gradient_divergence_laplace_match_oracle(name):
     from diffpiso_b200 import ops
     s = SMALL_SETUPS[name]()
@@ -106,7 +106,7 @@ def _cg_problem(s, seed, batch):
     return g, m, a_diag, c["beta"], c["dx_factor"], div
 
 
-@pytest.mark.parametrize("name", ["ldc8", "ldc32", "periodic16", "periodic24x20", "periodic32", "tml16x24", "sml16x48"] +
+@pytest.mark.parametrize("name", ["ldc8", "ldc32", "periodic16", "periodic24x20", "periodic32", "tml16x24", "sml16x48", "obstacle16x24"] +
                          list(STRIP_SETUPS))
 @pytest.mark.parametrize("fp64", [True, False])
 def test_pressure_cg_matches_oracle(name, fp64):
@@ -191,7 +191,7 @@ def test_pressure_cg_zero_rhs_and_max_iterations():
     assert its.cpu().tolist() == [37, 37] and torch.isfinite(x).all()
 
 
-@pytest.mark.parametrize("name", ["ldc8", "periodic16", "periodic24x20", "tml16x24", "sml16x48"])
+@pytest.mark.parametrize("name", ["ldc8", "periodic16", "periodic24x20", "tml16x24", "sml16x48", "obstacle16x24"])
 @pytest.mark.parametrize("transpose", [False, True])
 def test_bicgstab_matches_oracle(name, transpose):
     """Assembled -M systems of 2 samples: solution within 1e-5 relative L2 of the oracle, iteration counts / restarts /

@@ -98,7 +98,7 @@ def ref_pressure(lib, s, k_vu, div, fp64, tol):
     return lap, x, int(it[0])
 
 
-@pytest.mark.parametrize("name", ["ldc8", "ldc32", "periodic16", "periodic24x20", "periodic32", "tml16x24", "sml16x48"])
+@pytest.mark.parametrize("name", ["ldc8", "ldc32", "periodic16", "periodic24x20", "periodic32", "tml16x24", "sml16x48", "obstacle16x24"])
 @pytest.mark.parametrize("fp64", [True, False])
 def test_oracle_pressure_solve_equals_reference_kernels(ref, name, fp64):
     """Laplace matrix bit-exact; fp64 CG iteration count equal up to one check period (the quantised cadence of SURVEY
