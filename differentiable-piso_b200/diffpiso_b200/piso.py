@@ -96,6 +96,7 @@ class _PisoStepFn(torch.autograd.Function):
         p2, its2, lap2 = _pressure_solve(c, a_diag, div2, 1000 + c.unrolling_step)
         vel_next, pres_next = ops.corrector2(g, u_s2, h, p2, a_diag, pres, p1, m["access"], c.dy, c.dx, c.beta, c.pbc_inc)
         ctx.c = c
+        ctx.set_materialize_grads(False)        # no zero-filled gradients for the 15 non-differentiable extras
         ctx.has_forcing = forcing is not None
         ctx.dvals_batched = dvals.shape[0] == vel.shape[0]
         ctx.save_for_backward(values, values_neg, a_diag, vel)
