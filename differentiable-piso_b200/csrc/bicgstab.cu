@@ -687,10 +687,14 @@ int dpiso_bicgstab_ilu(int batch, const dpiso_bicg_tables *h_tab_u, const dpiso_
         prm.ring_depth = region_ints >= 16 * P * 9 ? 16 : (region_ints >= 8 * P * 9 ? 8 : 2);
         if (region_ints < 2 * P * 9) prm.compact = 0;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        DPISO_CUDA_TRY(cudaFuncSetAttribute(bicgstab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 1024));
-        attr_set = true;
+    {   // the attribute is per device: remember which devices of this process have it
+        static unsigned long long attr_set_mask = 0;
+        int dev = 0;
+        DPISO_CUDA_TRY(cudaGetDevice(&dev));
+        if (dev >= 64 || !(attr_set_mask & (1ull << dev))) {
+            DPISO_CUDA_TRY(cudaFuncSetAttribute(bicgstab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 1024));
+            if (dev < 64) attr_set_mask |= 1ull << dev;
+        }
     }
     bicgstab_kernel<<<batch * 2, kBicgThreads, smem, (cudaStream_t)stream>>>(prm);
     DPISO_CHECK_LAUNCH();
