@@ -25,8 +25,8 @@ constexpr int kBicgThreads = 512;
 constexpr int kMaxWa = 6;
 
 struct BicgTab {
-    int n, n_levels, wa, max_level, wl, wu;
-    const int *level_ptr, *perm, *a_col, *a_src, *a_rev;
+    int n, n_levels, wa, max_level, wl, wu, dx, rows_ok;
+    const int *level_ptr, *perm, *a_col, *a_src, *a_rev, *r_col, *r_src, *r_rev;
 };
 
 struct BicgParams {
@@ -41,6 +41,8 @@ struct BicgParams {
     int lp_cap;            // ints reserved for the level_ptr copy in smem
     int compact;           // rows have <= 4 lower and <= 4 upper entries: compact triangular sweeps
     int ring_depth;        // levels in flight in the cp.async ring (16, 8 or 2)
+    int rows_kernel;       // 1: bicgstab_rows_kernel (row-major layout, one thread per grid row in the sweeps)
+    int rows_threads;      // its sweep threads P = roundup32(max dy)
     int dbg;               // profiling experiments only (DPISO_BICG_DBG): 1 skip level barrier, 2 skip refill, 4 skip recurrence
     const float *values, *rhs, *x0;
     float *x;
@@ -293,6 +295,9 @@ struct CompactPlanes {
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
@@ -610,6 +615,318 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_kernel(const BicgPar
     }
 }
 
+
+// ===============================================================================================================
+// Row-major variant (default where the grid allows it).  Same algorithm, same arithmetic, same results as
+// bicgstab_kernel, but nothing is permuted: every vector and plane is indexed by the ORIGINAL row i = ly * dx + lx, and
+// the wavefront schedule is implicit.  In the three kinds of sweeps (ILU(0), L solve, U solve) thread j owns grid row
+// ly = j and walks along x as the level d = lx + ly advances, so
+//   * its row data is ONE contiguous stream per plane (pointer + x): a per-thread cp.async ring with compile-time slot
+//     offsets, no level pointers, no index arithmetic;
+//   * the x-neighbour operand is the thread's own previous result (a register), the y-neighbour operand is the
+//     neighbouring lane's previous result (one shuffle); only a warp-edge lane and the periodic wrap entries ("far") read
+//     the solve vector in shared memory, which the per-level named barrier has made complete;
+//   * entries sit in canonical slots by kind (lower: [far below the y-neighbour, y-neighbour, far above it,
+//     x-neighbour], upper: [x-neighbour, far below the y-neighbour, y-neighbour, far above it]) -- the ascending-column
+//     order of the row, hence the same fma chain as the CSR formulation (structure.py checks that every row fits).
+// ===============================================================================================================
+constexpr int kRowsRing = 8;
+
+struct RowsPlanes {
+    float4 *lval;      // [n] ILU: A lower values in, l_ik out
+    float4 *arv;       // [n] ILU only: reverse entries u_ki = A(k, i) of the lower slots (aliases rh, p, v, tt)
+    int2 *lfar;        // [n] columns of the two far lower slots, -1 = absent
+    float4 *uval;      // [n] upper values (unchanged by ILU(0) on this pattern)
+    int2 *ufar;        // [n]
+    float *udiag;      // [n] A diagonal in, pivot out
+};
+
+// MODE 0: ILU(0) (zs = pivots), 1: L solve (ext = right-hand side), 2: U solve
+template <int MODE>
+__device__ __noinline__ void sweep_rows(const RowsPlanes pl, const float *ext, int dx, int dy, int P) {
+    constexpr int D = kRowsRing;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4 *const r16a = (float4 *)smem_raw;                           // [D][P] values
+    float4 *const r16b = r16a + D * P;                                 // [D][P] ILU: reverse values
+    int2 *const r8 = (int2 *)(r16b + D * P);                           // [D][P] far columns
+    float *const r4 = (float *)(r8 + D * P);                           // [D][P] right-hand side / diagonal
+    float *const zs = r4 + D * P;                                      // [n] solve vector / pivots
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int nl = dx + dy - 1;
+    __syncthreads();
+    if (t < P) {
+        const bool rowok = t < dy;
+        const int i0 = t * dx;
+        const float4 *gval = MODE == 2 ? pl.uval : pl.lval;
+        const int2 *gfar = MODE == 2 ? pl.ufar : pl.lfar;
+        const float *gext = MODE == 1 ? ext : pl.udiag;
+        // x of this thread at sweep step s
+        auto x_of = [&](int s) { return (MODE == 2 ? nl - 1 - s : s) - t; };
+        auto issue = [&](int s, int slot) {
+            const int x = x_of(s);
+            if (rowok && s < nl && (unsigned)x < (unsigned)dx) {
+                const int i = i0 + x, k = slot * P + t;
+                cp_async16(r16a + k, gval + i);
+                if (MODE == 0) cp_async16(r16b + k, pl.arv + i);
+                cp_async8(r8 + k, gfar + i);
+                cp_async4(r4 + k, gext + i);
+            }
+            cp_async_commit();
+        };
+        const bool edge = MODE == 2 ? (lane == 31 && t + 1 < dy) : (lane == 0 && t > 0);
+        const int nb_off = MODE == 2 ? dx : -dx;
+#pragma unroll
+        for (int u = 0; u < D - 1; u++) issue(u, u);
+        float prev = 1.0f;                                             // (a finite non-zero stand-in for absent operands)
+#pragma unroll 1
+        for (int s0 = 0; s0 < nl; s0 += D) {
+#pragma unroll
+            for (int u = 0; u < D; u++) {
+                const int s = s0 + u;
+                issue(s + D - 1, (u + D - 1) % D);
+                cp_async_wait<D - 1>();
+                float nb = MODE == 2 ? __shfl_down_sync(0xffffffffu, prev, 1) : __shfl_up_sync(0xffffffffu, prev, 1);
+                const int x = x_of(s);
+                float res = prev;
+                if (rowok && s < nl && (unsigned)x < (unsigned)dx) {
+                    const int i = i0 + x, k = u * P + t;
+                    const float4 v = r16a[k];
+                    const int2 fc = r8[k];
+                    const float e = r4[k];
+                    if (edge) nb = zs[i + nb_off];
+                    if (MODE == 0) {
+                        // l_ik = a_ik / u_kk, u_ii = a_ii - sum l_ik u_ki, lower entries in ascending column order
+                        const float4 rv = r16b[k];
+                        const float p0 = fc.x >= 0 ? zs[fc.x] : 1.0f, p2 = fc.y >= 0 ? zs[fc.y] : 1.0f;
+                        const float l0 = __fdiv_rn(v.x, p0), l1 = __fdiv_rn(v.y, nb), l2 = __fdiv_rn(v.z, p2), l3 = __fdiv_rn(v.w, prev);
+                        float dg = fmaf(-l0, rv.x, e);
+                        dg = fmaf(-l1, rv.y, dg);
+                        dg = fmaf(-l2, rv.z, dg);
+                        dg = fmaf(-l3, rv.w, dg);
+                        pl.lval[i] = make_float4(l0, l1, l2, l3);
+                        pl.udiag[i] = dg;
+                        res = dg;
+                    } else if (MODE == 1) {
+                        const float f0 = fc.x >= 0 ? zs[fc.x] : 0.0f, f1 = fc.y >= 0 ? zs[fc.y] : 0.0f;
+                        float acc = fmaf(-v.x, f0, e);
+                        acc = fmaf(-v.y, nb, acc);
+                        acc = fmaf(-v.z, f1, acc);
+                        res = fmaf(-v.w, prev, acc);
+                    } else {
+                        const float f0 = fc.x >= 0 ? zs[fc.x] : 0.0f, f1 = fc.y >= 0 ? zs[fc.y] : 0.0f;
+                        float acc = fmaf(-v.x, prev, zs[i]);
+                        acc = fmaf(-v.y, f0, acc);
+                        acc = fmaf(-v.z, nb, acc);
+                        acc = fmaf(-v.w, f1, acc);
+                        res = __fdiv_rn(acc, e);
+                    }
+                    zs[i] = res;
+                }
+                prev = res;
+                named_bar(1, P);
+            }
+        }
+        cp_async_wait<0>();
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_rows_kernel(const BicgParams prm) {
+    long long tick = clock64();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double red[64];
+    const int sys = blockIdx.x;
+    const int sample = sys >> 1, comp = sys & 1;
+    const BicgTab &T = prm.tab[comp];
+    const int n = T.n, wa = T.wa, n_max = prm.n_max, dx = T.dx, dy = T.n / T.dx, P = prm.rows_threads;
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const int face_off = comp ? prm.tab[0].n : 0;
+    const float *values_c = prm.values + (size_t)sample * prm.nnz_total + (comp ? prm.nnz[0] : 0);
+    const int nnz_c = prm.nnz[comp];
+    const float *rhs_g = prm.rhs + (size_t)sample * prm.n_face + face_off;
+    const float *x0_g = prm.x0 + (size_t)sample * prm.n_face + face_off;
+    float *x_g = prm.x + (size_t)sample * prm.n_face + face_off;
+
+    float *ws = prm.workspace + (size_t)sys * prm.ws_floats;
+    float *__restrict__ a_val = ws;                               // [kMaxWa][n_max]  M(row, col), ELL in original order
+    RowsPlanes pl;
+    float *cur = a_val + (size_t)kMaxWa * n_max;
+    pl.lval = (float4 *)cur;  cur += 4 * (size_t)n_max;
+    pl.uval = (float4 *)cur;  cur += 4 * (size_t)n_max;
+    pl.lfar = (int2 *)cur;    cur += 2 * (size_t)n_max;
+    pl.ufar = (int2 *)cur;    cur += 2 * (size_t)n_max;
+    pl.udiag = cur;           cur += n_max;
+    float *__restrict__ b = cur;
+    float *__restrict__ x = b + n_max;
+    float *__restrict__ r = x + n_max;
+    float *__restrict__ rh = r + n_max;                           // rh, p, v, tt: contiguous, double as the ILU-only arv plane
+    float *__restrict__ p = rh + n_max;
+    float *__restrict__ v = p + n_max;
+    float *__restrict__ tt = v + n_max;
+    pl.arv = (float4 *)rh;
+    const int *__restrict__ t_col = T.r_col;
+    float *const zs = (float *)smem_raw + (size_t)kRowsRing * P * 11;      // behind the ring (11 floats per slot)
+
+    // ---- setup: ELL values, canonical rows, NaN guard (":245-256") -------------------------------------------
+    double nv = 0.0, nb = 0.0;
+#pragma unroll 8
+    for (int i = tid; i < nnz_c; i += NT) { const double a = values_c[i]; nv += a * a; }
+    for (int i = tid; i < n; i += NT) {
+        const float bi = rhs_g[i];
+        b[i] = bi; nb += (double)bi * bi;
+        x[i] = x0_g[i];                                               // cublasScopy(x_old -> x) (":261")
+        const int lx = i % dx;
+        float lv[4] = {0.f, 0.f, 0.f, 0.f}, rv[4] = {0.f, 0.f, 0.f, 0.f}, uv[4] = {0.f, 0.f, 0.f, 0.f};
+        int lf[2] = {-1, -1}, uf[2] = {-1, -1};
+        float dg = 1.0f;
+        for (int k = 0; k < wa; k++) {
+            const int src = T.r_src[k * n + i], rev = T.r_rev[k * n + i], col = t_col[k * n + i];
+            const float a = src >= 0 ? values_c[src] : 0.0f;
+            a_val[k * n_max + i] = a;
+            if (src < 0) continue;
+            if (col == i) { dg = a; continue; }
+            const float ar = rev >= 0 ? values_c[rev] : 0.0f;
+            int slot;
+            if (col < i) slot = (col == i - 1 && lx > 0) ? 3 : (col == i - dx ? 1 : (col < i - dx ? 0 : 2));
+            else slot = (col == i + 1 && lx < dx - 1) ? 0 : (col == i + dx ? 2 : (col < i + dx ? 1 : 3));
+#pragma unroll
+            for (int m = 0; m < 4; m++) {
+                if (slot == m) {
+                    if (col < i) { lv[m] = a; rv[m] = ar; } else uv[m] = a;
+                }
+            }
+            if (col < i && slot == 0) lf[0] = col;
+            if (col < i && slot == 2) lf[1] = col;
+            if (col > i && slot == 1) uf[0] = col;
+            if (col > i && slot == 3) uf[1] = col;
+        }
+        pl.lval[i] = make_float4(lv[0], lv[1], lv[2], lv[3]);
+        pl.arv[i] = make_float4(rv[0], rv[1], rv[2], rv[3]);
+        pl.uval[i] = make_float4(uv[0], uv[1], uv[2], uv[3]);
+        pl.lfar[i] = make_int2(lf[0], lf[1]);
+        pl.ufar[i] = make_int2(uf[0], uf[1]);
+        pl.udiag[i] = dg;
+    }
+    block_sum2(nv, nb, red);
+    int warn = (isnan((float)sqrt(nv)) || isnan((float)sqrt(nb))) ? 1 : 0;
+    DPISO_TICK(0);
+
+    // ---- ILU(0) (csrilu02, ":181-218") ---------------------------------------------------------------------
+    sweep_rows<0>(pl, nullptr, dx, dy, P);
+    DPISO_TICK(1);
+
+    auto precondition = [&](const float *src) {                      // zs = U^-1 L^-1 src   (csrsv2 x2, ":321-327")
+        sweep_rows<1>(pl, src, dx, dy, P);
+        sweep_rows<2>(pl, nullptr, dx, dy, P);
+    };
+    auto spmv_row = [&](const float *vec, int q) {                   // CsrmvEx row: fma in ascending column order
+        float av[kMaxWa];
+        int ac[kMaxWa];
+#pragma unroll
+        for (int k = 0; k < kMaxWa; k++) {                           // all loads first (memory-level parallelism)
+            av[k] = k < wa ? a_val[k * n_max + q] : 0.0f;
+            ac[k] = k < wa ? t_col[k * n + q] : q;
+        }
+        float acc = 0.0f;
+#pragma unroll
+        for (int k = 0; k < kMaxWa; k++)
+            if (k < wa) acc = fmaf(av[k], vec[ac[k]], acc);
+        return acc;
+    };
+
+    float alpha = 1.f, rho = 1.f, rhop = 1.f, omega = 1.f, beta, nrm_r = 0.f;
+    int it_count = 0, restarts = 0, exit_kind = 3;
+    const float tol = prm.tol;
+
+    for (int restart = 0; restart < 2; restart++) {
+        restarts = restart;
+        __syncthreads();
+        for (int q = tid; q < n; q += NT) zs[q] = x[q];               // r = b - A x  (":275-282")
+        __syncthreads();
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll 4
+        for (int q = tid; q < n; q += NT) {
+            const float rq = __fsub_rn(b[q], spmv_row(zs, q));
+            r[q] = rq; s0 += (double)rq * rq;
+        }
+        block_sum2(s0, s1, red);
+        nrm_r = (float)sqrt(s0);
+        if (nrm_r < tol) { exit_kind = 0; break; }                   // lucky guess (":287-289")
+        for (int q = tid; q < n; q += NT) { rh[q] = r[q]; p[q] = 0.0f; v[q] = 0.0f; }
+        exit_kind = 3;
+        float rho_next = (float)s0;                                  // r.rh with rh = r
+        for (int it = 0; it < prm.max_it; it++) {
+            it_count++;
+            rhop = rho;
+            rho = rho_next;
+            beta = __fmul_rn(__fdiv_rn(rho, rhop), __fdiv_rn(alpha, omega));
+            __syncthreads();
+#pragma unroll 4
+            for (int q = tid; q < n; q += NT) {                      // p = r + beta (p - omega v)  (":315-317")
+                float pq = fmaf(-omega, v[q], p[q]);
+                pq = __fmul_rn(beta, pq);
+                p[q] = __fadd_rn(pq, r[q]);
+            }
+            DPISO_TICK(4);
+            precondition(p);                                         // zs = p_hat
+            DPISO_TICK(2);
+            s0 = 0.0; s1 = 0.0;
+#pragma unroll 4
+            for (int q = tid; q < n; q += NT) {                      // v = A p_hat ; rh.v
+                const float vq = spmv_row(zs, q);
+                v[q] = vq; s0 += (double)rh[q] * vq;
+            }
+            block_sum2(s0, s1, red);
+            alpha = __fdiv_rn(rho, (float)s0);
+            s0 = 0.0; s1 = 0.0;
+#pragma unroll 4
+            for (int q = tid; q < n; q += NT) {                      // x += alpha p_hat ; r -= alpha v ; |r|
+                x[q] = fmaf(alpha, zs[q], x[q]);
+                const float rq = fmaf(-alpha, v[q], r[q]);
+                r[q] = rq; s0 += (double)rq * rq;
+            }
+            block_sum2(s0, s1, red);
+            nrm_r = (float)sqrt(s0);
+            if (nrm_r < tol) { exit_kind = 1; break; }
+            DPISO_TICK(4);
+            precondition(r);                                         // zs = s_hat
+            DPISO_TICK(2);
+            s0 = 0.0; s1 = 0.0;
+#pragma unroll 4
+            for (int q = tid; q < n; q += NT) {                      // t = A s_hat ; t.r ; t.t
+                const float tq = spmv_row(zs, q);
+                tt[q] = tq; s0 += (double)tq * r[q]; s1 += (double)tq * tq;
+            }
+            block_sum2(s0, s1, red);
+            omega = __fdiv_rn((float)s0, (float)s1);
+            s0 = 0.0; s1 = 0.0;
+#pragma unroll 4
+            for (int q = tid; q < n; q += NT) {                      // x += omega s_hat ; r -= omega t ; |r| ; r.rh
+                x[q] = fmaf(omega, zs[q], x[q]);
+                const float rq = fmaf(-omega, tt[q], r[q]);
+                r[q] = rq; s0 += (double)rq * rq; s1 += (double)rq * rh[q];
+            }
+            block_sum2(s0, s1, red);
+            nrm_r = (float)sqrt(s0);
+            rho_next = (float)s1;
+            if (nrm_r < tol) { exit_kind = 2; break; }
+        }
+        if (nrm_r > __fmul_rn(tol, 100.0f) || isnan(nrm_r)) {        // ":392-404"
+            __syncthreads();
+            for (int q = tid; q < n; q += NT) x[q] = 0.0f;
+            if (restart == 1) restarts = 2;
+        } else break;
+    }
+    __syncthreads();
+    DPISO_TICK(4);
+    for (int q = tid; q < n; q += NT) x_g[q] = x[q];
+    if (tid == 0) {
+        int *st = prm.stats + (size_t)sys * 4;
+        st[0] = it_count; st[1] = restarts; st[2] = warn; st[3] = exit_kind;
+        if (warn) *prm.warn = 1;
+    }
+}
+
 }  // namespace dpiso
 
 using namespace dpiso;
@@ -618,7 +935,9 @@ static long long *g_bicg_timing = nullptr;
 
 static void to_tab(const dpiso_bicg_tables *h, BicgTab &t) {
     t.n = h->n; t.n_levels = h->n_levels; t.wa = h->wa; t.max_level = h->max_level; t.wl = h->wl; t.wu = h->wu;
+    t.dx = h->dx; t.rows_ok = h->rows_ok;
     t.level_ptr = h->level_ptr; t.perm = h->perm; t.a_col = h->a_col; t.a_src = h->a_src; t.a_rev = h->a_rev;
+    t.r_col = h->r_col; t.r_src = h->r_src; t.r_rev = h->r_rev;
 }
 
 extern "C" {
@@ -686,6 +1005,28 @@ int dpiso_bicgstab_ilu(int batch, const dpiso_bicg_tables *h_tab_u, const dpiso_
         const size_t P = (size_t)((max_level + 31) & ~31);
         prm.ring_depth = region_ints >= 16 * P * 9 ? 16 : (region_ints >= 8 * P * 9 ? 8 : 2);
         if (region_ints < 2 * P * 9) prm.compact = 0;
+    }
+    // row-major kernel: every row in canonical slots, one sweep thread per grid row, ring + solve vector in shared memory
+    prm.rows_kernel = 0;
+    if (h_tab_u->rows_ok && h_tab_v->rows_ok && h_tab_u->r_col && h_tab_v->r_col && h_tab_u->dx > 0 && h_tab_v->dx > 0 &&
+        !(prm.dbg & 8)) {
+        const int dy_u = h_tab_u->n / h_tab_u->dx, dy_v = h_tab_v->n / h_tab_v->dx;
+        const int Pr = ((dy_u > dy_v ? dy_u : dy_v) + 31) & ~31;
+        const size_t need = (size_t)kRowsRing * Pr * 11 * sizeof(float) + (size_t)prm.n_max * sizeof(float);
+        if (Pr <= kBicgThreads && need <= kBudget) {
+            prm.rows_kernel = 1;
+            prm.rows_threads = Pr;
+            static unsigned long long rows_attr_mask = 0;
+            int dev = 0;
+            DPISO_CUDA_TRY(cudaGetDevice(&dev));
+            if (dev >= 64 || !(rows_attr_mask & (1ull << dev))) {
+                DPISO_CUDA_TRY(cudaFuncSetAttribute(bicgstab_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 1024));
+                if (dev < 64) rows_attr_mask |= 1ull << dev;
+            }
+            bicgstab_rows_kernel<<<batch * 2, kBicgThreads, need, (cudaStream_t)stream>>>(prm);
+            DPISO_CHECK_LAUNCH();
+            return DPISO_OK;
+        }
     }
     {   // the attribute is per device: remember which devices of this process have it
         static unsigned long long attr_set_mask = 0;

@@ -140,9 +140,22 @@ def bicg_tables(ny, nx, per_x, per_y, comp, transpose):
     orig_row = perm[None, :].repeat(wa, 0)
     assert np.all((a_col < q[None, :])[real & (colp < orig_row)])
     assert np.all((a_col > q[None, :])[real & (colp > orig_row)])
+    # Row-major variant of the solver (bicgstab_rows_kernel): every row keeps its entries in canonical slots by kind --
+    # lower: [far below the y-neighbour, y-neighbour (x, y-1), far above it, x-neighbour (x-1, y)], upper mirrored -- which
+    # preserves the ascending-column order only if each far slot is used at most once per row.
+    regular = ((ci == row_of - 1) & (lx[row_of] > 0)) | ((ci == row_of + 1) & (lx[row_of] < Dx - 1)) | \
+              (ci == row_of - Dx) | (ci == row_of + Dx) | (ci == row_of)
+    far = ~regular
+    slot_kind = np.where(ci < row_of,
+                         np.where(far, np.where(ci < row_of - Dx, 0, 2), np.where(ci == row_of - Dx, 1, 3)),
+                         np.where(far, np.where(ci > row_of + Dx, 7, 5), np.where(ci == row_of + Dx, 6, 4)))
+    offdiag = ci != row_of
+    rows_ok = int(np.unique(row_of[offdiag] * 8 + slot_kind[offdiag]).size == int(offdiag.sum()))
     wl = int(np.bincount(row_of[lower], minlength=n).max()) if lower.any() else 0
     wu = int(np.bincount(row_of[upper], minlength=n).max()) if upper.any() else 0
-    return dict(n=n, n_levels=int(counts.size), wa=wa, max_level=int(counts.max()), wl=wl, wu=wu,
+    return dict(n=n, n_levels=int(counts.size), wa=wa, max_level=int(counts.max()), wl=wl, wu=wu, dx=int(Dx), rows_ok=rows_ok,
+                r_col=np.ascontiguousarray(np.where(col_e >= 0, col_e, rows_all[None, :]), np.int32),
+                r_src=np.ascontiguousarray(src_e, np.int32), r_rev=np.ascontiguousarray(rev_e, np.int32),
                 level_ptr=level_ptr.astype(np.int32), perm=perm.astype(np.int32),
                 a_col=np.ascontiguousarray(a_col, np.int32), a_src=np.ascontiguousarray(a_src, np.int32),
                 a_rev=np.ascontiguousarray(a_rev, np.int32), nnz=int(a.nnz))

@@ -121,12 +121,17 @@ typedef struct {
     int wa;               /* ELL width: max entries per row of the (possibly transposed) matrix, <= 6 */
     int max_level;        /* rows in the largest level */
     int wl, wu;           /* max number of lower / upper entries in a row */
+    int dx;               /* faces per grid row of this component (original row index = ly * dx + lx) */
+    int rows_ok;          /* 1: every row fits the canonical slot layout of the row-major solver kernel */
     const int *level_ptr; /* [n_levels+1] first position of each level (level-major numbering) */
     const int *perm;      /* [n] level-major position -> original row */
     const int *a_col;     /* [wa][n] column (as level-major position) per entry, in ascending ORIGINAL column
                              order; padding entries come last and point at the row itself */
     const int *a_src;     /* [wa][n] index into this component's CSR values holding M(row, col); -1 = padding */
     const int *a_rev;     /* [wa][n] index into this component's CSR values holding M(col, row); -1 = absent */
+    const int *r_col;     /* [wa][n] the same three tables in ORIGINAL row order with original column indices (padding */
+    const int *r_src;     /*         entries point at the row itself / -1): used by the row-major solver kernel, which  */
+    const int *r_rev;     /*         needs no permutation; may be NULL (then rows_ok must be 0)                          */
 } dpiso_bicg_tables;
 
 /* gd = M^T gh - (A - beta) gh: adjoint of dpiso_h_apply w.r.t. (u** - u*); takes the tables of M = A^T */
