@@ -44,6 +44,8 @@ struct BicgParams {
     int rows_kernel;       // 1: bicgstab_rows_kernel (row-major layout, one thread per grid row in the sweeps)
     int rows_threads;      // its sweep threads P = roundup32(max dy)
     int dbg;               // profiling experiments only (DPISO_BICG_DBG): 1 skip level barrier, 2 skip refill, 4 skip recurrence
+                           // (level-major kernel); 8 force the level-major kernel; 16 row-major sweeps with progress flags
+                           // instead of the per-level barrier (slower: 1.39 M vs 1.22 M cycles)
     const float *values, *rhs, *x0;
     float *x;
     int *stats;
@@ -642,9 +644,10 @@ struct RowsPlanes {
 };
 
 // MODE 0: ILU(0) (zs = pivots), 1: L solve (ext = right-hand side), 2: U solve
-template <int MODE>
+template <int MODE, bool kBarrier>
 __device__ __noinline__ void sweep_rows(const RowsPlanes pl, const float *ext, int dx, int dy, int P) {
     constexpr int D = kRowsRing;
+    __shared__ int s_prog[kBicgThreads / 32];
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *const r16a = (float4 *)smem_raw;                           // [D][P] values
     float4 *const r16b = r16a + D * P;                                 // [D][P] ILU: reverse values
@@ -653,8 +656,12 @@ __device__ __noinline__ void sweep_rows(const RowsPlanes pl, const float *ext, i
     float *const zs = r4 + D * P;                                      // [n] solve vector / pivots
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int nl = dx + dy - 1;
+    if (!kBarrier && t < kBicgThreads / 32) s_prog[t] = -1;
     __syncthreads();
     if (t < P) {
+        volatile int *const prog = s_prog;
+        volatile float *const zv = zs;
+        const int lead = MODE == 2 ? warp + 1 : warp - 1;             // the warp this one depends on (it runs ahead)
         const bool rowok = t < dy;
         const int i0 = t * dx;
         const float4 *gval = MODE == 2 ? pl.uval : pl.lval;
@@ -693,7 +700,10 @@ __device__ __noinline__ void sweep_rows(const RowsPlanes pl, const float *ext, i
                     const float4 v = r16a[k];
                     const int2 fc = r8[k];
                     const float e = r4[k];
-                    if (edge) nb = zs[i + nb_off];
+                    if (edge) {
+                        if (!kBarrier) { while (prog[lead] < s - 1) {} }   // the leading warp has stored step s - 1
+                        nb = zv[i + nb_off];
+                    }
                     if (MODE == 0) {
                         // l_ik = a_ik / u_kk, u_ii = a_ii - sum l_ik u_ki, lower entries in ascending column order
                         const float4 rv = r16b[k];
@@ -720,10 +730,11 @@ __device__ __noinline__ void sweep_rows(const RowsPlanes pl, const float *ext, i
                         acc = fmaf(-v.w, f1, acc);
                         res = __fdiv_rn(acc, e);
                     }
-                    zs[i] = res;
+                    zv[i] = res;
                 }
                 prev = res;
-                named_bar(1, P);
+                if (kBarrier) named_bar(1, P);
+                else if (lane == (MODE == 2 ? 0 : 31)) prog[warp] = s;   // result, then progress: same thread, in order
             }
         }
         cp_async_wait<0>();
@@ -812,12 +823,12 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_rows_kernel(const Bi
     DPISO_TICK(0);
 
     // ---- ILU(0) (csrilu02, ":181-218") ---------------------------------------------------------------------
-    sweep_rows<0>(pl, nullptr, dx, dy, P);
+    if (prm.dbg & 16) sweep_rows<0, false>(pl, nullptr, dx, dy, P); else sweep_rows<0, true>(pl, nullptr, dx, dy, P);
     DPISO_TICK(1);
 
     auto precondition = [&](const float *src) {                      // zs = U^-1 L^-1 src   (csrsv2 x2, ":321-327")
-        sweep_rows<1>(pl, src, dx, dy, P);
-        sweep_rows<2>(pl, nullptr, dx, dy, P);
+        if (prm.dbg & 16) { sweep_rows<1, false>(pl, src, dx, dy, P); sweep_rows<2, false>(pl, nullptr, dx, dy, P); }
+        else { sweep_rows<1, true>(pl, src, dx, dy, P); sweep_rows<2, true>(pl, nullptr, dx, dy, P); }
     };
     auto spmv_row = [&](const float *vec, int q) {                   // CsrmvEx row: fma in ascending column order
         float av[kMaxWa];
