@@ -151,6 +151,9 @@ def bicg_tables(ny, nx, per_x, per_y, comp, transpose):
                          np.where(far, np.where(ci > row_of + Dx, 7, 5), np.where(ci == row_of + Dx, 6, 4)))
     offdiag = ci != row_of
     rows_ok = int(np.unique(row_of[offdiag] * 8 + slot_kind[offdiag]).size == int(offdiag.sum()))
+    # the sweeps read far operands one level ahead of their use: they must be at least two levels old
+    if far.any() and int(np.abs(level[ci[far]] - level[row_of[far]]).min()) < 2:
+        rows_ok = 0
     wl = int(np.bincount(row_of[lower], minlength=n).max()) if lower.any() else 0
     wu = int(np.bincount(row_of[upper], minlength=n).max()) if upper.any() else 0
     return dict(n=n, n_levels=int(counts.size), wa=wa, max_level=int(counts.max()), wl=wl, wu=wu, dx=int(Dx), rows_ok=rows_ok,

@@ -22,13 +22,14 @@ def main():
     rhs = vel * beta
     neg = torch.neg(values)
     out = {}
+    max_it = int(os.environ.get('BICG_MAXIT', '10000'))
     for tr in (False, True):
         cnt = torch.zeros(8, dtype=torch.int64, device=dev)
-        x, st, w = ops.bicgstab_ilu(g, neg, rhs, vel, 1e-8, 10000, tr)
+        x, st, w = ops.bicgstab_ilu(g, neg, rhs, vel, 1e-8, max_it, tr)
         torch.cuda.synchronize()
         N.lib.dpiso_bicgstab_set_timing(cnt.data_ptr())
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); x, st, w = ops.bicgstab_ilu(g, neg, rhs, vel, 1e-8, 10000, tr); e1.record()
+        e0.record(); x, st, w = ops.bicgstab_ilu(g, neg, rhs, vel, 1e-8, max_it, tr); e1.record()
         torch.cuda.synchronize()
         N.lib.dpiso_bicgstab_set_timing(None)
         c = cnt.cpu().numpy()
