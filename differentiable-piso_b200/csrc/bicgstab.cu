@@ -27,6 +27,9 @@ constexpr int kMaxWa = 6;
 struct BicgTab {
     int n, n_levels, wa, max_level, wl, wu, dx, rows_ok;
     const int *level_ptr, *perm, *a_col, *a_src, *a_rev, *r_col, *r_src, *r_rev;
+    const int4 *c_lsrc, *c_lrev, *c_usrc;
+    const int2 *c_lfar, *c_ufar;
+    const int *c_dsrc;
 };
 
 struct BicgParams {
@@ -637,9 +640,9 @@ constexpr int kRowsRing = 8;
 struct RowsPlanes {
     float4 *lval;      // [n] ILU: A lower values in, l_ik out
     float4 *arv;       // [n] ILU only: reverse entries u_ki = A(k, i) of the lower slots (aliases rh, p, v, tt)
-    int2 *lfar;        // [n] columns of the two far lower slots, -1 = absent
+    const int2 *lfar;  // [n] columns of the two far lower slots, -1 = absent (static table, shared by all systems)
     float4 *uval;      // [n] upper values (unchanged by ILU(0) on this pattern)
-    int2 *ufar;        // [n]
+    const int2 *ufar;  // [n]
     float *udiag;      // [n] A diagonal in, pivot out
 };
 
@@ -764,8 +767,8 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_rows_kernel(const Bi
     float *cur = a_val + (size_t)kMaxWa * n_max;
     pl.lval = (float4 *)cur;  cur += 4 * (size_t)n_max;
     pl.uval = (float4 *)cur;  cur += 4 * (size_t)n_max;
-    pl.lfar = (int2 *)cur;    cur += 2 * (size_t)n_max;
-    pl.ufar = (int2 *)cur;    cur += 2 * (size_t)n_max;
+    pl.lfar = T.c_lfar;
+    pl.ufar = T.c_ufar;
     pl.udiag = cur;           cur += n_max;
     float *__restrict__ b = cur;
     float *__restrict__ x = b + n_max;
@@ -786,37 +789,20 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_rows_kernel(const Bi
         const float bi = rhs_g[i];
         b[i] = bi; nb += (double)bi * bi;
         x[i] = x0_g[i];                                               // cublasScopy(x_old -> x) (":261")
-        const int lx = i % dx;
-        float lv[4] = {0.f, 0.f, 0.f, 0.f}, rv[4] = {0.f, 0.f, 0.f, 0.f}, uv[4] = {0.f, 0.f, 0.f, 0.f};
-        int lf[2] = {-1, -1}, uf[2] = {-1, -1};
-        float dg = 1.0f;
         for (int k = 0; k < wa; k++) {
-            const int src = T.r_src[k * n + i], rev = T.r_rev[k * n + i], col = t_col[k * n + i];
-            const float a = src >= 0 ? values_c[src] : 0.0f;
-            a_val[k * n_max + i] = a;
-            if (src < 0) continue;
-            if (col == i) { dg = a; continue; }
-            const float ar = rev >= 0 ? values_c[rev] : 0.0f;
-            int slot;
-            if (col < i) slot = (col == i - 1 && lx > 0) ? 3 : (col == i - dx ? 1 : (col < i - dx ? 0 : 2));
-            else slot = (col == i + 1 && lx < dx - 1) ? 0 : (col == i + dx ? 2 : (col < i + dx ? 1 : 3));
-#pragma unroll
-            for (int m = 0; m < 4; m++) {
-                if (slot == m) {
-                    if (col < i) { lv[m] = a; rv[m] = ar; } else uv[m] = a;
-                }
-            }
-            if (col < i && slot == 0) lf[0] = col;
-            if (col < i && slot == 2) lf[1] = col;
-            if (col > i && slot == 1) uf[0] = col;
-            if (col > i && slot == 3) uf[1] = col;
+            const int src = T.r_src[k * n + i];
+            a_val[k * n_max + i] = src >= 0 ? values_c[src] : 0.0f;
         }
-        pl.lval[i] = make_float4(lv[0], lv[1], lv[2], lv[3]);
-        pl.arv[i] = make_float4(rv[0], rv[1], rv[2], rv[3]);
-        pl.uval[i] = make_float4(uv[0], uv[1], uv[2], uv[3]);
-        pl.lfar[i] = make_int2(lf[0], lf[1]);
-        pl.ufar[i] = make_int2(uf[0], uf[1]);
-        pl.udiag[i] = dg;
+        // canonical rows straight from the host's slot tables
+        auto val4 = [&](const int4 s4) {
+            return make_float4(s4.x >= 0 ? values_c[s4.x] : 0.0f, s4.y >= 0 ? values_c[s4.y] : 0.0f,
+                               s4.z >= 0 ? values_c[s4.z] : 0.0f, s4.w >= 0 ? values_c[s4.w] : 0.0f);
+        };
+        pl.lval[i] = val4(T.c_lsrc[i]);
+        pl.arv[i] = val4(T.c_lrev[i]);
+        pl.uval[i] = val4(T.c_usrc[i]);
+        const int ds = T.c_dsrc[i];
+        pl.udiag[i] = ds >= 0 ? values_c[ds] : 1.0f;
     }
     block_sum2(nv, nb, red);
     int warn = (isnan((float)sqrt(nv)) || isnan((float)sqrt(nb))) ? 1 : 0;
@@ -949,6 +935,8 @@ static void to_tab(const dpiso_bicg_tables *h, BicgTab &t) {
     t.dx = h->dx; t.rows_ok = h->rows_ok;
     t.level_ptr = h->level_ptr; t.perm = h->perm; t.a_col = h->a_col; t.a_src = h->a_src; t.a_rev = h->a_rev;
     t.r_col = h->r_col; t.r_src = h->r_src; t.r_rev = h->r_rev;
+    t.c_lsrc = (const int4 *)h->c_lsrc; t.c_lrev = (const int4 *)h->c_lrev; t.c_usrc = (const int4 *)h->c_usrc;
+    t.c_lfar = (const int2 *)h->c_lfar; t.c_ufar = (const int2 *)h->c_ufar; t.c_dsrc = h->c_dsrc;
 }
 
 extern "C" {
@@ -1019,7 +1007,8 @@ int dpiso_bicgstab_ilu(int batch, const dpiso_bicg_tables *h_tab_u, const dpiso_
     }
     // row-major kernel: every row in canonical slots, one sweep thread per grid row, ring + solve vector in shared memory
     prm.rows_kernel = 0;
-    if (h_tab_u->rows_ok && h_tab_v->rows_ok && h_tab_u->r_col && h_tab_v->r_col && h_tab_u->dx > 0 && h_tab_v->dx > 0 &&
+    if (h_tab_u->rows_ok && h_tab_v->rows_ok && h_tab_u->r_col && h_tab_v->r_col && h_tab_u->c_lsrc && h_tab_v->c_lsrc &&
+        h_tab_u->dx > 0 && h_tab_v->dx > 0 &&
         !(prm.dbg & 8)) {
         const int dy_u = h_tab_u->n / h_tab_u->dx, dy_v = h_tab_v->n / h_tab_v->dx;
         const int Pr = ((dy_u > dy_v ? dy_u : dy_v) + 31) & ~31;

@@ -34,7 +34,9 @@ class BicgTables(C.Structure):
     _fields_ = [("n", C.c_int), ("n_levels", C.c_int), ("wa", C.c_int), ("max_level", C.c_int),
                 ("wl", C.c_int), ("wu", C.c_int), ("dx", C.c_int), ("rows_ok", C.c_int), ("level_ptr", C.c_void_p),
                 ("perm", C.c_void_p), ("a_col", C.c_void_p), ("a_src", C.c_void_p), ("a_rev", C.c_void_p),
-                ("r_col", C.c_void_p), ("r_src", C.c_void_p), ("r_rev", C.c_void_p)]
+                ("r_col", C.c_void_p), ("r_src", C.c_void_p), ("r_rev", C.c_void_p), ("c_lsrc", C.c_void_p),
+                ("c_lrev", C.c_void_p), ("c_usrc", C.c_void_p), ("c_lfar", C.c_void_p), ("c_ufar", C.c_void_p),
+                ("c_dsrc", C.c_void_p)]
 
 
 _I, _F, _P, _SZ = C.c_int, C.c_float, C.c_void_p, C.c_size_t

@@ -41,12 +41,15 @@ class Geometry(object):
             for comp in (0, 1):
                 h = S.bicg_tables(self.ny, self.nx, self.per_x, self.per_y, comp, bool(transpose))
                 dev = {k: torch.from_numpy(h[k]).to(self.device)
-                       for k in ("level_ptr", "perm", "a_col", "a_src", "a_rev", "r_col", "r_src", "r_rev")}
+                       for k in ("level_ptr", "perm", "a_col", "a_src", "a_rev", "r_col", "r_src", "r_rev", "c_lsrc", "c_lrev",
+                                 "c_usrc", "c_lfar", "c_ufar", "c_dsrc")}
                 st = N.BicgTables(h["n"], h["n_levels"], h["wa"], h["max_level"], h["wl"], h["wu"], h["dx"], h["rows_ok"],
                                   dev["level_ptr"].data_ptr(),
                                   dev["perm"].data_ptr(), dev["a_col"].data_ptr(), dev["a_src"].data_ptr(),
                                   dev["a_rev"].data_ptr(), dev["r_col"].data_ptr(), dev["r_src"].data_ptr(),
-                                  dev["r_rev"].data_ptr())
+                                  dev["r_rev"].data_ptr(), dev["c_lsrc"].data_ptr(), dev["c_lrev"].data_ptr(),
+                                  dev["c_usrc"].data_ptr(), dev["c_lfar"].data_ptr(), dev["c_ufar"].data_ptr(),
+                                  dev["c_dsrc"].data_ptr())
                 structs.append(st)
                 keep.append(dev)
             t = self._tables[bool(transpose)] = (structs[0], structs[1], keep)

@@ -154,11 +154,27 @@ def bicg_tables(ny, nx, per_x, per_y, comp, transpose):
     # the sweeps read far operands one level ahead of their use: they must be at least two levels old
     if far.any() and int(np.abs(level[ci[far]] - level[row_of[far]]).min()) < 2:
         rows_ok = 0
+    # canonical source tables of the row-major kernel: CSR value index of every slot (-1 = absent), reverse entries of the
+    # lower slots, the pivot's index, and the columns of the far slots
+    c_lsrc = np.full((n, 4), -1, np.int32); c_lrev = np.full((n, 4), -1, np.int32); c_usrc = np.full((n, 4), -1, np.int32)
+    c_lfar = np.full((n, 2), -1, np.int32); c_ufar = np.full((n, 2), -1, np.int32); c_dsrc = np.full(n, -1, np.int32)
+    if rows_ok:
+        lo_e, up_e = offdiag & (ci < row_of), offdiag & (ci > row_of)
+        c_lsrc[row_of[lo_e], slot_kind[lo_e]] = src[lo_e]
+        c_lrev[row_of[lo_e], slot_kind[lo_e]] = rev[lo_e]
+        c_usrc[row_of[up_e], slot_kind[up_e] - 4] = src[up_e]
+        fl = lo_e & far
+        c_lfar[row_of[fl], slot_kind[fl] // 2] = ci[fl]
+        fu = up_e & far
+        c_ufar[row_of[fu], (slot_kind[fu] - 4) // 2] = ci[fu]
+        dg_e = ci == row_of
+        c_dsrc[row_of[dg_e]] = src[dg_e]
     wl = int(np.bincount(row_of[lower], minlength=n).max()) if lower.any() else 0
     wu = int(np.bincount(row_of[upper], minlength=n).max()) if upper.any() else 0
     return dict(n=n, n_levels=int(counts.size), wa=wa, max_level=int(counts.max()), wl=wl, wu=wu, dx=int(Dx), rows_ok=rows_ok,
                 r_col=np.ascontiguousarray(np.where(col_e >= 0, col_e, rows_all[None, :]), np.int32),
                 r_src=np.ascontiguousarray(src_e, np.int32), r_rev=np.ascontiguousarray(rev_e, np.int32),
+                c_lsrc=c_lsrc, c_lrev=c_lrev, c_usrc=c_usrc, c_lfar=c_lfar, c_ufar=c_ufar, c_dsrc=c_dsrc,
                 level_ptr=level_ptr.astype(np.int32), perm=perm.astype(np.int32),
                 a_col=np.ascontiguousarray(a_col, np.int32), a_src=np.ascontiguousarray(a_src, np.int32),
                 a_rev=np.ascontiguousarray(a_rev, np.int32), nnz=int(a.nnz))

@@ -132,6 +132,14 @@ typedef struct {
     const int *r_col;     /* [wa][n] the same three tables in ORIGINAL row order with original column indices (padding */
     const int *r_src;     /*         entries point at the row itself / -1): used by the row-major solver kernel, which  */
     const int *r_rev;     /*         needs no permutation; may be NULL (then rows_ok must be 0)                          */
+    /* canonical slots of the row-major kernel (lower: [far below the y-neighbour, y-neighbour, far above it, x-neighbour],
+     * upper: [x-neighbour, far below the y-neighbour, y-neighbour, far above it]); all [n] in original row order */
+    const int *c_lsrc;    /* int[n][4] CSR value index of the lower slots, -1 = absent */
+    const int *c_lrev;    /* int[n][4] CSR value index of their reverse entries M(col, row) */
+    const int *c_usrc;    /* int[n][4] CSR value index of the upper slots */
+    const int *c_lfar;    /* int[n][2] column of the two far lower slots, -1 = absent */
+    const int *c_ufar;    /* int[n][2] column of the two far upper slots */
+    const int *c_dsrc;    /* int[n]    CSR value index of the diagonal entry */
 } dpiso_bicg_tables;
 
 /* gd = M^T gh - (A - beta) gh: adjoint of dpiso_h_apply w.r.t. (u** - u*); takes the tables of M = A^T */
