@@ -59,11 +59,13 @@ def _linear_solve(c, values_neg, rhs, x0, transpose, unrolling_step):
     return ls.solve(values_neg, rp, ci, rhs, shape, x0, offset=1, transpose=transpose, unrolling_step=unrolling_step)
 
 
-def _pressure_solve(c, a_diag, div, unrolling_step):
+def _pressure_solve(c, a_diag, div, unrolling_step, scaling=None):
     ps = c.sim.pressure_solver
     b = div.shape[0]
     div4 = div.reshape(b, c.g.ny, c.g.nx, 1)
-    if getattr(ps, "_dpiso_native", False):
+    if scaling is not None:
+        pass
+    elif getattr(ps, "_dpiso_native", False):
         scaling = ScalingFromDiagonal(a_diag, c.beta, c.dx_factor)
     else:   # foreign plug-in: materialise 1/(beta - A) * dx_factor as a staggered tensor (piso_tf.py:53-54)
         scaling = stagger_flattened_data((1.0 / (c.beta - a_diag)) * c.dx_factor, (b, c.g.ny + 1, c.g.nx + 1, 2), True)
@@ -88,12 +90,14 @@ class _PisoStepFn(torch.autograd.Function):
         u_star = u_star.contiguous()
         # corrector 1 (piso_tf.py:51-58)
         div1 = ops.fv_divergence(g, u_star, c.dy, c.dx)
-        p1, its1, lap1 = _pressure_solve(c, a_diag, div1, c.unrolling_step)
+        native_ps = getattr(c.sim.pressure_solver, "_dpiso_native", False)
+        scaling = ScalingFromDiagonal(a_diag, c.beta, c.dx_factor) if native_ps else None   # both solves share the matrix
+        p1, its1, lap1 = _pressure_solve(c, a_diag, div1, c.unrolling_step, scaling)
         u_s2 = ops.corrector1(g, u_star, p1, a_diag, m["access"], c.dy, c.dx, c.beta, c.pbc_inc)
         # corrector 2 (piso_tf.py:61-75)
         h = ops.h_apply(g, values, a_diag, u_star, u_s2, c.beta)
         div2 = ops.fv_divergence(g, h, c.dy, c.dx, a_diag=a_diag, beta=c.beta)
-        p2, its2, lap2 = _pressure_solve(c, a_diag, div2, 1000 + c.unrolling_step)
+        p2, its2, lap2 = _pressure_solve(c, a_diag, div2, 1000 + c.unrolling_step, scaling)
         vel_next, pres_next = ops.corrector2(g, u_s2, h, p2, a_diag, pres, p1, m["access"], c.dy, c.dx, c.beta, c.pbc_inc)
         ctx.c = c
         ctx.set_materialize_grads(False)        # no zero-filled gradients for the 15 non-differentiable extras
@@ -115,7 +119,9 @@ class _PisoStepFn(torch.autograd.Function):
         # p_next = p + p1 + p2 ; u_next = u** + (h - G(p2)/prod)/(beta-A)
         p2_bar = ops.fv_gradient_adj(g, g_vel, m["access"], c.dy, c.dx, c.pbc_inc, a_diag=a_diag, beta=c.beta,
                                      divisor=c.prod, negate=True, base=g_pres)
-        d2_bar, _, _ = _pressure_solve(c, a_diag, p2_bar, 1100 + c.unrolling_step)
+        native_ps = getattr(c.sim.pressure_solver, "_dpiso_native", False)
+        scaling = ScalingFromDiagonal(a_diag, c.beta, c.dx_factor) if native_ps else None
+        d2_bar, _, _ = _pressure_solve(c, a_diag, p2_bar, 1100 + c.unrolling_step, scaling)
         # h_bar = (g_vel + D^T d2_bar) / (beta - A)
         h_bar = ops.fv_divergence_adj(g, d2_bar, c.dy, c.dx, base=g_vel, a_diag=a_diag, beta=c.beta)
         delta_bar = ops.h_apply_adj(g, values, a_diag, h_bar, c.beta)
@@ -123,7 +129,7 @@ class _PisoStepFn(torch.autograd.Function):
         # u** = u* - G(p1)/(beta-A)/prod
         p1_bar = ops.fv_gradient_adj(g, us2_bar, m["access"], c.dy, c.dx, c.pbc_inc, a_diag=a_diag, beta=c.beta,
                                      divisor=c.prod, negate=True, base=g_pres)
-        d1_bar, _, _ = _pressure_solve(c, a_diag, p1_bar, 100 + c.unrolling_step)
+        d1_bar, _, _ = _pressure_solve(c, a_diag, p1_bar, 100 + c.unrolling_step, scaling)
         # u*_bar = (us2_bar - delta_bar) + D^T d1_bar
         ustar_bar = ops.fv_divergence_adj(g, d1_bar, c.dy, c.dx, base=us2_bar - delta_bar)
         # predictor: transposed solve, same initial-guess tensor as forward, times (1 - warn) (linear_solver.py:169-173)

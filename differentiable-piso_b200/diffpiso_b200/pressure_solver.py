@@ -34,6 +34,8 @@ class ScalingFromDiagonal(object):
 
     def __init__(self, a_diag_flat, beta, dx_factor):
         self.a_diag, self.beta, self.dx_factor = a_diag_flat, float(beta), float(dx_factor)
+        self._lap = {}      # pressure matrix built from this diagonal, per precision: the two solves of a pass share it
+                            # (the reference rebuilds the identical matrix for every solve)
 
 
 class _PressureSolveFn(torch.autograd.Function):
@@ -92,8 +94,11 @@ class PisoPressureSolverCudaCustom(PoissonSolver):
         if self.laplace_rank_deficient is None:                      # ":83-87" (cached on first use, like the reference)
             self.laplace_rank_deficient = masks["rank_deficient"]
         if isinstance(scaling_field, ScalingFromDiagonal):
-            lap = ops.laplace(geom, masks["active"], masks["access"], scaling_field.a_diag, 1, scaling_field.beta,
-                              scaling_field.dx_factor, fp64=self.cast_to_double)
+            lap = scaling_field._lap.get(self.cast_to_double)
+            if lap is None:
+                lap = ops.laplace(geom, masks["active"], masks["access"], scaling_field.a_diag, 1, scaling_field.beta,
+                                  scaling_field.dx_factor, fp64=self.cast_to_double)
+                scaling_field._lap[self.cast_to_double] = lap
         else:
             k = flatten_staggered_data(as_tensor(scaling_field), coord_flip=False).contiguous()   # ":70"
             if k.shape[0] == 1 and b > 1:
