@@ -834,6 +834,9 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_rows_kernel(const Bi
     float alpha = 1.f, rho = 1.f, rhop = 1.f, omega = 1.f, beta, nrm_r = 0.f;
     int it_count = 0, restarts = 0, exit_kind = 3;
     const float tol = prm.tol;
+    const int n4 = n & ~3;                                           // float4 part of the vector phases (planes are 16-byte aligned)
+    auto ld4 = [](const float *a) { return *reinterpret_cast<const float4 *>(a); };
+    auto st4 = [](float *a, const float4 val) { *reinterpret_cast<float4 *>(a) = val; };
 
     for (int restart = 0; restart < 2; restart++) {
         restarts = restart;
@@ -858,12 +861,17 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_rows_kernel(const Bi
             rho = rho_next;
             beta = __fmul_rn(__fdiv_rn(rho, rhop), __fdiv_rn(alpha, omega));
             __syncthreads();
-#pragma unroll 4
-            for (int q = tid; q < n; q += NT) {                      // p = r + beta (p - omega v)  (":315-317")
-                float pq = fmaf(-omega, v[q], p[q]);
-                pq = __fmul_rn(beta, pq);
-                p[q] = __fadd_rn(pq, r[q]);
+#pragma unroll 2
+            for (int q = tid * 4; q < n4; q += NT * 4) {             // p = r + beta (p - omega v)  (":315-317")
+                const float4 vv = ld4(v + q), rr = ld4(r + q);
+                float4 pp = ld4(p + q);
+                pp.x = __fadd_rn(__fmul_rn(beta, fmaf(-omega, vv.x, pp.x)), rr.x);
+                pp.y = __fadd_rn(__fmul_rn(beta, fmaf(-omega, vv.y, pp.y)), rr.y);
+                pp.z = __fadd_rn(__fmul_rn(beta, fmaf(-omega, vv.z, pp.z)), rr.z);
+                pp.w = __fadd_rn(__fmul_rn(beta, fmaf(-omega, vv.w, pp.w)), rr.w);
+                st4(p + q, pp);
             }
+            for (int q = n4 + tid; q < n; q += NT) p[q] = __fadd_rn(__fmul_rn(beta, fmaf(-omega, v[q], p[q])), r[q]);
             DPISO_TICK(4);
             precondition(p);                                         // zs = p_hat
             DPISO_TICK(2);
@@ -876,8 +884,16 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_rows_kernel(const Bi
             block_sum2(s0, s1, red);
             alpha = __fdiv_rn(rho, (float)s0);
             s0 = 0.0; s1 = 0.0;
-#pragma unroll 4
-            for (int q = tid; q < n; q += NT) {                      // x += alpha p_hat ; r -= alpha v ; |r|
+#pragma unroll 2
+            for (int q = tid * 4; q < n4; q += NT * 4) {             // x += alpha p_hat ; r -= alpha v ; |r|
+                const float4 zz = ld4(zs + q), vv = ld4(v + q);
+                float4 xx = ld4(x + q), rr = ld4(r + q);
+                xx.x = fmaf(alpha, zz.x, xx.x); xx.y = fmaf(alpha, zz.y, xx.y); xx.z = fmaf(alpha, zz.z, xx.z); xx.w = fmaf(alpha, zz.w, xx.w);
+                rr.x = fmaf(-alpha, vv.x, rr.x); rr.y = fmaf(-alpha, vv.y, rr.y); rr.z = fmaf(-alpha, vv.z, rr.z); rr.w = fmaf(-alpha, vv.w, rr.w);
+                st4(x + q, xx); st4(r + q, rr);
+                s0 += (double)rr.x * rr.x; s0 += (double)rr.y * rr.y; s0 += (double)rr.z * rr.z; s0 += (double)rr.w * rr.w;
+            }
+            for (int q = n4 + tid; q < n; q += NT) {
                 x[q] = fmaf(alpha, zs[q], x[q]);
                 const float rq = fmaf(-alpha, v[q], r[q]);
                 r[q] = rq; s0 += (double)rq * rq;
@@ -897,8 +913,17 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_rows_kernel(const Bi
             block_sum2(s0, s1, red);
             omega = __fdiv_rn((float)s0, (float)s1);
             s0 = 0.0; s1 = 0.0;
-#pragma unroll 4
-            for (int q = tid; q < n; q += NT) {                      // x += omega s_hat ; r -= omega t ; |r| ; r.rh
+#pragma unroll 2
+            for (int q = tid * 4; q < n4; q += NT * 4) {             // x += omega s_hat ; r -= omega t ; |r| ; r.rh
+                const float4 zz = ld4(zs + q), t4 = ld4(tt + q), hh = ld4(rh + q);
+                float4 xx = ld4(x + q), rr = ld4(r + q);
+                xx.x = fmaf(omega, zz.x, xx.x); xx.y = fmaf(omega, zz.y, xx.y); xx.z = fmaf(omega, zz.z, xx.z); xx.w = fmaf(omega, zz.w, xx.w);
+                rr.x = fmaf(-omega, t4.x, rr.x); rr.y = fmaf(-omega, t4.y, rr.y); rr.z = fmaf(-omega, t4.z, rr.z); rr.w = fmaf(-omega, t4.w, rr.w);
+                st4(x + q, xx); st4(r + q, rr);
+                s0 += (double)rr.x * rr.x; s0 += (double)rr.y * rr.y; s0 += (double)rr.z * rr.z; s0 += (double)rr.w * rr.w;
+                s1 += (double)rr.x * hh.x; s1 += (double)rr.y * hh.y; s1 += (double)rr.z * hh.z; s1 += (double)rr.w * hh.w;
+            }
+            for (int q = n4 + tid; q < n; q += NT) {
                 x[q] = fmaf(omega, zs[q], x[q]);
                 const float rq = fmaf(-omega, tt[q], r[q]);
                 r[q] = rq; s0 += (double)rq * rq; s1 += (double)rq * rh[q];
