@@ -831,6 +831,29 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_rows_kernel(const Bi
         return acc;
     };
 
+    // four consecutive rows at once: float4 / int4 loads of every ELL plane (n is a multiple of 4 here), same fma order
+    auto spmv_row4 = [&](const float *vec, int q) {
+        float4 av[kMaxWa];
+        int4 ac[kMaxWa];
+#pragma unroll
+        for (int k = 0; k < kMaxWa; k++) {
+            av[k] = k < wa ? *reinterpret_cast<const float4 *>(a_val + (size_t)k * n_max + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            ac[k] = k < wa ? *reinterpret_cast<const int4 *>(t_col + (size_t)k * n + q) : make_int4(q, q, q, q);
+        }
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < kMaxWa; k++) {
+            if (k < wa) {
+                acc.x = fmaf(av[k].x, vec[ac[k].x], acc.x);
+                acc.y = fmaf(av[k].y, vec[ac[k].y], acc.y);
+                acc.z = fmaf(av[k].z, vec[ac[k].z], acc.z);
+                acc.w = fmaf(av[k].w, vec[ac[k].w], acc.w);
+            }
+        }
+        return acc;
+    };
+    const bool vec4 = (n & 3) == 0;                                  // r_col planes have stride n: int4 loads need n % 4 == 0
+
     float alpha = 1.f, rho = 1.f, rhop = 1.f, omega = 1.f, beta, nrm_r = 0.f;
     int it_count = 0, restarts = 0, exit_kind = 3;
     const float tol = prm.tol;
@@ -844,10 +867,20 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_rows_kernel(const Bi
         for (int q = tid; q < n; q += NT) zs[q] = x[q];               // r = b - A x  (":275-282")
         __syncthreads();
         double s0 = 0.0, s1 = 0.0;
+        if (vec4) {
+#pragma unroll 2
+            for (int q = tid * 4; q < n; q += NT * 4) {
+                const float4 ax = spmv_row4(zs, q), bb = ld4(b + q);
+                const float4 rr = make_float4(__fsub_rn(bb.x, ax.x), __fsub_rn(bb.y, ax.y), __fsub_rn(bb.z, ax.z), __fsub_rn(bb.w, ax.w));
+                st4(r + q, rr);
+                s0 += (double)rr.x * rr.x; s0 += (double)rr.y * rr.y; s0 += (double)rr.z * rr.z; s0 += (double)rr.w * rr.w;
+            }
+        } else {
 #pragma unroll 4
-        for (int q = tid; q < n; q += NT) {
-            const float rq = __fsub_rn(b[q], spmv_row(zs, q));
-            r[q] = rq; s0 += (double)rq * rq;
+            for (int q = tid; q < n; q += NT) {
+                const float rq = __fsub_rn(b[q], spmv_row(zs, q));
+                r[q] = rq; s0 += (double)rq * rq;
+            }
         }
         block_sum2(s0, s1, red);
         nrm_r = (float)sqrt(s0);
@@ -876,10 +909,19 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_rows_kernel(const Bi
             precondition(p);                                         // zs = p_hat
             DPISO_TICK(2);
             s0 = 0.0; s1 = 0.0;
+            if (vec4) {
+#pragma unroll 2
+                for (int q = tid * 4; q < n; q += NT * 4) {          // v = A p_hat ; rh.v
+                    const float4 vq = spmv_row4(zs, q), hh = ld4(rh + q);
+                    st4(v + q, vq);
+                    s0 += (double)hh.x * vq.x; s0 += (double)hh.y * vq.y; s0 += (double)hh.z * vq.z; s0 += (double)hh.w * vq.w;
+                }
+            } else {
 #pragma unroll 4
-            for (int q = tid; q < n; q += NT) {                      // v = A p_hat ; rh.v
-                const float vq = spmv_row(zs, q);
-                v[q] = vq; s0 += (double)rh[q] * vq;
+                for (int q = tid; q < n; q += NT) {
+                    const float vq = spmv_row(zs, q);
+                    v[q] = vq; s0 += (double)rh[q] * vq;
+                }
             }
             block_sum2(s0, s1, red);
             alpha = __fdiv_rn(rho, (float)s0);
@@ -905,10 +947,20 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_rows_kernel(const Bi
             precondition(r);                                         // zs = s_hat
             DPISO_TICK(2);
             s0 = 0.0; s1 = 0.0;
+            if (vec4) {
+#pragma unroll 2
+                for (int q = tid * 4; q < n; q += NT * 4) {          // t = A s_hat ; t.r ; t.t
+                    const float4 tq = spmv_row4(zs, q), rr = ld4(r + q);
+                    st4(tt + q, tq);
+                    s0 += (double)tq.x * rr.x; s0 += (double)tq.y * rr.y; s0 += (double)tq.z * rr.z; s0 += (double)tq.w * rr.w;
+                    s1 += (double)tq.x * tq.x; s1 += (double)tq.y * tq.y; s1 += (double)tq.z * tq.z; s1 += (double)tq.w * tq.w;
+                }
+            } else {
 #pragma unroll 4
-            for (int q = tid; q < n; q += NT) {                      // t = A s_hat ; t.r ; t.t
-                const float tq = spmv_row(zs, q);
-                tt[q] = tq; s0 += (double)tq * r[q]; s1 += (double)tq * tq;
+                for (int q = tid; q < n; q += NT) {
+                    const float tq = spmv_row(zs, q);
+                    tt[q] = tq; s0 += (double)tq * r[q]; s1 += (double)tq * tq;
+                }
             }
             block_sum2(s0, s1, red);
             omega = __fdiv_rn((float)s0, (float)s1);
