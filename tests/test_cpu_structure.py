@@ -98,6 +98,75 @@ def test_bicg_tables_reproduce_generic_ilu0(ny, nx, per_x, per_y):
             assert np.array_equal(_emulate_lu(tab, vals, b), O.lu_solve(trp, tci, lu, b))
 
 
+def _emulate_rows(tab, vals, b):
+    """numpy emulation of bicgstab_rows_kernel's canonical-slot ILU(0) + L/U sweeps in wavefront order: thread ly walks
+    along x, lower slots [far, y-neighbour, far, x-neighbour], upper slots [x-neighbour, far, y-neighbour, far]."""
+    n, dx = tab["n"], tab["dx"]
+    dy = n // dx
+    f32 = np.float32
+    lsrc, lrev, usrc, lfar, ufar, dsrc = (tab[k] for k in ("c_lsrc", "c_lrev", "c_usrc", "c_lfar", "c_ufar", "c_dsrc"))
+
+    def val(idx):
+        return np.where(idx >= 0, vals[np.maximum(idx, 0)], 0).astype(f32)
+
+    def fma(x, y, z):
+        return f32(np.float64(x) * np.float64(y) + np.float64(z))
+    alow, arv, uval, dg = val(lsrc), val(lrev), val(usrc), val(dsrc)
+    piv, lval = np.zeros(n, f32), np.zeros((n, 4), f32)
+    order = sorted(range(n), key=lambda i: (i % dx + i // dx, i))            # level by level
+    for i in order:                                                           # ILU(0)
+        lx = i % dx
+        ops = [piv[lfar[i, 0]] if lfar[i, 0] >= 0 else f32(1), piv[i - dx] if i >= dx else f32(1),
+               piv[lfar[i, 1]] if lfar[i, 1] >= 0 else f32(1), piv[i - 1] if lx > 0 else f32(1)]
+        d = dg[i]
+        for m in range(4):
+            lik = f32(alow[i, m] / ops[m])
+            lval[i, m] = lik
+            d = fma(-lik, arv[i, m], d)
+        piv[i] = d
+    z = np.zeros(n, f32)
+    for i in order:                                                           # L solve
+        lx = i % dx
+        ops = [z[lfar[i, 0]] if lfar[i, 0] >= 0 else f32(0), z[i - dx] if i >= dx else f32(0),
+               z[lfar[i, 1]] if lfar[i, 1] >= 0 else f32(0), z[i - 1] if lx > 0 else f32(0)]
+        acc = b[i]
+        for m in range(4):
+            acc = fma(-lval[i, m], ops[m], acc)
+        z[i] = acc
+    for i in reversed(order):                                                 # U solve
+        lx = i % dx
+        ops = [z[i + 1] if lx < dx - 1 else f32(0), z[ufar[i, 0]] if ufar[i, 0] >= 0 else f32(0),
+               z[i + dx] if i + dx < n else f32(0), z[ufar[i, 1]] if ufar[i, 1] >= 0 else f32(0)]
+        acc = z[i]
+        for m in range(4):
+            acc = fma(-uval[i, m], ops[m], acc)
+        z[i] = f32(acc / piv[i])
+    return z
+
+
+@pytest.mark.parametrize("ny,nx,per_x,per_y", [(5, 6, 0, 0), (6, 5, 1, 1), (7, 6, 1, 0), (6, 7, 0, 1), (8, 8, 1, 1)])
+def test_row_major_canonical_slots_reproduce_generic_ilu0(ny, nx, per_x, per_y):
+    """The canonical-slot tables of the row-major BiCGStab kernel: ILU(0) + triangular sweeps emulated in numpy are
+    BIT-identical to the oracle's generic IKJ ILU(0) + CSR triangular solves, for A and A^T."""
+    rng = np.random.RandomState(1)
+    rp, ci = S.csr_pattern(ny, nx, per_x, per_y)
+    n_u, n_v, z_u, z_v = S.sizes(ny, nx, per_x, per_y)
+    for comp in (0, 1):
+        n = (n_u, n_v)[comp]
+        rpc = rp[:n_u + 1] if comp == 0 else rp[n_u + 1:]
+        cic = ci[:z_u] if comp == 0 else ci[z_u:]
+        vals = (rng.randn(rpc[-1]) * 0.1).astype(np.float32)
+        vals[cic == np.repeat(np.arange(n), np.diff(rpc))] += 2.0
+        b = rng.randn(n).astype(np.float32)
+        for tr in (False, True):
+            tab = S.bicg_tables(ny, nx, per_x, per_y, comp, tr)
+            assert tab["rows_ok"] == 1
+            trp, tci, tval = O.csr_transpose(rpc, cic, vals) if tr else (rpc, cic, vals)
+            lu, zero_pivot = O.ilu0(trp, tci, tval)
+            assert zero_pivot == -1
+            assert np.array_equal(_emulate_rows(tab, vals, b), O.lu_solve(trp, tci, lu, b))
+
+
 def test_tables_reject_degenerate_grid():
     with pytest.raises(NotImplementedError):
         S.bicg_tables(3, 3, True, True, 0, False)
