@@ -197,8 +197,13 @@ def piso_step(velocity, pressure, pressure_inc1, pressure_inc2, dt, simulation_p
     pres = as_tensor(pressure.data).reshape(b, g.nc)
     dvals = _flat_faces(dirichlet_values, b, g, "dirichlet_values").to(vel.device)
     forcing = None if forcing_term is None else _flat_faces(forcing_term, b, g, "forcing_term").to(vel.device)
-    if viscosity_field is None:
-        visc = torch.tensor([float(sim.viscosity)], dtype=torch.float32, device=vel.device)   # piso_tf.py:21-24
+    if viscosity_field is None:                                              # piso_tf.py:21-24
+        key = (float(sim.viscosity), str(vel.device))
+        cached = getattr(sim, "_visc_tensor", None)
+        if cached is None or cached[0] != key:                               # uploaded once: no host->device copy per step
+            cached = (key, torch.full((1,), key[0], dtype=torch.float32, device=vel.device))
+            sim._visc_tensor = cached
+        visc = cached[1]
     else:
         visc = as_tensor(viscosity_field).to(vel.device)
         if visc.dim() == 4:
