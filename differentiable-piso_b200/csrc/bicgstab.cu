@@ -3,7 +3,11 @@
 // Re-design of BicgstabIluLinearSolveLauncher (CUDAsrc/multi_bicgstab_ilu_linear_solve_op.cu.cc:85-453), which drives
 // cuSPARSE csrilu02 / csrsv2 / CsrmvEx and cuBLAS level-1 calls from the host (19 library launches and 6 blocking
 // reductions per iteration, one host thread per velocity component).  Here ONE persistent CTA owns one
-// (sample, component) system for the whole solve:
+// (sample, component) system for the whole solve.  Two kernels implement the same sequence:
+//   bicgstab_rows_kernel  row-major layout, one sweep thread per grid row, canonical entry slots, float4 vector phases;
+//                         default whenever the solve vector + cp.async ring fit shared memory (see its header below)
+//   bicgstab_kernel       level-major layout (described next); fallback for larger grids
+// bicgstab_kernel:
 //   * the matrix is re-packed once into a level-major ELL layout (rows ordered by the lx+ly wavefront, <= 6 entries
 //     per row, column order = ascending original column so that every sum is accumulated in CSR order);
 //   * ILU(0) and the four triangular solves per iteration sweep the wavefront levels inside the kernel; the vector
