@@ -96,7 +96,7 @@ __global__ void fv_divergence_adj_kernel(int batch, int ny, int nx, int per_x, i
     gv[t] = v;
 }
 
-struct AdjTab { int n, wa; const int *perm, *a_col, *a_src; };
+struct AdjTab { int n, wa; const int *perm, *a_col, *a_src, *r_col, *r_src; };
 
 // gd = M^T gh - (A - beta) gh : adjoint of explicit_H_csr w.r.t. its vector argument.  Uses the level-major tables of
 // M^T (built for the adjoint BiCGStab): row q of M^T lists the entries M(col, row) with their CSR positions.
@@ -112,6 +112,17 @@ __global__ void h_apply_adj_kernel(int batch, AdjTab tu, AdjTab tv, int nnz_u, i
     const int q = comp ? i - tu.n : i;
     const size_t fo = (size_t)b * nf + (comp ? tu.n : 0);
     const float *val = values + (size_t)b * (nnz_u + nnz_v) + (comp ? nnz_u : 0);
+    if (T.r_col) {
+        // row-major tables (original row order, original column indices, same ascending-column entry order): coalesced
+        // output, neighbour gathers; identical sums
+        float acc = 0.0f;
+        for (int k = 0; k < T.wa; k++) {
+            const int src = T.r_src[k * T.n + q];
+            if (src >= 0) acc = fadd(acc, fmul(val[src], gh[fo + T.r_col[k * T.n + q]]));
+        }
+        gd[fo + q] = fsub(acc, fmul(fsub(a_diag[fo + q], beta), gh[fo + q]));
+        return;
+    }
     const int row = T.perm[q];
     float acc = 0.0f;
     for (int k = 0; k < T.wa; k++) {
@@ -175,8 +186,9 @@ int dpiso_h_apply_adj(int batch, const dpiso_bicg_tables *h_tabT_u, const dpiso_
                       int nnz_v, float beta, const float *values, const float *a_diag, const float *gh, float *gd,
                       void *stream) {
     DPISO_REQUIRE(batch >= 1 && h_tabT_u && h_tabT_v && values && a_diag && gh && gd, "bad arguments");
-    AdjTab tu = {h_tabT_u->n, h_tabT_u->wa, h_tabT_u->perm, h_tabT_u->a_col, h_tabT_u->a_src};
-    AdjTab tv = {h_tabT_v->n, h_tabT_v->wa, h_tabT_v->perm, h_tabT_v->a_col, h_tabT_v->a_src};
+    AdjTab tu = {h_tabT_u->n, h_tabT_u->wa, h_tabT_u->perm, h_tabT_u->a_col, h_tabT_u->a_src, h_tabT_u->r_col, h_tabT_u->r_src};
+    AdjTab tv = {h_tabT_v->n, h_tabT_v->wa, h_tabT_v->perm, h_tabT_v->a_col, h_tabT_v->a_src, h_tabT_v->r_col, h_tabT_v->r_src};
+    if (!tu.r_col || !tv.r_col || !tu.r_src || !tv.r_src) { tu.r_col = tv.r_col = nullptr; }
     const long long n = (long long)batch * (tu.n + tv.n);
     h_apply_adj_kernel<<<blocks_adj(n), kThreadsAdj, 0, (cudaStream_t)stream>>>(batch, tu, tv, nnz_u, nnz_v, beta,
                                                                                  values, a_diag, gh, gd);
