@@ -51,8 +51,7 @@ struct BicgParams {
     int rows_kernel;       // 1: bicgstab_rows_kernel (row-major layout, one thread per grid row in the sweeps)
     int rows_threads;      // its sweep threads P = roundup32(max dy)
     int dbg;               // profiling experiments only (DPISO_BICG_DBG): 1 skip level barrier, 2 skip refill, 4 skip recurrence
-                           // (level-major kernel); 8 force the level-major kernel; 16 row-major sweeps with progress flags
-                           // instead of the per-level barrier (slower: 1.39 M vs 1.22 M cycles)
+                           // (level-major kernel); 8 force the level-major kernel
     const float *values, *rhs, *x0;
     float *x;
     int *stats;
@@ -651,24 +650,22 @@ struct RowsPlanes {
 };
 
 // MODE 0: ILU(0) (zs = pivots), 1: L solve (ext = right-hand side), 2: U solve
-template <int MODE, bool kBarrier>
-__device__ __noinline__ void sweep_rows(const RowsPlanes pl, const float *ext, int dx, int dy, int P) {
+// kZsSmem = false: the solve vector does not fit shared memory and lives in global memory (L2); only the warp-edge lanes,
+// the far operands, the U solve's start values and the result stores touch it -- the x- and y-neighbour operands stay in
+// registers / shuffles, which is what makes this kernel usable far beyond the shared-memory capacity.
+template <int MODE, bool kZsSmem>
+__device__ __noinline__ void sweep_rows(const RowsPlanes pl, const float *ext, int dx, int dy, int P, float *zs_global) {
     constexpr int D = kRowsRing;
-    __shared__ int s_prog[kBicgThreads / 32];
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *const r16a = (float4 *)smem_raw;                           // [D][P] values
     float4 *const r16b = r16a + D * P;                                 // [D][P] ILU: reverse values
     int2 *const r8 = (int2 *)(r16b + D * P);                           // [D][P] far columns
     float *const r4 = (float *)(r8 + D * P);                           // [D][P] right-hand side / diagonal
-    float *const zs = r4 + D * P;                                      // [n] solve vector / pivots
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    float *const zs = kZsSmem ? r4 + D * P : zs_global;                // [n] solve vector / pivots
+    const int t = threadIdx.x, lane = t & 31;
     const int nl = dx + dy - 1;
-    if (!kBarrier && t < kBicgThreads / 32) s_prog[t] = -1;
     __syncthreads();
     if (t < P) {
-        volatile int *const prog = s_prog;
-        volatile float *const zv = zs;
-        const int lead = MODE == 2 ? warp + 1 : warp - 1;             // the warp this one depends on (it runs ahead)
         const bool rowok = t < dy;
         const int i0 = t * dx;
         const float4 *gval = MODE == 2 ? pl.uval : pl.lval;
@@ -707,10 +704,7 @@ __device__ __noinline__ void sweep_rows(const RowsPlanes pl, const float *ext, i
                     const float4 v = r16a[k];
                     const int2 fc = r8[k];
                     const float e = r4[k];
-                    if (edge) {
-                        if (!kBarrier) { while (prog[lead] < s - 1) {} }   // the leading warp has stored step s - 1
-                        nb = zv[i + nb_off];
-                    }
+                    if (edge) nb = zs[i + nb_off];
                     if (MODE == 0) {
                         // l_ik = a_ik / u_kk, u_ii = a_ii - sum l_ik u_ki, lower entries in ascending column order
                         const float4 rv = r16b[k];
@@ -737,11 +731,10 @@ __device__ __noinline__ void sweep_rows(const RowsPlanes pl, const float *ext, i
                         acc = fmaf(-v.w, f1, acc);
                         res = __fdiv_rn(acc, e);
                     }
-                    zv[i] = res;
+                    zs[i] = res;
                 }
                 prev = res;
-                if (kBarrier) named_bar(1, P);
-                else if (lane == (MODE == 2 ? 0 : 31)) prog[warp] = s;   // result, then progress: same thread, in order
+                named_bar(1, P);
             }
         }
         cp_async_wait<0>();
@@ -749,6 +742,7 @@ __device__ __noinline__ void sweep_rows(const RowsPlanes pl, const float *ext, i
     __syncthreads();
 }
 
+template <bool kZsSmem>
 __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_rows_kernel(const BicgParams prm) {
     long long tick = clock64();
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -783,7 +777,8 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_rows_kernel(const Bi
     float *__restrict__ tt = v + n_max;
     pl.arv = (float4 *)rh;
     const int *__restrict__ t_col = T.r_col;
-    float *const zs = (float *)smem_raw + (size_t)kRowsRing * P * 11;      // behind the ring (11 floats per slot)
+    float *const zs_g = tt + n_max;                                        // global home of the solve vector (kZsSmem = false)
+    float *const zs = kZsSmem ? (float *)smem_raw + (size_t)kRowsRing * P * 11 : zs_g;   // behind the ring (11 floats per slot)
 
     // ---- setup: ELL values, canonical rows, NaN guard (":245-256") -------------------------------------------
     double nv = 0.0, nb = 0.0;
@@ -813,12 +808,12 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_rows_kernel(const Bi
     DPISO_TICK(0);
 
     // ---- ILU(0) (csrilu02, ":181-218") ---------------------------------------------------------------------
-    if (prm.dbg & 16) sweep_rows<0, false>(pl, nullptr, dx, dy, P); else sweep_rows<0, true>(pl, nullptr, dx, dy, P);
+    sweep_rows<0, kZsSmem>(pl, nullptr, dx, dy, P, zs_g);
     DPISO_TICK(1);
 
     auto precondition = [&](const float *src) {                      // zs = U^-1 L^-1 src   (csrsv2 x2, ":321-327")
-        if (prm.dbg & 16) { sweep_rows<1, false>(pl, src, dx, dy, P); sweep_rows<2, false>(pl, nullptr, dx, dy, P); }
-        else { sweep_rows<1, true>(pl, src, dx, dy, P); sweep_rows<2, true>(pl, nullptr, dx, dy, P); }
+        sweep_rows<1, kZsSmem>(pl, src, dx, dy, P, zs_g);
+        sweep_rows<2, kZsSmem>(pl, nullptr, dx, dy, P, zs_g);
     };
     auto spmv_row = [&](const float *vec, int q) {                   // CsrmvEx row: fma in ascending column order
         float av[kMaxWa];
@@ -1093,18 +1088,22 @@ int dpiso_bicgstab_ilu(int batch, const dpiso_bicg_tables *h_tab_u, const dpiso_
         !(prm.dbg & 8)) {
         const int dy_u = h_tab_u->n / h_tab_u->dx, dy_v = h_tab_v->n / h_tab_v->dx;
         const int Pr = ((dy_u > dy_v ? dy_u : dy_v) + 31) & ~31;
-        const size_t need = (size_t)kRowsRing * Pr * 11 * sizeof(float) + (size_t)prm.n_max * sizeof(float);
-        if (Pr <= kBicgThreads && need <= kBudget) {
+        const size_t ring = (size_t)kRowsRing * Pr * 11 * sizeof(float);
+        const size_t need_smem = ring + (size_t)prm.n_max * sizeof(float);
+        if (Pr <= kBicgThreads && ring <= kBudget) {
+            const bool zs_smem = need_smem <= kBudget;              // else the solve vector stays in global memory (L2)
             prm.rows_kernel = 1;
             prm.rows_threads = Pr;
             static unsigned long long rows_attr_mask = 0;
             int dev = 0;
             DPISO_CUDA_TRY(cudaGetDevice(&dev));
             if (dev >= 64 || !(rows_attr_mask & (1ull << dev))) {
-                DPISO_CUDA_TRY(cudaFuncSetAttribute(bicgstab_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 1024));
+                DPISO_CUDA_TRY(cudaFuncSetAttribute(bicgstab_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 1024));
+                DPISO_CUDA_TRY(cudaFuncSetAttribute(bicgstab_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 1024));
                 if (dev < 64) rows_attr_mask |= 1ull << dev;
             }
-            bicgstab_rows_kernel<<<batch * 2, kBicgThreads, need, (cudaStream_t)stream>>>(prm);
+            if (zs_smem) bicgstab_rows_kernel<true><<<batch * 2, kBicgThreads, need_smem, (cudaStream_t)stream>>>(prm);
+            else bicgstab_rows_kernel<false><<<batch * 2, kBicgThreads, ring, (cudaStream_t)stream>>>(prm);
             DPISO_CHECK_LAUNCH();
             return DPISO_OK;
         }
