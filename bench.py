@@ -399,6 +399,8 @@ def run_ours(args):
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                      "algorithmic_bytes_per_launch": bytes_per_launch, "mean_cg_iterations": mean_it,
+                     "cg_iterations_min_max": [float(cg_its.min()), float(cg_its.max())],
+                     "mean_of_per_launch_max_iterations": float(np.mean([float(it.max()) for _, _, it in cg_events[:len(cg_ms)]])),
                      "avg_launch_ms": cg_avg_ms, "cg_share_of_step": float(sum(cg_ms) / ms),
                      "note": "solver state is register/smem resident for the whole solve, so the algorithmic HBM model "
                              "of SURVEY 8(d) (168 B/cell/iteration) is exceeded by design (frac > 1); traffic = "
