@@ -92,7 +92,20 @@ def run_reference_step(ns, log, s, vel_flat, pres, forcing_flat, w_u, w_p):
     def tens(x):
         return x.detach().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
     asm = [kw for n, kw in fwd_calls if n == "assemble"][0]
+    # the reference's CPU solver path (LinearSolverScipy, linear_solver.py:33-57): CSR matrices assembled by the reference's
+    # convert_to_scipy_csr (piso_helpers.py:326-343) from the arrays piso_step hands to the solver (-M, [u, v] order) and
+    # solved directly with scipy.sparse.linalg.spsolve -- forward system and the transposed system of the adjoint
+    import scipy.sparse.linalg as spla
+    mats = ns["convert_to_scipy_csr"](-tens(out[4]).astype(np.float64), tens(out[5]), tens(out[6]),
+                                      np.array([1, ny + 1, nx + 1, 2]))
+    n_u = ny * (nx + 1)
+    rhs_np = tens(out[10]).astype(np.float64)
+    adj_rhs = [kw for n, kw in bwd_calls if n == "bicgstab"][0]["rhs"].astype(np.float64)
+    sp_fwd = np.concatenate([spla.spsolve(mats[0].tocsc(), rhs_np[:n_u]), spla.spsolve(mats[1].tocsc(), rhs_np[n_u:])])
+    sp_adj = np.concatenate([spla.spsolve(mats[0].T.tocsc(), adj_rhs[:n_u]), spla.spsolve(mats[1].T.tocsc(), adj_rhs[n_u:])])
+    adj_sol = [kw for n, kw in bwd_calls if n == "bicgstab"][0]
     res = dict(
+        u_star_spsolve=sp_fwd.astype(np.float32), bicg_adj_spsolve=sp_adj.astype(np.float32),
         vel=vel_flat, pres=pres, forcing=forcing_flat, w_u=w_u, w_p=w_p,
         vel_next=flat(v_next), pres_next=tens(p_next).ravel(), p1=tens(out[2].data).ravel(), p2=tens(out[3].data).ravel(),
         values=tens(out[4]), col_ind=tens(out[5]), row_ptr=tens(out[6]), u_star=flat(out[7]), u_s2=flat(out[8]),

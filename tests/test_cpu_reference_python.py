@@ -192,3 +192,24 @@ def test_losses_match_reference(name, factor):
     per, _ = fn([0.0] * steps, [grids], [gt], steps, bw, factor, sponge, sum_steps=False, loss_influence_range=2)
     assert np.isclose(float(total), float(g[name + "_sum"]), rtol=2e-5)
     assert np.allclose([float(x) for x in per], g[name + "_steps"], rtol=2e-5)
+
+
+@pytest.mark.parametrize("name", STEP_SETUPS)
+def test_oracle_bicgstab_matches_reference_cpu_solver(name):
+    """The reference's CPU solver path (LinearSolverScipy, linear_solver.py:33-57: CSR from convert_to_scipy_csr,
+    piso_helpers.py:326-343, solved with spsolve) on the matrices and right-hand sides of the step, forward and
+    transposed: the oracle's ILU0-BiCGStab agrees to fp32 level."""
+    g, s = load_step(name), SMALL_SETUPS[name]()
+    ny, nx = s["ny"], s["nx"]
+    n_u = ny * (nx + 1)
+    rp, ci, neg = g["row_ptr"], g["col_ind"], -g["values"]
+    z_u = int(rp[n_u])
+    for lo, hi, rps, zs in ((0, n_u, rp[:n_u + 1], slice(0, z_u)), (n_u, None, rp[n_u + 1:], slice(z_u, None))):
+        x, st = O.bicgstab_ilu(rps, ci[zs], neg[zs], g["rhs"][lo:hi], g["vel"][lo:hi], s["bicg_tol"], s["bicg_max_it"], False)
+        assert rel_l2(x, g["u_star_spsolve"][lo:hi]) < 1e-6
+        xt, st = O.bicgstab_ilu(rps, ci[zs], neg[zs], g["bwd_bicg_rhs"][lo:hi], g["bwd_bicg_x0"][lo:hi], s["bicg_tol"],
+                                s["bicg_max_it"], True)
+        # (absolute stopping tolerance: small right-hand sides -- the obstacle case uses 1e-3 loss weights -- end with a
+        #  larger relative error)
+        assert rel_l2(xt, g["bicg_adj_spsolve"][lo:hi]) < 2e-5
+    assert rel_l2(g["u_star"], g["u_star_spsolve"]) < 1e-6
