@@ -641,12 +641,14 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_kernel(const BicgPar
 constexpr int kRowsRing = 8;
 
 struct RowsPlanes {
-    float4 *lval;      // [n] ILU: A lower values in, l_ik out
+    float4 *alow;      // [n] A lower values in canonical slots (kept: the SpMV reads them)
+    float *adiag;      // [n] A diagonal (kept)
+    float4 *lval;      // [n] l_ik (written by the ILU sweep)
     float4 *arv;       // [n] ILU only: reverse entries u_ki = A(k, i) of the lower slots (aliases rh, p, v, tt)
     const int2 *lfar;  // [n] columns of the two far lower slots, -1 = absent (static table, shared by all systems)
     float4 *uval;      // [n] upper values (unchanged by ILU(0) on this pattern)
     const int2 *ufar;  // [n]
-    float *udiag;      // [n] A diagonal in, pivot out
+    float *udiag;      // [n] pivots (written by the ILU sweep)
 };
 
 // MODE 0: ILU(0) (zs = pivots), 1: L solve (ext = right-hand side), 2: U solve
@@ -668,9 +670,9 @@ __device__ __noinline__ void sweep_rows(const RowsPlanes pl, const float *ext, i
     if (t < P) {
         const bool rowok = t < dy;
         const int i0 = t * dx;
-        const float4 *gval = MODE == 2 ? pl.uval : pl.lval;
+        const float4 *gval = MODE == 2 ? pl.uval : (MODE == 0 ? pl.alow : pl.lval);
         const int2 *gfar = MODE == 2 ? pl.ufar : pl.lfar;
-        const float *gext = MODE == 1 ? ext : pl.udiag;
+        const float *gext = MODE == 1 ? ext : (MODE == 0 ? pl.adiag : pl.udiag);
         // x of this thread at sweep step s
         auto x_of = [&](int s) { return (MODE == 2 ? nl - 1 - s : s) - t; };
         auto issue = [&](int s, int slot) {
@@ -750,7 +752,7 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_rows_kernel(const Bi
     const int sys = blockIdx.x;
     const int sample = sys >> 1, comp = sys & 1;
     const BicgTab &T = prm.tab[comp];
-    const int n = T.n, wa = T.wa, n_max = prm.n_max, dx = T.dx, dy = T.n / T.dx, P = prm.rows_threads;
+    const int n = T.n, n_max = prm.n_max, dx = T.dx, dy = T.n / T.dx, P = prm.rows_threads;
     const int tid = threadIdx.x, NT = blockDim.x;
     const int face_off = comp ? prm.tab[0].n : 0;
     const float *values_c = prm.values + (size_t)sample * prm.nnz_total + (comp ? prm.nnz[0] : 0);
@@ -760,9 +762,10 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_rows_kernel(const Bi
     float *x_g = prm.x + (size_t)sample * prm.n_face + face_off;
 
     float *ws = prm.workspace + (size_t)sys * prm.ws_floats;
-    float *__restrict__ a_val = ws;                               // [kMaxWa][n_max]  M(row, col), ELL in original order
     RowsPlanes pl;
-    float *cur = a_val + (size_t)kMaxWa * n_max;
+    float *cur = ws;
+    pl.alow = (float4 *)cur;  cur += 4 * (size_t)n_max;
+    pl.adiag = cur;           cur += n_max;
     pl.lval = (float4 *)cur;  cur += 4 * (size_t)n_max;
     pl.uval = (float4 *)cur;  cur += 4 * (size_t)n_max;
     pl.lfar = T.c_lfar;
@@ -776,7 +779,6 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_rows_kernel(const Bi
     float *__restrict__ v = p + n_max;
     float *__restrict__ tt = v + n_max;
     pl.arv = (float4 *)rh;
-    const int *__restrict__ t_col = T.r_col;
     float *const zs_g = tt + n_max;                                        // global home of the solve vector (kZsSmem = false)
     float *const zs = kZsSmem ? (float *)smem_raw + (size_t)kRowsRing * P * 11 : zs_g;   // behind the ring (11 floats per slot)
 
@@ -788,20 +790,16 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_rows_kernel(const Bi
         const float bi = rhs_g[i];
         b[i] = bi; nb += (double)bi * bi;
         x[i] = x0_g[i];                                               // cublasScopy(x_old -> x) (":261")
-        for (int k = 0; k < wa; k++) {
-            const int src = T.r_src[k * n + i];
-            a_val[k * n_max + i] = src >= 0 ? values_c[src] : 0.0f;
-        }
         // canonical rows straight from the host's slot tables
         auto val4 = [&](const int4 s4) {
             return make_float4(s4.x >= 0 ? values_c[s4.x] : 0.0f, s4.y >= 0 ? values_c[s4.y] : 0.0f,
                                s4.z >= 0 ? values_c[s4.z] : 0.0f, s4.w >= 0 ? values_c[s4.w] : 0.0f);
         };
-        pl.lval[i] = val4(T.c_lsrc[i]);
+        pl.alow[i] = val4(T.c_lsrc[i]);
         pl.arv[i] = val4(T.c_lrev[i]);
         pl.uval[i] = val4(T.c_usrc[i]);
         const int ds = T.c_dsrc[i];
-        pl.udiag[i] = ds >= 0 ? values_c[ds] : 1.0f;
+        pl.adiag[i] = ds >= 0 ? values_c[ds] : 1.0f;
     }
     block_sum2(nv, nb, red);
     int warn = (isnan((float)sqrt(nv)) || isnan((float)sqrt(nb))) ? 1 : 0;
@@ -815,43 +813,27 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_rows_kernel(const Bi
         sweep_rows<1, kZsSmem>(pl, src, dx, dy, P, zs_g);
         sweep_rows<2, kZsSmem>(pl, nullptr, dx, dy, P, zs_g);
     };
-    auto spmv_row = [&](const float *vec, int q) {                   // CsrmvEx row: fma in ascending column order
-        float av[kMaxWa];
-        int ac[kMaxWa];
-#pragma unroll
-        for (int k = 0; k < kMaxWa; k++) {                           // all loads first (memory-level parallelism)
-            av[k] = k < wa ? a_val[k * n_max + q] : 0.0f;
-            ac[k] = k < wa ? t_col[k * n + q] : q;
-        }
-        float acc = 0.0f;
-#pragma unroll
-        for (int k = 0; k < kMaxWa; k++)
-            if (k < wa) acc = fmaf(av[k], vec[ac[k]], acc);
+    // CsrmvEx row straight from the canonical planes: lower slots, diagonal, upper slots = ascending column order; the
+    // x- and y-neighbour columns are i -+ 1 and i -+ dx (absent slots carry a zero coefficient and a clamped index), only
+    // the periodic wrap entries need their column from the far tables.  One row per lane: coalesced float4 loads,
+    // conflict-free shared-memory gathers, no ELL value / index planes.
+    auto spmv_row = [&](const float *vec, int i) {
+        const float4 lo = pl.alow[i], up = pl.uval[i];
+        const float dg = pl.adiag[i];
+        const int2 lf = pl.lfar[i], uf = pl.ufar[i];
+        const float l0 = lf.x >= 0 ? vec[lf.x] : 0.0f, l2 = lf.y >= 0 ? vec[lf.y] : 0.0f;
+        const float u1 = uf.x >= 0 ? vec[uf.x] : 0.0f, u3 = uf.y >= 0 ? vec[uf.y] : 0.0f;
+        float acc = fmaf(lo.x, l0, 0.0f);
+        acc = fmaf(lo.y, vec[i - dx > 0 ? i - dx : 0], acc);
+        acc = fmaf(lo.z, l2, acc);
+        acc = fmaf(lo.w, vec[i > 0 ? i - 1 : 0], acc);
+        acc = fmaf(dg, vec[i], acc);
+        acc = fmaf(up.x, vec[i + 1 < n ? i + 1 : i], acc);
+        acc = fmaf(up.y, u1, acc);
+        acc = fmaf(up.z, vec[i + dx < n ? i + dx : i], acc);
+        acc = fmaf(up.w, u3, acc);
         return acc;
     };
-
-    // four consecutive rows at once: float4 / int4 loads of every ELL plane (n is a multiple of 4 here), same fma order
-    auto spmv_row4 = [&](const float *vec, int q) {
-        float4 av[kMaxWa];
-        int4 ac[kMaxWa];
-#pragma unroll
-        for (int k = 0; k < kMaxWa; k++) {
-            av[k] = k < wa ? *reinterpret_cast<const float4 *>(a_val + (size_t)k * n_max + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-            ac[k] = k < wa ? *reinterpret_cast<const int4 *>(t_col + (size_t)k * n + q) : make_int4(q, q, q, q);
-        }
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int k = 0; k < kMaxWa; k++) {
-            if (k < wa) {
-                acc.x = fmaf(av[k].x, vec[ac[k].x], acc.x);
-                acc.y = fmaf(av[k].y, vec[ac[k].y], acc.y);
-                acc.z = fmaf(av[k].z, vec[ac[k].z], acc.z);
-                acc.w = fmaf(av[k].w, vec[ac[k].w], acc.w);
-            }
-        }
-        return acc;
-    };
-    const bool vec4 = (n & 3) == 0;                                  // r_col planes have stride n: int4 loads need n % 4 == 0
 
     float alpha = 1.f, rho = 1.f, rhop = 1.f, omega = 1.f, beta, nrm_r = 0.f;
     int it_count = 0, restarts = 0, exit_kind = 3;
@@ -866,21 +848,12 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_rows_kernel(const Bi
         for (int q = tid; q < n; q += NT) zs[q] = x[q];               // r = b - A x  (":275-282")
         __syncthreads();
         double s0 = 0.0, s1 = 0.0;
-        if (vec4) {
-#pragma unroll 2
-            for (int q = tid * 4; q < n; q += NT * 4) {
-                const float4 ax = spmv_row4(zs, q), bb = ld4(b + q);
-                const float4 rr = make_float4(__fsub_rn(bb.x, ax.x), __fsub_rn(bb.y, ax.y), __fsub_rn(bb.z, ax.z), __fsub_rn(bb.w, ax.w));
-                st4(r + q, rr);
-                s0 += (double)rr.x * rr.x; s0 += (double)rr.y * rr.y; s0 += (double)rr.z * rr.z; s0 += (double)rr.w * rr.w;
-            }
-        } else {
 #pragma unroll 4
-            for (int q = tid; q < n; q += NT) {
-                const float rq = __fsub_rn(b[q], spmv_row(zs, q));
-                r[q] = rq; s0 += (double)rq * rq;
-            }
+        for (int q = tid; q < n; q += NT) {
+            const float rq = __fsub_rn(b[q], spmv_row(zs, q));
+            r[q] = rq; s0 += (double)rq * rq;
         }
+    
         block_sum2(s0, s1, red);
         nrm_r = (float)sqrt(s0);
         if (nrm_r < tol) { exit_kind = 0; break; }                   // lucky guess (":287-289")
@@ -908,20 +881,12 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_rows_kernel(const Bi
             precondition(p);                                         // zs = p_hat
             DPISO_TICK(2);
             s0 = 0.0; s1 = 0.0;
-            if (vec4) {
-#pragma unroll 2
-                for (int q = tid * 4; q < n; q += NT * 4) {          // v = A p_hat ; rh.v
-                    const float4 vq = spmv_row4(zs, q), hh = ld4(rh + q);
-                    st4(v + q, vq);
-                    s0 += (double)hh.x * vq.x; s0 += (double)hh.y * vq.y; s0 += (double)hh.z * vq.z; s0 += (double)hh.w * vq.w;
-                }
-            } else {
 #pragma unroll 4
-                for (int q = tid; q < n; q += NT) {
-                    const float vq = spmv_row(zs, q);
-                    v[q] = vq; s0 += (double)rh[q] * vq;
-                }
+            for (int q = tid; q < n; q += NT) {
+                const float vq = spmv_row(zs, q);
+                v[q] = vq; s0 += (double)rh[q] * vq;
             }
+        
             block_sum2(s0, s1, red);
             alpha = __fdiv_rn(rho, (float)s0);
             s0 = 0.0; s1 = 0.0;
@@ -946,21 +911,12 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_rows_kernel(const Bi
             precondition(r);                                         // zs = s_hat
             DPISO_TICK(2);
             s0 = 0.0; s1 = 0.0;
-            if (vec4) {
-#pragma unroll 2
-                for (int q = tid * 4; q < n; q += NT * 4) {          // t = A s_hat ; t.r ; t.t
-                    const float4 tq = spmv_row4(zs, q), rr = ld4(r + q);
-                    st4(tt + q, tq);
-                    s0 += (double)tq.x * rr.x; s0 += (double)tq.y * rr.y; s0 += (double)tq.z * rr.z; s0 += (double)tq.w * rr.w;
-                    s1 += (double)tq.x * tq.x; s1 += (double)tq.y * tq.y; s1 += (double)tq.z * tq.z; s1 += (double)tq.w * tq.w;
-                }
-            } else {
 #pragma unroll 4
-                for (int q = tid; q < n; q += NT) {
-                    const float tq = spmv_row(zs, q);
-                    tt[q] = tq; s0 += (double)tq * r[q]; s1 += (double)tq * tq;
-                }
+            for (int q = tid; q < n; q += NT) {
+                const float tq = spmv_row(zs, q);
+                tt[q] = tq; s0 += (double)tq * r[q]; s1 += (double)tq * tq;
             }
+        
             block_sum2(s0, s1, red);
             omega = __fdiv_rn((float)s0, (float)s1);
             s0 = 0.0; s1 = 0.0;
