@@ -96,3 +96,20 @@ def test_two_rank_gloo_closure_gradient_allreduce():
     T.training_iteration(opt, w, lambda: (net(x) ** 2).sum() / x.shape[0])
     for a, b in zip(res[0][2], w):
         assert torch.allclose(torch.from_numpy(a), b.detach(), rtol=1e-4, atol=1e-6)
+
+
+def test_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the oracle port on the host cores) prints one JSON line with the contract keys."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "piso_cell_updates_per_s_fwd_adjoint"
+    assert line["unit"] == "cell-updates/s" and line["value"] > 0 and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert line["config"]["workload"].startswith("decaying_turbulence_periodic_128x128")
