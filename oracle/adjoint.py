@@ -9,8 +9,11 @@ What TF-1.14 autodiff assembles from the reference's gradient registrations (SUR
   * finite_volume_gradient_tensor: autodiff of pad/slice/multiply; periodic axes use circular_padded_gradient's
     registered gradient (diffpiso/piso_helpers.py:226-233), quirk Q20;
   * explicit_H_csr: autodiff of gather / segment_sum = transposed product (diffpiso/piso_helpers.py:214-223).
-Parity status: UNPINNED by reference tests (there are none); the non-periodic branches are checked to be exact
-transposes of the forward operators by dot-product tests in tests/.
+Parity status: pinned against the reference's own Python -- every `grad` closure registered with tf.custom_gradient
+executed from source on PhiFlow's torch backend (tests/golden/reference_runner.py, tests/golden/ref_python/step_*.npz,
+tests/test_cpu_reference_python.py): op order, adjoint right-hand sides / initial guess, and the gradients w.r.t.
+velocity, pressure, forcing and Dirichlet values to solver tolerance.  The non-periodic branches are also checked to be
+exact transposes of the forward operators by dot-product tests in tests/.
 All arrays float32 numpy, one sample.
 """
 import numpy as np

@@ -6,14 +6,20 @@
  * cpu_baseline / --impl reference legs of bench.py, and only as the checker / the
  * reported CPU baseline.
  *
- * Parity status: the reference ships no golden vectors for this path.
- * Assembly, Laplace and the pressure CG are pinned on the GPU box against the
- * reference's own kernels compiled from /root/reference/CUDAsrc into oracle/_ref
- * (tests/test_gpu_reference_kernels.py).  The BiCGStab+ILU0 predictor depends on
- * cuSPARSE-10 legacy entry points (csrsv2 / CsrmvEx / csr2csc) that no longer exist
- * in CUDA 12.9, so for that part the parity is UNPINNED: the algorithm below is the
- * textbook one restated from the call sequence in
- * CUDAsrc/multi_bicgstab_ilu_linear_solve_op.cu.cc:233-411.
+ * Parity status: the reference ships no golden vectors for this path; the pins are made from the
+ * reference itself:
+ *   - assembly, CSR structure, Laplace matrix, pressure CG: the reference's own kernels compiled from
+ *     /root/reference/CUDAsrc into oracle/_ref and run on a B200 (tests/test_gpu_reference_pin.py), frozen as
+ *     tests/golden/ref_kernels/*.npz and checked on every CPU run (tests/test_cpu_golden.py): bit-exact;
+ *   - the step's glue (padding, constants, rhs, correctors, H, pressure accumulation) and the backward pass of the
+ *     registered gradients: the reference's own Python executed from source (tests/golden/reference_runner.py), frozen as
+ *     tests/golden/ref_python/step_*.npz (tests/test_cpu_reference_python.py): forward bit-identical, gradients to
+ *     solver tolerance;
+ *   - BiCGStab+ILU0: solutions pinned against the reference's CPU solver path (spsolve on CSR built by the reference's
+ *     convert_to_scipy_csr).  The cuSPARSE-10 arithmetic itself (csrilu02 / csrsv2 / CsrmvEx / csr2csc no longer exist
+ *     in CUDA 12.9) cannot be rebuilt, so iteration counts and ILU(0) rounding are UNPINNED there: the algorithm below
+ *     is the textbook one restated from the call sequence in
+ *     CUDAsrc/multi_bicgstab_ilu_linear_solve_op.cu.cc:233-411.
  *
  * Every function cites the reference file:line it follows (paths relative to
  * /root/reference).  Layout conventions:
