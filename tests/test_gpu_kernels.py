@@ -237,3 +237,28 @@ def test_bicgstab_nan_sets_warn_and_lucky_guess():
     rhs = torch.full((1, g.nf), float("nan"), device=DEV)
     _, st2, warn = ops.bicgstab_ilu(g, neg, rhs, x0, 1e-6, 5)
     assert int(warn.item()) == 1 and st2.cpu().numpy()[0, :, 2].tolist() == [1, 1]
+
+
+@pytest.mark.parametrize("name", ["periodic24x20", "sml16x48", "tml64x128"])
+@pytest.mark.parametrize("transpose", [False, True])
+def test_bicgstab_level_major_fallback_agrees_with_row_major(name, transpose):
+    """The two predictor kernels (row-major default, level-major fallback forced with DPISO_BICG_DBG=8) share the
+    per-row arithmetic; their dot products associate differently, so they agree to rounding, with iteration counts
+    within +-1."""
+    import os
+    from diffpiso_b200 import ops
+    s = ALL_SETUPS[name]()
+    g, m = _geom(s), _masks(s)
+    vels = np.stack([random_fields(s, 80 + i)[0] for i in range(2)])
+    visc = _t(np.atleast_1d(s["visc"]))
+    values, _ = ops.assemble(g, _t(vels), m["dirichlet"], m["active"], m["noslip"], visc, s["dy"], s["dx"], _beta(s))
+    neg = torch.neg(values)
+    rhs = _t(vels) * _beta(s)
+    x_rows, st_rows, _ = ops.bicgstab_ilu(g, neg, rhs, _t(vels), s["bicg_tol"], s["bicg_max_it"], transpose)
+    os.environ["DPISO_BICG_DBG"] = "8"
+    try:
+        x_lm, st_lm, _ = ops.bicgstab_ilu(g, neg, rhs, _t(vels), s["bicg_tol"], s["bicg_max_it"], transpose)
+    finally:
+        del os.environ["DPISO_BICG_DBG"]
+    assert int((st_rows[:, :, 0] - st_lm[:, :, 0]).abs().max()) <= 1
+    assert rel_l2(x_rows.cpu().numpy(), x_lm.cpu().numpy()) < 1e-5
