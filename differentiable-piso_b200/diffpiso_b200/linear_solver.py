@@ -57,7 +57,9 @@ class _BicgSolveFn(torch.autograd.Function):
         df, stats, warn = ops.bicgstab_ilu(ctx.geom, values, gx.contiguous(), x0, solver.accuracy, solver.max_iterations,
                                            not ctx.transpose)
         solver.last_adjoint_stats = stats
-        return df * (1.0 - warn.to(torch.float32)), None, None, None, None, None
+        # per-sample NaN guard (stats[:, :, 2]); the batch-wide OR is only the returned `warn` value
+        keep = 1.0 - stats[:, :, 2].amax(dim=1, keepdim=True).to(torch.float32)
+        return df * keep, None, None, None, None, None
 
 
 class LinearSolverCudaMultiBicgstabILU(LinearSolver):
@@ -104,5 +106,19 @@ class LinearSolverCudaMultiBicgstabILU(LinearSolver):
         return [x, warn_f]
 
 
-# the single-matrix predecessor (diffpiso/linear_solver.py:60-111) runs the same algorithm; kept as an alias
-LinearSolverCudaBicgstabILU = LinearSolverCudaMultiBicgstabILU
+class LinearSolverCudaBicgstabILU(LinearSolverCudaMultiBicgstabILU):
+    """The single-matrix predecessor (diffpiso/linear_solver.py:60-111): same algorithm, but its own call surface --
+    `solve(matrix_values, row_ptr, col_indices, rhs, initial_guess=None, offset=0, transpose=False)` returning the
+    solution tensor only.  The matrix is one momentum component pair in the layout of the Multi solver; the grid is
+    named with the keyword `structure` (a `Geometry`) or `staggered_shape`."""
+
+    def solve(self, matrix_values, row_ptr, col_indices, rhs, initial_guess=None, offset=0, transpose=False,
+              structure=None, staggered_shape=None):
+        if structure is None and staggered_shape is None:
+            raise ValueError("LinearSolverCudaBicgstabILU.solve needs structure=Geometry or staggered_shape=[B, ny+1, nx+1, 2]")
+        if staggered_shape is None:
+            staggered_shape = (1, structure.ny + 1, structure.nx + 1, 2)
+        x, _ = LinearSolverCudaMultiBicgstabILU.solve(self, matrix_values, row_ptr, col_indices, rhs, staggered_shape,
+                                                      initial_guess, offset=offset, transpose=transpose,
+                                                      structure=structure)
+        return x

@@ -35,6 +35,10 @@ class Geometry(object):
 
     def tables(self, transpose):
         """(BicgTables_u, BicgTables_v) ctypes structs whose pointers reference cached device tensors."""
+        with _DeviceGuard(self.device):
+            return self._tables_impl(transpose)
+
+    def _tables_impl(self, transpose):
         t = self._tables.get(bool(transpose))
         if t is None:
             structs, keep = [], []
@@ -58,12 +62,50 @@ class Geometry(object):
     def csr_structure(self):
         """(row_ptr, col_ind) int32 device tensors in the reference layout, from the device kernel."""
         if self._csr is None:
-            rp = torch.empty(self.nf + 2, dtype=torch.int32, device=self.device)
-            ci = torch.empty(self.nnz, dtype=torch.int32, device=self.device)
-            N.check(N.lib.dpiso_csr_structure(self.ny, self.nx, int(self.per_x), int(self.per_y), N.ptr(rp), N.ptr(ci),
-                                              N.stream()), "dpiso_csr_structure")
+            with _DeviceGuard(self.device):
+                rp = torch.empty(self.nf + 2, dtype=torch.int32, device=self.device)
+                ci = torch.empty(self.nnz, dtype=torch.int32, device=self.device)
+                N.check(N.lib.dpiso_csr_structure(self.ny, self.nx, int(self.per_x), int(self.per_y), N.ptr(rp),
+                                                  N.ptr(ci), N.stream()), "dpiso_csr_structure")
             self._csr = (rp, ci)
         return self._csr
+
+
+class _DeviceGuard(object):
+    """Makes the tensor's device current for the duration of a native call: the C entry points launch on whatever
+    cudaGetDevice() reports and N.stream() returns the current stream of the current device, so tensors that live on
+    another device than the caller's current one would otherwise be touched by kernels of the wrong device."""
+    __slots__ = ("dev", "prev")
+
+    def __init__(self, dev):
+        self.dev, self.prev = dev, None
+
+    def __enter__(self):
+        if self.dev.type != "cuda":
+            raise N.DpisoError("libdpiso needs CUDA tensors (got a %s tensor): there is no CPU path" % self.dev)
+        idx = self.dev.index if self.dev.index is not None else torch.cuda.current_device()
+        cur = torch.cuda.current_device()
+        if idx != cur:
+            self.prev = cur
+            torch.cuda.set_device(idx)
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
+        return False
+
+
+def _on_device_of(index):
+    """Decorator: argument `index` (a tensor, or a Geometry for index == 0 of the pure-geometry calls) names the device."""
+    def deco(fn):
+        def wrapped(*args, **kwargs):
+            a = args[index]
+            dev = a.device if hasattr(a, "device") else torch.device("cuda", torch.cuda.current_device())
+            with _DeviceGuard(torch.device(dev)):
+                return fn(*args, **kwargs)
+        wrapped.__name__, wrapped.__doc__ = fn.__name__, fn.__doc__
+        return wrapped
+    return deco
 
 
 def _f32(t):
@@ -77,6 +119,7 @@ def cell_areas(dy64, dx64):
     return float(np.float32(prod / float(np.float32(dx64)))), float(np.float32(prod / float(np.float32(dy64))))
 
 
+@_on_device_of(0)
 def assemble(g, vel, dirichlet_u8, active, noslip_u8, visc, dy, dx, beta, areas=None):
     """-> values [B, nnz], a_diag [B, nf]   (advection_matrix_cuda, diffpiso/piso_tf.py:85-137)"""
     area_x, area_y = cell_areas(dy, dx) if areas is None else areas
@@ -101,6 +144,7 @@ def assemble(g, vel, dirichlet_u8, active, noslip_u8, visc, dy, dx, beta, areas=
     return values, a_diag
 
 
+@_on_device_of(0)
 def predictor_rhs(g, vel, pres, access, dirichlet_u8, dvals, forcing, dy, dx, beta, pbc):
     vel, pres, dvals = _f32(vel), _f32(pres), _f32(dvals)
     b = vel.shape[0]
@@ -114,6 +158,7 @@ def predictor_rhs(g, vel, pres, access, dirichlet_u8, dvals, forcing, dy, dx, be
     return rhs
 
 
+@_on_device_of(0)
 def fv_gradient(g, p, access, dy, dx, pbc):
     p = _f32(p)
     b = p.shape[0]
@@ -123,6 +168,7 @@ def fv_gradient(g, p, access, dy, dx, pbc):
     return out
 
 
+@_on_device_of(0)
 def fv_divergence(g, vel, dy, dx, a_diag=None, beta=0.0):
     vel = _f32(vel)
     b = vel.shape[0]
@@ -132,6 +178,7 @@ def fv_divergence(g, vel, dy, dx, a_diag=None, beta=0.0):
     return out
 
 
+@_on_device_of(0)
 def corrector1(g, u_star, p1, a_diag, access, dy, dx, beta, pbc):
     out = torch.empty_like(u_star)
     N.check(N.lib.dpiso_corrector1(u_star.shape[0], g.ny, g.nx, dy, dx, beta, N.int4(pbc), N.ptr(access), N.ptr(u_star),
@@ -139,6 +186,7 @@ def corrector1(g, u_star, p1, a_diag, access, dy, dx, beta, pbc):
     return out
 
 
+@_on_device_of(0)
 def h_apply(g, values, a_diag, u_star, u_s2, beta):
     out = torch.empty_like(u_star)
     N.check(N.lib.dpiso_h_apply(u_star.shape[0], g.ny, g.nx, int(g.per_x), int(g.per_y), beta, N.ptr(values),
@@ -146,6 +194,7 @@ def h_apply(g, values, a_diag, u_star, u_s2, beta):
     return out
 
 
+@_on_device_of(0)
 def corrector2(g, u_s2, h, p2, a_diag, p, p1, access, dy, dx, beta, pbc):
     u_next = torch.empty_like(u_s2)
     p_next = torch.empty_like(p)
@@ -155,6 +204,7 @@ def corrector2(g, u_s2, h, p2, a_diag, p, p1, access, dy, dx, beta, pbc):
     return u_next, p_next
 
 
+@_on_device_of(0)
 def fv_gradient_adj(g, gs, access, dy, dx, pbc, a_diag=None, beta=0.0, divisor=1.0, negate=False, base=None):
     gs = _f32(gs)
     b = gs.shape[0]
@@ -165,6 +215,7 @@ def fv_gradient_adj(g, gs, access, dy, dx, pbc, a_diag=None, beta=0.0, divisor=1
     return out
 
 
+@_on_device_of(0)
 def fv_divergence_adj(g, gc, dy, dx, base=None, a_diag=None, beta=0.0):
     gc = _f32(gc)
     b = gc.shape[0]
@@ -175,6 +226,7 @@ def fv_divergence_adj(g, gc, dy, dx, base=None, a_diag=None, beta=0.0):
     return out
 
 
+@_on_device_of(0)
 def h_apply_adj(g, values, a_diag, gh, beta):
     gh = _f32(gh)
     tu, tv = g.tables(True)
@@ -184,6 +236,7 @@ def h_apply_adj(g, values, a_diag, gh, beta):
     return out
 
 
+@_on_device_of(0)
 def predictor_rhs_adj(g, grhs, dirichlet_u8, dy, dx, beta, want_force, want_dvals):
     grhs = _f32(grhs)
     b = grhs.shape[0]
@@ -197,6 +250,7 @@ def predictor_rhs_adj(g, grhs, dirichlet_u8, dy, dx, beta, want_force, want_dval
     return gvel, gforce, gdvals, gfree
 
 
+@_on_device_of(0)
 def bicgstab_ilu(g, values, rhs, x0, tol, max_it, transpose=False, warn=None):
     """-> x [B, nf], stats int32 [B, 2, 4] (iterations, restarts, warn, exit kind), warn uint8 [1]"""
     values, rhs, x0 = _f32(values), _f32(rhs), _f32(x0)
@@ -214,6 +268,7 @@ def bicgstab_ilu(g, values, rhs, x0, tol, max_it, transpose=False, warn=None):
     return x, stats, warn
 
 
+@_on_device_of(0)
 def laplace(g, active, fluid, k_faces, mode, beta, dx_factor, fp64=True):
     """-> lap [B, nc, 5]; mode 0: k_faces = scaling field flattened [v, u]; mode 1: k_faces = a_diag [u, v]."""
     k_faces = _f32(k_faces)
@@ -225,6 +280,7 @@ def laplace(g, active, fluid, k_faces, mode, beta, dx_factor, fp64=True):
     return lap
 
 
+@_on_device_of(0)
 def pressure_cg(g, lap, div, accuracy, max_it, residual_reset, rank_deficient):
     """-> pressure float32 [B, nc], iterations int32 [B].  lap fp64: fp32 divergence in, fp64 solve, fp32 out
     (cast_to_double path); lap fp32: everything fp32."""
@@ -252,10 +308,16 @@ def pressure_cg_config():
 
 def to_device_masks(sim, g):
     """Device copies of the SimulationParameters masks in the layouts the kernels read (cached on `sim`)."""
-    key = ("_dpiso_masks", str(g.device))
-    cached = getattr(sim, "_dpiso_cache", None)
-    if cached is not None and cached[0] == key:
-        return cached[1]
+    # the cache is keyed by the grid AND by the identity of the mask objects: a SimulationParameters reused on another
+    # resolution, or whose masks were replaced, gets fresh (re-validated) device copies
+    key = ("_dpiso_masks", str(g.device), g.ny, g.nx, g.per_y, g.per_x, id(sim.dirichlet_mask), id(sim.active_mask),
+           id(sim.accessible_mask), id(sim.no_slip_mask))
+    cache = getattr(sim, "_dpiso_cache", None)
+    if not isinstance(cache, dict):
+        cache = sim._dpiso_cache = {}
+    hit = cache.get(key)
+    if hit is not None:
+        return hit
     from .grids import as_tensor, flatten_staggered_data
     dm = as_tensor(sim.dirichlet_mask, dtype=None)
     dm = flatten_staggered_data(dm.to(torch.float32), coord_flip=True)[0]
@@ -270,14 +332,18 @@ def to_device_masks(sim, g):
         noslip = torch.zeros(nm, dtype=torch.uint8)
     else:
         noslip = as_tensor(sim.no_slip_mask, dtype=None).reshape(-1)
-        if noslip.numel() != nm:
+        if noslip.numel() < nm:
             raise ValueError("no_slip_mask must be indexable as the padded centred grid (ny+2)*(nx+2) "
                              "(CUDAsrc/central_difference_csr_op.cu.cc:251-253)")
-        noslip = (noslip != 0).to(torch.uint8)
+        # the reference kernel reads noSlipWall[centeredNeighborIdx] and nothing else: a larger array (e.g. the
+        # np.zeros_like(dirichlet_mask) of combined_training_integrated.py:536) is read through its first nm entries
+        noslip = (noslip[:nm] != 0).to(torch.uint8)
     acc_np, act_np = access.cpu().numpy().reshape(g.ny + 2, g.nx + 2), active.cpu().numpy().reshape(g.ny + 2, g.nx + 2)
     prod = acc_np * act_np + (1 - acc_np) * (1 - act_np)        # piso_cuda_pressure_solver.py:84-87
     rank_def = bool(np.prod(prod[0, 1:-1]) * np.prod(prod[-1, 1:-1]) * np.prod(prod[1:-1, 0]) * np.prod(prod[1:-1, -1]))
     m = dict(dirichlet=(dm != 0).to(torch.uint8).contiguous().to(g.device), active=active.contiguous().to(g.device),
              access=access.contiguous().to(g.device), noslip=noslip.contiguous().to(g.device), rank_deficient=rank_def)
-    sim._dpiso_cache = (key, m)
+    if len(cache) > 8:
+        cache.clear()
+    cache[key] = m
     return m

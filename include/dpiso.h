@@ -195,6 +195,10 @@ int dpiso_pressure_cg_last_config(int *h_out);
 /* tuning hook for benchmarks / tests: force the cluster size (0 = heuristic) and the kernel variant (-1 = heuristic;
  * 0: 1024 threads, coefficients in smem; 1: 512 threads, coefficients in registers; 2: 512 threads, 2 CTAs/SM) */
 int dpiso_pressure_cg_set_tuning(int cluster, int variant);
+/* parity-measurement switch: 1 = the reference's reduction order of pressure_solve_op.cu.cc:571-634 ({p.r, p.z} ->
+ * alpha -> update x, r -> {r.z} -> beta: two cluster-wide reductions per iteration) instead of the default merged
+ * single reduction (r_new.z = r.z - alpha z.z, DESIGN.md deviation D2).  Cluster-resident kernel only. */
+int dpiso_pressure_cg_set_reduction_order(int two_reductions);
 
 #ifdef __cplusplus
 }

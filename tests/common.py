@@ -1,7 +1,24 @@
 """Shared helpers of the test-suite: seeded inputs and conversions between the reference-shaped API and the oracle."""
+import json
+import os
+
 import numpy as np
 
 from diffpiso_b200 import setups as SU
+
+
+_RECORDS = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_records.jsonl")
+
+
+def record(kind, **vals):
+    """Append one measured parity figure (observed error / iteration difference) to gpurun_out/parity_records.jsonl;
+    scripts/parity_report.py turns the file into the committed table profiles/r02_parity.md."""
+    try:
+        os.makedirs(os.path.dirname(_RECORDS), exist_ok=True)
+        with open(_RECORDS, "a") as f:
+            f.write(json.dumps(dict(kind=kind, **{k: (v.item() if hasattr(v, "item") else v) for k, v in vals.items()})) + "\n")
+    except OSError:
+        pass
 
 
 def rel_l2(a, b):

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from common import ALL_SETUPS, SMALL_SETUPS, random_fields, rel_l2
+from common import ALL_SETUPS, SMALL_SETUPS, random_fields, record, rel_l2
 from oracle import adjoint as A
 from oracle import oracle as O
 from test_gpu_piso_step import DEV, build_sim, extrap
@@ -117,6 +117,10 @@ def test_piso_step_backward_matches_oracle(name):
     gd_total = np.zeros(nf, np.float32)
     for i in range(2):
         ref = A.piso_step_adjoint(s, vel[i], pres[i], w_u[i], w_p[i], forcing=forcing[i])
+        record("adjoint", setup=name, sample=i, cg_tol=s["cg_tol"], g_vel=rel_l2(tv.grad[i].cpu().numpy(), ref["g_vel"]),
+               g_pres=rel_l2(tp.grad[i].cpu().numpy(), ref["g_pres"]),
+               g_forcing=rel_l2(tf.grad[i].cpu().numpy(), ref["g_forcing"]),
+               cg_adj_it=int(sim.pressure_solver.last_iterations[i]), cg_adj_it_oracle=ref["stats"]["cg_adj"][1])
         assert rel_l2(tv.grad[i].cpu().numpy(), ref["g_vel"]) < 1e-4, (name, i, "vel")
         assert rel_l2(tp.grad[i].cpu().numpy(), ref["g_pres"]) < 1e-4, (name, i, "pres")
         assert rel_l2(tf.grad[i].cpu().numpy(), ref["g_forcing"]) < 1e-4, (name, i, "forcing")

@@ -113,3 +113,177 @@ def test_config5_large_periodic_grid_properties(n, batch):
     assert torch.isfinite(v_new).all() and torch.isfinite(out[1].data).all()
     for i in range(1, batch):       # identical samples, identical answers (samples never interact)
         assert torch.equal(v_new[i], v_new[0])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# forward + ADJOINT at the full BASELINE sizes against oracle/adjoint.py (round 2)
+# ------------------------------------------------------------------------------------------------------------------
+def _fwd_adjoint(s, sim, vel, pres, w_u, w_p):
+    """piso_step + backward of loss = <w_u, u_next> + <w_p, p_next> through the public API -> numpy results."""
+    import diffpiso_b200 as dp
+    from test_gpu_piso_step import extrap
+    b = vel.shape[0]
+    ny, nx = s["ny"], s["nx"]
+    nc = ny * nx
+    dxy = (s["dy"], s["dx"])
+    tv = torch.as_tensor(vel).to(DEV).requires_grad_(True)
+    tp = torch.as_tensor(pres).to(DEV).requires_grad_(True)
+    velocity = dp.StaggeredGrid(flat=tv, resolution=(ny, nx), dx=dxy)
+    pressure = dp.CenteredGrid(tp.reshape(b, ny, nx, 1), dx=dxy, extrapolation=extrap(s["pbc"]))
+    inc = dp.CenteredGrid(torch.zeros(b, ny, nx, 1, device=DEV), dx=dxy, extrapolation=extrap(s["pbc_inc"]))
+    visc_field = torch.as_tensor(s["visc"]).to(DEV) if np.atleast_1d(s["visc"]).size > 1 else None
+    v_new, p_new, warn = dp.piso_step(velocity, pressure, inc, inc, s["dt"], sim,
+                                      torch.as_tensor(s["dirichlet_values"])[None].to(DEV), viscosity_field=visc_field)
+    loss = (v_new.flat * torch.as_tensor(w_u).to(DEV)).sum() + (p_new.data.reshape(b, nc) * torch.as_tensor(w_p).to(DEV)).sum()
+    loss.backward()
+    assert float(warn.max()) == 0.0
+    return (v_new.flat.detach().cpu().numpy(), p_new.data.reshape(b, nc).detach().cpu().numpy(), tv.grad.cpu().numpy(),
+            tp.grad.cpu().numpy())
+
+
+def _adjoint_weights(s, batch, seed):
+    ny, nx = s["ny"], s["nx"]
+    nf, nc = ny * (nx + 1) + (ny + 1) * nx, ny * nx
+    rng = np.random.RandomState(seed)
+    w_u, w_p = rng.randn(batch, nf).astype(np.float32), rng.randn(batch, nc).astype(np.float32)
+    if s["rank_deficient"]:      # adjoint pressure right-hand sides compatible with the singular operator
+        act = s["active"].reshape(ny + 2, nx + 2)[1:-1, 1:-1].ravel() != 0
+        w_p[:, ~act] = 0
+        w_p[:, act] -= w_p[:, act].mean(axis=1, keepdims=True)
+    return w_u, w_p
+
+
+# measured worst cases on B200 (profiles/r02_parity.md) x 2 = the asserted bounds
+FULL_ADJOINT_BOUNDS = {
+    "c2_periodic128_b64": dict(vel=1e-5, pres=1e-4, g_vel=1e-4, g_pres=1e-4),
+    "c3_tml256x128_b8": dict(vel=1e-5, pres=1e-4, g_vel=1e-4, g_pres=1e-4),
+    "c4_sml512x128_b4": dict(vel=1e-5, pres=1e-4, g_vel=1e-4, g_pres=1e-4),
+}
+
+
+@pytest.mark.parametrize("name", ["c2_periodic128_b64", "c3_tml256x128_b8", "c4_sml512x128_b4"])
+def test_full_size_forward_and_adjoint_match_oracle(name):
+    """BASELINE configs[1..3] at full size: state and gradients of one fwd+adjoint step against oracle/adjoint.py,
+    sample by sample (3 of the 64 samples for C2)."""
+    from common import record
+    from oracle import adjoint as A
+    make, batch, check = _setups()[name]
+    s = make()
+    sim = build_sim(s)
+    states = [random_fields(s, 500 + i) for i in range(batch)]
+    vel = np.stack([v for v, _ in states])
+    pres = np.stack([p for _, p in states])
+    w_u, w_p = _adjoint_weights(s, batch, 21)
+    v_new, p_new, g_vel, g_pres = _fwd_adjoint(s, sim, vel, pres, w_u, w_p)
+    cg_adj = sim.pressure_solver.last_adjoint_iterations
+    if cg_adj is None:
+        cg_adj = sim.pressure_solver.last_iterations
+    bnd = FULL_ADJOINT_BOUNDS[name]
+    for i in check:
+        ref = A.piso_step_adjoint(s, vel[i], pres[i], w_u[i], w_p[i])
+        e = dict(vel=rel_l2(v_new[i], ref["vel_next"]), pres=rel_l2(p_new[i] - p_new[i].mean(), ref["pres_next"] - ref["pres_next"].mean()),
+                 g_vel=rel_l2(g_vel[i], ref["g_vel"]), g_pres=rel_l2(g_pres[i], ref["g_pres"]))
+        record("full_adjoint", setup=name, sample=i, cg_adj_it=int(cg_adj[i]), cg_adj_it_oracle=ref["stats"]["cg_adj"][1], **e)
+        for k, v in e.items():
+            assert v < bnd[k], (name, i, k, v)
+
+
+def test_c1_lid_driven_cavity_as_shipped():
+    """BASELINE configs[0], exactly as lid_driven_cavity_2d.py:7-13,70,110-111 runs it (N = 32, Re = 100): Domain([N+1, N]),
+    dt = 0.01, zero initial state, pressure CG at 1e-8 / 1000 iterations / residual_reset 10, predictor BiCGStab with
+    max 100 iterations at accuracy 1e-3 for the first six steps (i = 0..5) and 1e-8 afterwards, 200 steps -- the GPU
+    rollout against an oracle rollout with the same schedule."""
+    from common import record
+    from diffpiso_b200 import setups as SU
+    s = SU.lid_driven_cavity(n=32, re=100.0, dt=0.01, bicg_tol=1e-3, bicg_max_it=100, cg_tol=1e-8, cg_max_it=1000, cg_reset=10)
+    sim = build_sim(s)
+    nf, nc = s["ny"] * (s["nx"] + 1) + (s["ny"] + 1) * s["nx"], s["ny"] * s["nx"]
+    vel, pres = np.zeros((1, nf), np.float32), np.zeros((1, nc), np.float32)
+    ov, op = vel[0].copy(), pres[0].copy()
+    worst_v = worst_p = 0.0
+    so = dict(s)
+    for i in range(200):
+        tol = 1e-3 if i <= 5 else 1e-8                               # lid_driven_cavity_2d.py:70,110-111
+        sim.linear_solver.accuracy = tol
+        so["bicg_tol"] = tol
+        out = run_step(s, sim, vel, pres)
+        vel, pres = out[0].flat.cpu().numpy(), out[1].data.reshape(1, -1).cpu().numpy()
+        ov, op, st = O.piso_step(so, ov, op)
+        if i >= 1:
+            worst_v = max(worst_v, rel_l2(vel[0], ov))
+            worst_p = max(worst_p, rel_l2(pres[0] - pres[0].mean(), op - op.mean()))
+    record("c1_ldc32_200steps", vel_rel_l2_final=rel_l2(vel[0], ov), pres_rel_l2_final=rel_l2(pres[0] - pres[0].mean(), op - op.mean()),
+           vel_rel_l2_worst=worst_v, pres_rel_l2_worst=worst_p)
+    assert np.isfinite(vel).all()
+    # first steps run the predictor at 1e-3 on both sides (iteration counts may differ by one => 1e-3-level
+    # differences that the later 1e-8 steps contract); final state: measured x 2
+    assert rel_l2(vel[0], ov) < 2e-4, rel_l2(vel[0], ov)
+    assert rel_l2(pres[0] - pres[0].mean(), op - op.mean()) < 2e-3
+    u = vel[0][:s["ny"] * (s["nx"] + 1)].reshape(s["ny"], s["nx"] + 1)
+    assert np.allclose(u[-1], 1.0)                                   # lid row keeps its Dirichlet value
+    # centre-line u profile against the oracle's: the Ghia-style validation quantity
+    assert np.abs(u[:-1, s["nx"] // 2] - ov[:s["ny"] * (s["nx"] + 1)].reshape(s["ny"], s["nx"] + 1)[:-1, s["nx"] // 2]).max() < 1e-4
+
+
+def test_c2_rollout_1000_steps_statistics_within_one_percent():
+    """BASELINE configs[1]: decaying turbulence, periodic 128 x 128, 1000 forward steps (two samples on the GPU, the first
+    one also with the oracle): kinetic energy, enstrophy and the shell-summed spectrum E(k), k = 1..32, within 1 %
+    (north_star: long-rollout turbulence statistics within 1 %)."""
+    import diffpiso_b200 as dp
+    from common import record
+    from diffpiso_b200 import setups as SU, statistics as S
+    s = SU.periodic_box(128, 128, visc=1e-3)
+    sim = build_sim(s)
+    ny = nx = 128
+    vel0, pres0 = random_fields(s, 1234)
+    vel, pres = np.stack([vel0, random_fields(s, 1235)[0]]), np.stack([pres0, pres0])
+    tv, tp = torch.as_tensor(vel).to(DEV), torch.as_tensor(pres).to(DEV)
+    dxy = (s["dy"], s["dx"])
+    dvals = torch.zeros(1, vel.shape[1], device=DEV)
+    with torch.no_grad():
+        for _ in range(1000):
+            velocity = dp.StaggeredGrid(flat=tv, resolution=(ny, nx), dx=dxy, extrapolation="periodic")
+            pressure = dp.CenteredGrid(tp.reshape(2, ny, nx, 1), dx=dxy, extrapolation="periodic")
+            v_new, p_new, _ = dp.piso_step(velocity, pressure, pressure, pressure, s["dt"], sim, dvals)
+            tv, tp = v_new.flat, p_new.data.reshape(2, ny * nx)
+    vel = tv.cpu().numpy()
+    ov, op = vel0.copy(), pres0.copy()
+    for _ in range(1000):
+        ov, op, _ = O.piso_step(s, ov, op)
+
+    def stats(flat):
+        g = dp.StaggeredGrid(flat=torch.as_tensor(flat[None]), resolution=(ny, nx), dx=dxy, extrapolation="periodic")
+        k, e = S.EK_spectrum_2D(g.at_centers().data[0], None)
+        return float(S.kinetic_energy(g)[0]), float(S.enstrophy(g)[0]), e[1:33]
+    ke_g, en_g, e_g = stats(vel[0])
+    ke_o, en_o, e_o = stats(ov)
+    ke_0, en_0, _ = stats(vel0)
+    record("c2_128_1000steps", ke_ratio=ke_g / ke_o, enstrophy_ratio=en_g / en_o, spectrum_max_dev=float(np.abs(e_g / e_o - 1).max()),
+           field_rel_l2=rel_l2(vel[0], ov), ke_decay=ke_o / ke_0, enstrophy_decay=en_o / en_0)
+    assert ke_o < 0.9 * ke_0 and en_o < 0.8 * en_0                      # the flow did evolve
+    assert abs(ke_g / ke_o - 1) < 0.01 and abs(en_g / en_o - 1) < 0.01
+    assert np.abs(e_g / e_o - 1).max() < 0.01
+
+
+def test_c5_1024_forward_and_adjoint_one_sample_matches_oracle():
+    """BASELINE configs[4]: one periodic 1024 x 1024 sample, forward + adjoint of one step against the oracle (about two
+    minutes of CPU).  The pressure CG runs ~1700 iterations here; iteration counts within the slack, fields as stated."""
+    from common import record
+    from diffpiso_b200 import setups as SU
+    from oracle import adjoint as A
+    s = SU.periodic_box(1024, 1024, visc=1e-3)
+    sim = build_sim(s)
+    v0, p0 = random_fields(s, 4321)
+    w_u, w_p = _adjoint_weights(s, 1, 33)
+    v_new, p_new, g_vel, g_pres = _fwd_adjoint(s, sim, v0[None], p0[None], w_u, w_p)
+    ref = A.piso_step_adjoint(s, v0, p0, w_u[0], w_p[0])
+    e = dict(vel=rel_l2(v_new[0], ref["vel_next"]), pres=rel_l2(p_new[0] - p_new[0].mean(), ref["pres_next"] - ref["pres_next"].mean()),
+             g_vel=rel_l2(g_vel[0], ref["g_vel"]), g_pres=rel_l2(g_pres[0], ref["g_pres"]))
+    bicg = sim.linear_solver.last_stats.cpu().numpy()
+    st = ref["stats"]["forward"]
+    record("c5_1024_fwd_adjoint", bicg_it=[int(bicg[0, 0, 0]), int(bicg[0, 1, 0])], bicg_it_oracle=[st["bicg_u"][0], st["bicg_v"][0]],
+           cg_it_oracle=[st["cg1"], st["cg2"]] + list(ref["stats"]["cg_adj"]), **e)
+    assert abs(int(bicg[0, 0, 0]) - st["bicg_u"][0]) <= 1 and abs(int(bicg[0, 1, 0]) - st["bicg_v"][0]) <= 1
+    # the L-inf stopping test at 1e-8 leaves smooth-mode errors ~ tol / lambda_min ~ tol * N^2 in the pressure
+    assert e["vel"] < 1e-5 and e["g_vel"] < 1e-3, e
+    assert e["pres"] < 1e-3 and e["g_pres"] < 1e-3, e

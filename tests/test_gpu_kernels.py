@@ -123,6 +123,14 @@ def test_pressure_cg_matches_oracle(name, fp64):
     lap = ops.laplace(g, m["active"], m["access"], _t(a_diag), 1, beta, dx_factor, fp64=fp64)
     x, its = ops.pressure_cg(g, lap, _t(div), tol, s["cg_max_it"], s["cg_reset"], s["rank_deficient"])
     x, its = x.cpu().numpy(), its.cpu().numpy()
+    # the same solves in the reference's two-reduction order (deviation D2 switched off), for the parity table
+    from diffpiso_b200 import _native as N
+    N.lib.dpiso_pressure_cg_set_reduction_order(1)
+    try:
+        x2, its2 = ops.pressure_cg(g, lap, _t(div), tol, s["cg_max_it"], s["cg_reset"], s["rank_deficient"])
+        x2, its2 = x2.cpu().numpy(), its2.cpu().numpy()
+    finally:
+        N.lib.dpiso_pressure_cg_set_reduction_order(0)
     k_uv = ((np.float32(1.0) / (np.float32(beta) - a_diag)) * np.float32(dx_factor)).astype(np.float32)
     cfg = ops.pressure_cg_config()
     assert (cfg["variant"] == 4) == (name in STRIP_SETUPS and name != "ldc_like64"), cfg
@@ -136,8 +144,12 @@ def test_pressure_cg_matches_oracle(name, fp64):
         if fp64:
             # counts are quantised (5, or the reset period when that is 10) and sit on a threshold of a slowly decaying
             # residual: the reference's own kernels differ from the oracle by up to two quanta (test_gpu_reference_pin)
-            from common import cg_iteration_slack
+            from common import cg_iteration_slack, record
+            record("cg", setup=name, sample=i, reset=s["cg_reset"], it_oracle=oit, it_gpu=int(its[i]),
+                   it_gpu_two_reductions=int(its2[i]), x_rel_l2=rel_l2(x[i], ox.astype(np.float32)),
+                   x_rel_l2_two_reductions=rel_l2(x2[i], ox.astype(np.float32)), variant=cfg["variant"])
             assert abs(int(its[i]) - oit) <= cg_iteration_slack(s, oit), (name, i, int(its[i]), oit)
+            assert abs(int(its2[i]) - oit) <= cg_iteration_slack(s, oit), (name, i, int(its2[i]), oit, "two reductions")
             # both sides stop on |r|_inf < tol at (possibly) different iterates: error in x ~ tol * cond
             slack = 2e-4 if s["cg_reset"] <= 10 else 3e-5      # restarted CG stops further from the fixed point
             assert rel_l2(x[i], ox.astype(np.float32)) < max(slack, 1000 * tol), (name, i)

@@ -13,7 +13,7 @@ import os
 import numpy as np
 import pytest
 
-from common import SMALL_SETUPS, random_fields, rel_l2
+from common import ALL_SETUPS, SMALL_SETUPS, random_fields, record, rel_l2
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -98,18 +98,21 @@ def ref_pressure(lib, s, k_vu, div, fp64, tol):
     return lap, x, int(it[0])
 
 
-@pytest.mark.parametrize("name", ["ldc8", "ldc32", "periodic16", "periodic24x20", "periodic32", "tml16x24", "sml16x48", "obstacle16x24"])
+@pytest.mark.parametrize("name", ["ldc8", "ldc32", "periodic16", "periodic24x20", "periodic32", "tml16x24", "sml16x48", "obstacle16x24",
+                                  "periodic64", "periodic128", "periodic64x32", "tml64x128", "sml32x128", "ldc_like64"])
 @pytest.mark.parametrize("fp64", [True, False])
 def test_oracle_pressure_solve_equals_reference_kernels(ref, name, fp64):
     """Laplace matrix bit-exact; fp64 CG iteration count equal up to one check period (the quantised cadence of SURVEY
     Q2 is produced by the reference itself) up to two quanta / 10% and the solution within 2e-5 relative L2 -- cuBLAS
     reductions associate differently from the oracle's sequential sums and the stopping test sits on a slowly decaying
     residual; fp32 solution within 2e-2."""
-    s = SMALL_SETUPS[name]()
+    if name not in SMALL_SETUPS and not fp64:
+        pytest.skip("fp32 reference solve only pinned on the small setups")
+    s = ALL_SETUPS[name]()
     ny, nx = s["ny"], s["nx"]
     n_u, n_v = ny * (nx + 1), (ny + 1) * nx
     from common import pressure_problem
-    a_diag, div, _ = pressure_problem(s, 17)
+    a_diag, div, _ = pressure_problem(s, 17 if name in SMALL_SETUPS else 5)
     c = O.step_constants(s["dy"], s["dx"], s["dt"])
     k_uv = ((np.float32(1.0) / (np.float32(c["beta"]) - a_diag)) * np.float32(c["dx_factor"])).astype(np.float32)
     k_vu = np.concatenate([k_uv[n_u:], k_uv[:n_u]])
@@ -122,9 +125,12 @@ def test_oracle_pressure_solve_equals_reference_kernels(ref, name, fp64):
                             s["rank_deficient"])
     if fp64:
         from common import cg_iteration_slack
+        record("cg_reference_kernel", setup=name, reset=s["cg_reset"], it_oracle=oit, it_reference=it,
+               x_rel_l2=rel_l2(ox, x))
         assert abs(it - oit) <= cg_iteration_slack(s, oit), (name, it, oit)
         assert rel_l2(ox, x) < max(2e-5, 1000 * tol), rel_l2(ox, x)
     else:
         assert rel_l2(ox, x) < 5e-2, (rel_l2(ox, x), it, oit)
-    np.savez_compressed(os.path.join(OUT, "pressure_%s_%s.npz" % (name, "f64" if fp64 else "f32")), k_vu=k_vu, div=div,
-                        lap=lap, x=x, iterations=np.int32(it), tol=np.float32(tol))
+    if name in SMALL_SETUPS:
+        np.savez_compressed(os.path.join(OUT, "pressure_%s_%s.npz" % (name, "f64" if fp64 else "f32")), k_vu=k_vu, div=div,
+                            lap=lap, x=x, iterations=np.int32(it), tol=np.float32(tol))
