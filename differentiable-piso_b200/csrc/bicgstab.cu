@@ -53,9 +53,13 @@ struct BicgParams {
     int dbg;               // profiling experiments only (DPISO_BICG_DBG): 1 skip level barrier, 2 skip refill, 4 skip recurrence
                            // (level-major kernel); 8 force the level-major kernel
     const float *values, *rhs, *x0;
+    float sign;            // +1 / -1: the solve runs on sign * values (piso_tf.py:42 passes -M)
     float *x;
     int *stats;
-    uint8_t *warn;
+    float *warn;
+    float *pivots_out;     // optional [batch][n_face]: ILU(0) pivots of this solve (row-major kernel)
+    const float *pivots_in; // optional [batch][n_face]: pivots of the other orientation -> no factorisation sweep
+    int reuse_mask;        // bit c: component c takes pivots_in
     float *workspace;
     float tol;
     int max_it;
@@ -96,7 +100,7 @@ struct RowRegs {
 //   MODE 1: L solve   zs[q] = in[q] - sum_{col<q} lu*zs[col]
 //   MODE 2: U solve   zs[q] = (zs[q] - sum_{col>q} lu*zs[col]) / lu_diag
 template <int MODE>
-__device__ __noinline__ void wavefront(const BicgTab &T, int n_max, const float *__restrict__ values_c, const float *a_val,
+__device__ __noinline__ void wavefront(const BicgTab &T, int n_max, const float *__restrict__ values_c, float sign, const float *a_val,
                           float *lu, const float *in, float *zs) {
     const int wa = T.wa, n = T.n;
     const int P = min((int)blockDim.x, (T.max_level + 31) & ~31);
@@ -121,7 +125,7 @@ __device__ __noinline__ void wavefront(const BicgTab &T, int n_max, const float 
                             const float lik = __fdiv_rn(a, zs[col]);
                             lu[k * n_max + q] = lik;
                             const int rev = T.a_rev[k * n + q];
-                            if (rev >= 0) diag = fmaf(-lik, values_c[rev], diag);
+                            if (rev >= 0) diag = fmaf(-lik, sign * values_c[rev], diag);
                         } else if (k != dslot) {
                             lu[k * n_max + q] = a;                    // U entries are unchanged by ILU(0) on this pattern
                         }
@@ -445,8 +449,8 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_kernel(const BicgPar
         x[q] = x0_g[orig];                                           // cublasScopy(x_old -> x) (":261")
         for (int k = 0; k < wa; k++) {
             const int src = T.a_src[k * n + q], rev = T.a_rev[k * n + q];
-            a_val[k * n_max + q] = src >= 0 ? values_c[src] : 0.0f;
-            a_rv[k * n_max + q] = rev >= 0 ? values_c[rev] : 0.0f;
+            a_val[k * n_max + q] = src >= 0 ? prm.sign * values_c[src] : 0.0f;
+            a_rv[k * n_max + q] = rev >= 0 ? prm.sign * values_c[rev] : 0.0f;
         }
     }
     block_sum2(nv, nb, red);
@@ -458,7 +462,7 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_kernel(const BicgPar
     if (fast) {
         if (zsm) wavefront_staged<0, true>(T, prm.lp_cap, n_max, a_val, a_rv, lu, nullptr, zs_glob, prm.stage_rows);
         else wavefront_staged<0, false>(T, prm.lp_cap, n_max, a_val, a_rv, lu, nullptr, zs_glob, prm.stage_rows);
-    } else wavefront<0>(T, n_max, values_c, a_val, lu, nullptr, zs);
+    } else wavefront<0>(T, n_max, values_c, prm.sign, a_val, lu, nullptr, zs);
     __syncthreads();
     DPISO_TICK(1);
     if (fast && zsm && prm.compact) {            // compact every row once: <= 4 lower entries, <= 4 upper entries + pivot
@@ -509,8 +513,8 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_kernel(const BicgPar
             wavefront_staged<1, false>(T, prm.lp_cap, n_max, lu, nullptr, nullptr, src, zs_glob, prm.stage_rows);
             wavefront_staged<2, false>(T, prm.lp_cap, n_max, lu, nullptr, nullptr, nullptr, zs_glob, prm.stage_rows);
         } else {
-            wavefront<1>(T, n_max, nullptr, nullptr, lu, src, zs);
-            wavefront<2>(T, n_max, nullptr, nullptr, lu, nullptr, zs);
+            wavefront<1>(T, n_max, nullptr, 1.0f, nullptr, lu, src, zs);
+            wavefront<2>(T, n_max, nullptr, 1.0f, nullptr, lu, nullptr, zs);
         }
     };
     auto spmv_row = [&](const float *vec, int q) {                   // CsrmvEx row: fma in ascending column order
@@ -619,7 +623,7 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_kernel(const BicgPar
     if (tid == 0) {
         int *st = prm.stats + (size_t)sys * 4;
         st[0] = it_count; st[1] = restarts; st[2] = warn; st[3] = exit_kind;
-        if (warn) *prm.warn = 1;
+        if (warn) *prm.warn = 1.0f;
     }
 }
 
@@ -791,22 +795,44 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_rows_kernel(const Bi
         b[i] = bi; nb += (double)bi * bi;
         x[i] = x0_g[i];                                               // cublasScopy(x_old -> x) (":261")
         // canonical rows straight from the host's slot tables
+        const float sg = prm.sign;
         auto val4 = [&](const int4 s4) {
-            return make_float4(s4.x >= 0 ? values_c[s4.x] : 0.0f, s4.y >= 0 ? values_c[s4.y] : 0.0f,
-                               s4.z >= 0 ? values_c[s4.z] : 0.0f, s4.w >= 0 ? values_c[s4.w] : 0.0f);
+            return make_float4(s4.x >= 0 ? sg * values_c[s4.x] : 0.0f, s4.y >= 0 ? sg * values_c[s4.y] : 0.0f,
+                               s4.z >= 0 ? sg * values_c[s4.z] : 0.0f, s4.w >= 0 ? sg * values_c[s4.w] : 0.0f);
         };
         pl.alow[i] = val4(T.c_lsrc[i]);
         pl.arv[i] = val4(T.c_lrev[i]);
         pl.uval[i] = val4(T.c_usrc[i]);
         const int ds = T.c_dsrc[i];
-        pl.adiag[i] = ds >= 0 ? values_c[ds] : 1.0f;
+        pl.adiag[i] = ds >= 0 ? sg * values_c[ds] : 1.0f;
     }
     block_sum2(nv, nb, red);
     int warn = (isnan((float)sqrt(nv)) || isnan((float)sqrt(nb))) ? 1 : 0;
     DPISO_TICK(0);
 
     // ---- ILU(0) (csrilu02, ":181-218") ---------------------------------------------------------------------
-    sweep_rows<0, kZsSmem>(pl, nullptr, dx, dy, P, zs_g);
+    if (prm.pivots_in && ((prm.reuse_mask >> comp) & 1)) {
+        // factor reuse: the pivots d of the solve with the other orientation of this matrix are given, and
+        // ILU(0)(M^T) = (U^T D^-1)(D L^T): l'_ik = m_ik / d_k, upper entries unchanged, pivots d -- a parallel pass
+        // instead of the wavefront sweep (same division as the sweep, MODE 0 of sweep_rows)
+        const float *d_in = prm.pivots_in + (size_t)sample * prm.n_face + face_off;
+        __syncthreads();
+        for (int i = tid; i < n; i += NT) {
+            const float4 a = pl.alow[i];
+            const int2 fc = pl.lfar[i];
+            const float p0 = fc.x >= 0 ? d_in[fc.x] : 1.0f, p2 = fc.y >= 0 ? d_in[fc.y] : 1.0f;
+            const float p1 = i - dx >= 0 ? d_in[i - dx] : 1.0f, p3 = i >= 1 ? d_in[i - 1] : 1.0f;
+            pl.lval[i] = make_float4(__fdiv_rn(a.x, p0), __fdiv_rn(a.y, p1), __fdiv_rn(a.z, p2), __fdiv_rn(a.w, p3));
+            pl.udiag[i] = d_in[i];
+        }
+        __syncthreads();
+    } else {
+        sweep_rows<0, kZsSmem>(pl, nullptr, dx, dy, P, zs_g);
+        if (prm.pivots_out) {
+            float *d_out = prm.pivots_out + (size_t)sample * prm.n_face + face_off;
+            for (int i = tid; i < n; i += NT) d_out[i] = pl.udiag[i];
+        }
+    }
     DPISO_TICK(1);
 
     auto precondition = [&](const float *src) {                      // zs = U^-1 L^-1 src   (csrsv2 x2, ":321-327")
@@ -952,7 +978,7 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_rows_kernel(const Bi
     if (tid == 0) {
         int *st = prm.stats + (size_t)sys * 4;
         st[0] = it_count; st[1] = restarts; st[2] = warn; st[3] = exit_kind;
-        if (warn) *prm.warn = 1;
+        if (warn) *prm.warn = 1.0f;
     }
 }
 
@@ -986,9 +1012,38 @@ size_t dpiso_bicgstab_workspace_floats(const dpiso_bicg_tables *h_tab_u, const d
     return (3 * (size_t)kMaxWa + 8) * n_pad + 17 * n_pad;
 }
 
+static int g_reuse_always = 0;
+static int g_bicg_dbg = -1;          // >= 0 overrides DPISO_BICG_DBG (tests force the level-major kernel with 8)
+
+static bool rows_kernel_applies(const dpiso_bicg_tables *h_tab_u, const dpiso_bicg_tables *h_tab_v, int *p_rows) {
+    if (!(h_tab_u->rows_ok && h_tab_v->rows_ok && h_tab_u->c_lsrc && h_tab_v->c_lsrc && h_tab_u->dx > 0 && h_tab_v->dx > 0))
+        return false;
+    const int dy_u = h_tab_u->n / h_tab_u->dx, dy_v = h_tab_v->n / h_tab_v->dx;
+    const int Pr = ((dy_u > dy_v ? dy_u : dy_v) + 31) & ~31;
+    const size_t ring = (size_t)kRowsRing * Pr * 11 * sizeof(float);
+    if (p_rows) *p_rows = Pr;
+    return Pr <= kBicgThreads && ring <= 200 * 1024;
+}
+
+int dpiso_bicgstab_supports_factor_reuse(const dpiso_bicg_tables *h_tab_u, const dpiso_bicg_tables *h_tab_v) {
+    if (!h_tab_u || !h_tab_v) return 0;
+    return rows_kernel_applies(h_tab_u, h_tab_v, nullptr) ? 1 : 0;
+}
+
+int dpiso_bicgstab_set_debug(int dbg) {
+    g_bicg_dbg = dbg;
+    return DPISO_OK;
+}
+
+int dpiso_bicgstab_set_reuse_policy(int always) {
+    g_reuse_always = always ? 1 : 0;
+    return DPISO_OK;
+}
+
 int dpiso_bicgstab_ilu(int batch, const dpiso_bicg_tables *h_tab_u, const dpiso_bicg_tables *h_tab_v, int nnz_u,
-                       int nnz_v, const float *values, const float *rhs, const float *x0, float tol, int max_it,
-                       float *x, int *stats, uint8_t *warn, float *workspace, void *stream) {
+                       int nnz_v, const float *values, int negate, const float *rhs, const float *x0, float tol,
+                       int max_it, float *x, int *stats, float *warn, float *pivots_out, const float *pivots_in,
+                       float *workspace, void *stream) {
     DPISO_REQUIRE(batch >= 1 && h_tab_u && h_tab_v, "bad arguments");
     DPISO_REQUIRE(values && rhs && x0 && x && stats && warn && workspace, "null pointer");
     DPISO_REQUIRE(h_tab_u->wa >= 1 && h_tab_u->wa <= kMaxWa && h_tab_v->wa >= 1 && h_tab_v->wa <= kMaxWa,
@@ -1001,9 +1056,15 @@ int dpiso_bicgstab_ilu(int batch, const dpiso_bicg_tables *h_tab_u, const dpiso_
     prm.n_max = ((h_tab_u->n > h_tab_v->n ? h_tab_u->n : h_tab_v->n) + 3) & ~3;     // plane stride, 16-byte aligned
     prm.ws_floats = dpiso_bicgstab_workspace_floats(h_tab_u, h_tab_v);
     prm.values = values; prm.rhs = rhs; prm.x0 = x0; prm.x = x; prm.stats = stats; prm.warn = warn;
+    prm.sign = negate ? -1.0f : 1.0f;
+    prm.pivots_out = nullptr; prm.pivots_in = nullptr; prm.reuse_mask = 0;
     prm.workspace = workspace; prm.tol = tol; prm.max_it = max_it;
     prm.timing = g_bicg_timing;
-    { const char *e = getenv("DPISO_BICG_DBG"); prm.dbg = e ? atoi(e) : 0; }
+    {   // profiling experiments only; read once per process
+        static const int dbg_env = [] { const char *e = getenv("DPISO_BICG_DBG"); return e ? atoi(e) : 0; }();
+        prm.dbg = g_bicg_dbg >= 0 ? g_bicg_dbg : dbg_env;
+    }
+    DPISO_CUDA_TRY(cudaMemsetAsync(warn, 0, sizeof(float), (cudaStream_t)stream));
     // shared memory plan: level_ptr copy + two stage buffers (staged wavefront) + the solve vector zs
     const size_t kBudget = 200 * 1024;
     const int max_level = h_tab_u->max_level > h_tab_v->max_level ? h_tab_u->max_level : h_tab_v->max_level;
@@ -1039,14 +1100,13 @@ int dpiso_bicgstab_ilu(int batch, const dpiso_bicg_tables *h_tab_u, const dpiso_
     }
     // row-major kernel: every row in canonical slots, one sweep thread per grid row, ring + solve vector in shared memory
     prm.rows_kernel = 0;
-    if (h_tab_u->rows_ok && h_tab_v->rows_ok && h_tab_u->r_col && h_tab_v->r_col && h_tab_u->c_lsrc && h_tab_v->c_lsrc &&
-        h_tab_u->dx > 0 && h_tab_v->dx > 0 &&
-        !(prm.dbg & 8)) {
-        const int dy_u = h_tab_u->n / h_tab_u->dx, dy_v = h_tab_v->n / h_tab_v->dx;
-        const int Pr = ((dy_u > dy_v ? dy_u : dy_v) + 31) & ~31;
+    int Pr = 0;
+    if (rows_kernel_applies(h_tab_u, h_tab_v, &Pr) && !(prm.dbg & 8)) {
         const size_t ring = (size_t)kRowsRing * Pr * 11 * sizeof(float);
         const size_t need_smem = ring + (size_t)prm.n_max * sizeof(float);
-        if (Pr <= kBicgThreads && ring <= kBudget) {
+        {
+            prm.pivots_out = pivots_out; prm.pivots_in = pivots_in;
+            prm.reuse_mask = g_reuse_always ? 3 : ((h_tab_u->sym ? 1 : 0) | (h_tab_v->sym ? 2 : 0));
             const bool zs_smem = need_smem <= kBudget;              // else the solve vector stays in global memory (L2)
             prm.rows_kernel = 1;
             prm.rows_threads = Pr;

@@ -61,7 +61,8 @@ __global__ void fv_gradient_adj_kernel(int batch, int ny, int nx, float dy, floa
 // v[0] = g[N-2]*c - g[0]*c,  v[N] = g[N-1]*c - g[0]*c.
 __global__ void fv_divergence_adj_kernel(int batch, int ny, int nx, int per_x, int per_y, float dy, float dx, float prod,
                                          const float *__restrict__ gc, const float *__restrict__ base,
-                                         const float *__restrict__ a_diag, float beta, float *__restrict__ gv) {
+                                         const float *__restrict__ base_sub, const float *__restrict__ a_diag,
+                                         float beta, float *__restrict__ gv) {
     const int nc = ny * nx, n_u = ny * (nx + 1), nf = n_u + (ny + 1) * nx;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)batch * nf) return;
@@ -91,7 +92,7 @@ __global__ void fv_divergence_adj_kernel(int batch, int ny, int nx, int per_x, i
         }
     }
     float v = fadd(fdiv(fmul(-hi, prod), d), fdiv(fmul(lo, prod), d));
-    if (base) v = fadd(base[t], v);
+    if (base) v = fadd(base_sub ? fsub(base[t], base_sub[t]) : base[t], v);
     if (a_diag) v = fdiv(v, fsub(beta, a_diag[t]));
     gv[t] = v;
 }
@@ -102,7 +103,8 @@ struct AdjTab { int n, wa; const int *perm, *a_col, *a_src, *r_col, *r_src; };
 // M^T (built for the adjoint BiCGStab): row q of M^T lists the entries M(col, row) with their CSR positions.
 __global__ void h_apply_adj_kernel(int batch, AdjTab tu, AdjTab tv, int nnz_u, int nnz_v, float beta,
                                    const float *__restrict__ values, const float *__restrict__ a_diag,
-                                   const float *__restrict__ gh, float *__restrict__ gd) {
+                                   const float *__restrict__ gh, float *__restrict__ gd,
+                                   const float *__restrict__ base, float *__restrict__ sum) {
     const int nf = tu.n + tv.n;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)batch * nf) return;
@@ -120,7 +122,9 @@ __global__ void h_apply_adj_kernel(int batch, AdjTab tu, AdjTab tv, int nnz_u, i
             const int src = T.r_src[k * T.n + q];
             if (src >= 0) acc = fadd(acc, fmul(val[src], gh[fo + T.r_col[k * T.n + q]]));
         }
-        gd[fo + q] = fsub(acc, fmul(fsub(a_diag[fo + q], beta), gh[fo + q]));
+        const float out = fsub(acc, fmul(fsub(a_diag[fo + q], beta), gh[fo + q]));
+        gd[fo + q] = out;
+        if (sum) sum[fo + q] = fadd(base[fo + q], out);
         return;
     }
     const int row = T.perm[q];
@@ -129,19 +133,27 @@ __global__ void h_apply_adj_kernel(int batch, AdjTab tu, AdjTab tv, int nnz_u, i
         const int src = T.a_src[k * T.n + q];
         if (src >= 0) acc = fadd(acc, fmul(val[src], gh[fo + T.perm[T.a_col[k * T.n + q]]]));
     }
-    gd[fo + row] = fsub(acc, fmul(fsub(a_diag[fo + row], beta), gh[fo + row]));
+    const float out = fsub(acc, fmul(fsub(a_diag[fo + row], beta), gh[fo + row]));
+    gd[fo + row] = out;
+    if (sum) sum[fo + row] = fadd(base[fo + row], out);
 }
 
 // adjoint of the rhs assembly (piso_tf.py:36-40, piso_helpers.py:170): with m = dirichlet mask,
 //   gvel = (1-m)*grhs*beta,  gforce = (1-m)*grhs*prod,  gdvals = -m*grhs,  gfree = (1-m)*grhs (input of -G^T)
 __global__ void predictor_rhs_adj_kernel(int batch, int nf, float prod, float beta, const uint8_t *__restrict__ dirichlet,
-                                         const float *__restrict__ grhs, float *__restrict__ gvel,
+                                         const float *__restrict__ grhs, const int *__restrict__ solve_stats,
+                                         float *__restrict__ gvel,
                                          float *__restrict__ gforce, float *__restrict__ gdvals,
                                          float *__restrict__ gfree) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (long long)batch * nf) return;
     const int i = (int)(t % nf);
-    const float g = grhs[t];
+    float g = grhs[t];
+    if (solve_stats) {          // df * (1 - warn) of linear_solver.py:169-173, per sample
+        const int b = (int)(t / nf);
+        const float keep = (solve_stats[b * 8 + 2] | solve_stats[b * 8 + 6]) ? 0.0f : 1.0f;
+        g = fmul(g, keep);
+    }
     const bool m = dirichlet[i] != 0;
     const float gf = m ? 0.0f : g;
     gvel[t] = fmul(gf, beta);
@@ -172,38 +184,39 @@ int dpiso_fv_gradient_adj(int batch, int ny, int nx, float dy, float dx, const i
 }
 
 int dpiso_fv_divergence_adj(int batch, int ny, int nx, int per_x, int per_y, float dy, float dx, const float *gc,
-                            const float *base, const float *a_diag, float beta, float *gv, void *stream) {
+                            const float *base, const float *base_sub, const float *a_diag, float beta, float *gv,
+                            void *stream) {
     DPISO_REQUIRE(batch >= 1 && ny >= 3 && nx >= 3, "bad sizes");
-    DPISO_REQUIRE(gc && gv, "null pointer");
+    DPISO_REQUIRE(gc && gv && (base || !base_sub), "null pointer");
     const long long n = (long long)batch * (ny * (nx + 1) + (ny + 1) * nx);
     fv_divergence_adj_kernel<<<blocks_adj(n), kThreadsAdj, 0, (cudaStream_t)stream>>>(
-        batch, ny, nx, per_x ? 1 : 0, per_y ? 1 : 0, dy, dx, cell_prod_adj(dy, dx), gc, base, a_diag, beta, gv);
+        batch, ny, nx, per_x ? 1 : 0, per_y ? 1 : 0, dy, dx, cell_prod_adj(dy, dx), gc, base, base_sub, a_diag, beta, gv);
     DPISO_CHECK_LAUNCH();
     return DPISO_OK;
 }
 
 int dpiso_h_apply_adj(int batch, const dpiso_bicg_tables *h_tabT_u, const dpiso_bicg_tables *h_tabT_v, int nnz_u,
                       int nnz_v, float beta, const float *values, const float *a_diag, const float *gh, float *gd,
-                      void *stream) {
-    DPISO_REQUIRE(batch >= 1 && h_tabT_u && h_tabT_v && values && a_diag && gh && gd, "bad arguments");
+                      const float *base, float *sum, void *stream) {
+    DPISO_REQUIRE(batch >= 1 && h_tabT_u && h_tabT_v && values && a_diag && gh && gd && (base || !sum), "bad arguments");
     AdjTab tu = {h_tabT_u->n, h_tabT_u->wa, h_tabT_u->perm, h_tabT_u->a_col, h_tabT_u->a_src, h_tabT_u->r_col, h_tabT_u->r_src};
     AdjTab tv = {h_tabT_v->n, h_tabT_v->wa, h_tabT_v->perm, h_tabT_v->a_col, h_tabT_v->a_src, h_tabT_v->r_col, h_tabT_v->r_src};
     if (!tu.r_col || !tv.r_col || !tu.r_src || !tv.r_src) { tu.r_col = tv.r_col = nullptr; }
     const long long n = (long long)batch * (tu.n + tv.n);
     h_apply_adj_kernel<<<blocks_adj(n), kThreadsAdj, 0, (cudaStream_t)stream>>>(batch, tu, tv, nnz_u, nnz_v, beta,
-                                                                                 values, a_diag, gh, gd);
+                                                                                 values, a_diag, gh, gd, base, sum);
     DPISO_CHECK_LAUNCH();
     return DPISO_OK;
 }
 
 int dpiso_predictor_rhs_adj(int batch, int ny, int nx, float dy, float dx, float beta, const uint8_t *dirichlet,
-                            const float *grhs, float *gvel, float *gforce, float *gdvals, float *gfree,
-                            void *stream) {
+                            const float *grhs, const int *solve_stats, float *gvel, float *gforce, float *gdvals,
+                            float *gfree, void *stream) {
     DPISO_REQUIRE(batch >= 1 && ny >= 3 && nx >= 3, "bad sizes");
     DPISO_REQUIRE(dirichlet && grhs && gvel && gfree, "null pointer");
     const int nf = ny * (nx + 1) + (ny + 1) * nx;
     predictor_rhs_adj_kernel<<<blocks_adj((long long)batch * nf), kThreadsAdj, 0, (cudaStream_t)stream>>>(
-        batch, nf, cell_prod_adj(dy, dx), beta, dirichlet, grhs, gvel, gforce, gdvals, gfree);
+        batch, nf, cell_prod_adj(dy, dx), beta, dirichlet, grhs, solve_stats, gvel, gforce, gdvals, gfree);
     DPISO_CHECK_LAUNCH();
     return DPISO_OK;
 }

@@ -36,7 +36,7 @@ class BicgTables(C.Structure):
                 ("perm", C.c_void_p), ("a_col", C.c_void_p), ("a_src", C.c_void_p), ("a_rev", C.c_void_p),
                 ("r_col", C.c_void_p), ("r_src", C.c_void_p), ("r_rev", C.c_void_p), ("c_lsrc", C.c_void_p),
                 ("c_lrev", C.c_void_p), ("c_usrc", C.c_void_p), ("c_lfar", C.c_void_p), ("c_ufar", C.c_void_p),
-                ("c_dsrc", C.c_void_p)]
+                ("c_dsrc", C.c_void_p), ("owner", C.c_void_p), ("owner_is_host", C.c_int), ("sym", C.c_int)]
 
 
 _I, _F, _P, _SZ = C.c_int, C.c_float, C.c_void_p, C.c_size_t
@@ -53,17 +53,24 @@ _SIGS = {
     "dpiso_h_apply": ([_I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P, _P], _I),
     "dpiso_corrector2": ([_I, _I, _I, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P], _I),
     "dpiso_fv_gradient_adj": ([_I, _I, _I, _F, _F, _P, _P, _P, _P, _F, _F, _I, _P, _P, _P], _I),
-    "dpiso_fv_divergence_adj": ([_I, _I, _I, _I, _I, _F, _F, _P, _P, _P, _F, _P, _P], _I),
-    "dpiso_h_apply_adj": ([_I, _P, _P, _I, _I, _F, _P, _P, _P, _P, _P], _I),
-    "dpiso_predictor_rhs_adj": ([_I, _I, _I, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P], _I),
+    "dpiso_fv_divergence_adj": ([_I, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _F, _P, _P], _I),
+    "dpiso_h_apply_adj": ([_I, _P, _P, _I, _I, _F, _P, _P, _P, _P, _P, _P, _P], _I),
+    "dpiso_predictor_rhs_adj": ([_I, _I, _I, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P], _I),
+    "dpiso_bicg_tables_create": ([_I, _I, _I, _I, _I, _I, _P, _P], _I),
+    "dpiso_bicg_tables_create_host": ([_I, _I, _I, _I, _I, _I, _P], _I),
+    "dpiso_bicg_tables_destroy": ([_P], _I),
     "dpiso_bicgstab_workspace_floats": ([_P, _P], _SZ),
     "dpiso_bicgstab_set_timing": ([_P], _I),
-    "dpiso_bicgstab_ilu": ([_I, _P, _P, _I, _I, _P, _P, _P, _F, _I, _P, _P, _P, _P, _P], _I),
+    "dpiso_bicgstab_set_debug": ([_I], _I),
+    "dpiso_bicgstab_set_reuse_policy": ([_I], _I),
+    "dpiso_bicgstab_supports_factor_reuse": ([_P, _P], _I),
+    "dpiso_bicgstab_ilu": ([_I, _P, _P, _I, _I, _P, _I, _P, _P, _F, _I, _P, _P, _P, _P, _P, _P, _P], _I),
     "dpiso_laplace_f64": ([_I, _I, _I, _P, _P, _P, _I, _F, _F, _P, _P], _I),
     "dpiso_laplace_f32": ([_I, _I, _I, _P, _P, _P, _I, _F, _F, _P, _P], _I),
-    "dpiso_pressure_cg_f64": ([_I, _I, _I, _I, _I, _P, _P, _F, _I, _I, _I, _P, _P, _P, _P], _I),
-    "dpiso_pressure_cg_f32": ([_I, _I, _I, _I, _I, _P, _P, _F, _I, _I, _I, _P, _P, _P, _P], _I),
-    "dpiso_pressure_cg_mixed": ([_I, _I, _I, _I, _I, _P, _P, _F, _I, _I, _I, _P, _P, _P], _I),
+    "dpiso_pressure_cg_workspace_bytes": ([_I, _I, _I, _I, _I], _SZ),
+    "dpiso_pressure_cg_f64": ([_I, _I, _I, _I, _I, _P, _P, _F, _I, _I, _I, _P, _P, _P, _P, _P], _I),
+    "dpiso_pressure_cg_f32": ([_I, _I, _I, _I, _I, _P, _P, _F, _I, _I, _I, _P, _P, _P, _P, _P], _I),
+    "dpiso_pressure_cg_mixed": ([_I, _I, _I, _I, _I, _P, _P, _F, _I, _I, _I, _P, _P, _P, _P], _I),
     "dpiso_pressure_cg_last_config": ([_P], _I),
     "dpiso_pressure_cg_set_tuning": ([_I, _I], _I),
     "dpiso_pressure_cg_set_reduction_order": ([_I], _I),

@@ -41,21 +41,26 @@ def _infer_periodic(ny, nx, nnz_total):
 class _BicgSolveFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, rhs, values, x0, solver, geom, transpose):
-        x, stats, warn = ops.bicgstab_ilu(geom, values, rhs, x0, solver.accuracy, solver.max_iterations, transpose)
+        pivots = None
+        if ctx.needs_input_grad[0] and solver.reuse_factors and ops.factor_reuse_supported(geom):
+            pivots = torch.empty_like(rhs)
+        x, stats, warn = ops.bicgstab_ilu(geom, values, rhs, x0, solver.accuracy, solver.max_iterations, transpose,
+                                          pivots_out=pivots)
         solver.last_stats = stats
-        ctx.solver, ctx.geom, ctx.transpose = solver, geom, transpose
-        ctx.save_for_backward(values, x0)
-        warn_f = warn.to(torch.float32)
-        ctx.mark_non_differentiable(warn_f)
-        return x, warn_f
+        ctx.solver, ctx.geom, ctx.transpose, ctx.has_pivots = solver, geom, transpose, pivots is not None
+        ctx.save_for_backward(*([values, x0] + ([pivots] if pivots is not None else [])))
+        ctx.mark_non_differentiable(warn)
+        return x, warn
 
     @staticmethod
     def backward(ctx, gx, gwarn):
-        values, x0 = ctx.saved_tensors
+        saved = ctx.saved_tensors
+        values, x0 = saved[0], saved[1]
         solver = ctx.solver
-        # linear_solver.py:169-173: same op on ds with `not transpose`, same initial-guess tensor, times (1 - warn)
+        # linear_solver.py:169-173: same op on ds with `not transpose`, same initial-guess tensor, times (1 - warn);
+        # the ILU(0) pivots of the forward solve are reused where that is exact (structurally symmetric components)
         df, stats, warn = ops.bicgstab_ilu(ctx.geom, values, gx.contiguous(), x0, solver.accuracy, solver.max_iterations,
-                                           not ctx.transpose)
+                                           not ctx.transpose, pivots_in=saved[2] if ctx.has_pivots else None)
         solver.last_adjoint_stats = stats
         # per-sample NaN guard (stats[:, :, 2]); the batch-wide OR is only the returned `warn` value
         keep = 1.0 - stats[:, :, 2].amax(dim=1, keepdim=True).to(torch.float32)
@@ -67,7 +72,7 @@ class LinearSolverCudaMultiBicgstabILU(LinearSolver):
 
     _dpiso_native = True
 
-    def __init__(self, accuracy=1e-5, max_iterations=2000, cast_to_double=False):
+    def __init__(self, accuracy=1e-5, max_iterations=2000, cast_to_double=False, reuse_factors=True):
         LinearSolver.__init__(self, 'CUDA dual iLU-preconditioned BiCGStab solve', supported_devices=('GPU',),
                               supports_guess=True, supports_batch=True, solver_type='iterative', input_format='csr')
         if cast_to_double:
@@ -75,8 +80,24 @@ class LinearSolverCudaMultiBicgstabILU(LinearSolver):
         self.max_iterations = int(max_iterations)
         self.cast_to_double = False
         self.accuracy = float(accuracy)
+        # adjoint solves take the forward ILU(0) pivots instead of factorising A^T again, per component and only where
+        # that is the reference's preconditioner up to rounding (structurally symmetric pattern); components
+        # that are periodic along their staggered axis (Q18) always re-factorise like the reference
+        self.reuse_factors = bool(reuse_factors)
         self.last_stats = None
         self.last_adjoint_stats = None
+
+    def solve_native(self, geom, values, rhs, x0, transpose, negate=False, pivots_out=None, pivots_in=None,
+                     adjoint=False):
+        """The solve without autograd bookkeeping, for callers that own forward and backward themselves (piso_step):
+        -> (x, warn float32 [1], stats int32 [B, 2, 4])."""
+        x, stats, warn = ops.bicgstab_ilu(geom, values, rhs, x0, self.accuracy, self.max_iterations, transpose,
+                                          negate=negate, pivots_out=pivots_out, pivots_in=pivots_in)
+        if adjoint:
+            self.last_adjoint_stats = stats
+        else:
+            self.last_stats = stats
+        return x, warn, stats
 
     def solve(self, matrix_values, row_ptr, col_indices, rhs, staggered_shape, initial_guess=None, offset=0,
               transpose=False, unrolling_step=0, warn=None, structure=None):

@@ -23,6 +23,7 @@ class Geometry(object):
         self.n_u, self.n_v, self.nnz_u, self.nnz_v = S.sizes(self.ny, self.nx, self.per_x, self.per_y)
         self.nf, self.nc, self.nnz = self.n_u + self.n_v, self.ny * self.nx, self.nnz_u + self.nnz_v
         self._tables = {}
+        self._scratch = {}
         self._csr = None
 
     @classmethod
@@ -41,23 +42,24 @@ class Geometry(object):
     def _tables_impl(self, transpose):
         t = self._tables.get(bool(transpose))
         if t is None:
-            structs, keep = [], []
+            structs = []
             for comp in (0, 1):
-                h = S.bicg_tables(self.ny, self.nx, self.per_x, self.per_y, comp, bool(transpose))
-                dev = {k: torch.from_numpy(h[k]).to(self.device)
-                       for k in ("level_ptr", "perm", "a_col", "a_src", "a_rev", "r_col", "r_src", "r_rev", "c_lsrc", "c_lrev",
-                                 "c_usrc", "c_lfar", "c_ufar", "c_dsrc")}
-                st = N.BicgTables(h["n"], h["n_levels"], h["wa"], h["max_level"], h["wl"], h["wu"], h["dx"], h["rows_ok"],
-                                  dev["level_ptr"].data_ptr(),
-                                  dev["perm"].data_ptr(), dev["a_col"].data_ptr(), dev["a_src"].data_ptr(),
-                                  dev["a_rev"].data_ptr(), dev["r_col"].data_ptr(), dev["r_src"].data_ptr(),
-                                  dev["r_rev"].data_ptr(), dev["c_lsrc"].data_ptr(), dev["c_lrev"].data_ptr(),
-                                  dev["c_usrc"].data_ptr(), dev["c_lfar"].data_ptr(), dev["c_ufar"].data_ptr(),
-                                  dev["c_dsrc"].data_ptr())
+                st = N.BicgTables()
+                # built on the host by the library itself (csrc/tables.cu) and uploaded once per grid and device
+                N.check(N.lib.dpiso_bicg_tables_create(self.ny, self.nx, int(self.per_x), int(self.per_y), comp,
+                                                       int(bool(transpose)), C.byref(st), N.stream()),
+                        "dpiso_bicg_tables_create")
                 structs.append(st)
-                keep.append(dev)
-            t = self._tables[bool(transpose)] = (structs[0], structs[1], keep)
+            t = self._tables[bool(transpose)] = (structs[0], structs[1])
         return t[0], t[1]
+
+    def scratch(self, key, nbytes):
+        """Per-grid scratch buffer (uint8) reused by successive calls on the same stream; `key` names the consumer."""
+        k = (key, torch.cuda.current_stream(self.device).cuda_stream)
+        buf = self._scratch.get(k)
+        if buf is None or buf.numel() < nbytes:
+            buf = self._scratch[k] = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        return buf
 
     def csr_structure(self):
         """(row_ptr, col_ind) int32 device tensors in the reference layout, from the device kernel."""
@@ -216,56 +218,71 @@ def fv_gradient_adj(g, gs, access, dy, dx, pbc, a_diag=None, beta=0.0, divisor=1
 
 
 @_on_device_of(0)
-def fv_divergence_adj(g, gc, dy, dx, base=None, a_diag=None, beta=0.0):
+def fv_divergence_adj(g, gc, dy, dx, base=None, a_diag=None, beta=0.0, base_sub=None):
+    """([base [- base_sub]] + D^T gc) [/ (beta - a_diag)]"""
     gc = _f32(gc)
     b = gc.shape[0]
     out = torch.empty((b, g.nf), dtype=torch.float32, device=gc.device)
     N.check(N.lib.dpiso_fv_divergence_adj(b, g.ny, g.nx, int(g.per_x), int(g.per_y), dy, dx, N.ptr(gc),
-                                          N.ptr(None if base is None else _f32(base)), N.ptr(a_diag), beta, N.ptr(out),
-                                          N.stream()), "dpiso_fv_divergence_adj")
+                                          N.ptr(None if base is None else _f32(base)),
+                                          N.ptr(None if base_sub is None else _f32(base_sub)), N.ptr(a_diag), beta,
+                                          N.ptr(out), N.stream()), "dpiso_fv_divergence_adj")
     return out
 
 
 @_on_device_of(0)
-def h_apply_adj(g, values, a_diag, gh, beta):
+def h_apply_adj(g, values, a_diag, gh, beta, base=None):
+    """gd = M_off^T gh; with `base` also returns base + gd (one pass)."""
     gh = _f32(gh)
     tu, tv = g.tables(True)
     out = torch.empty_like(gh)
+    total = None if base is None else torch.empty_like(gh)
     N.check(N.lib.dpiso_h_apply_adj(gh.shape[0], C.byref(tu), C.byref(tv), g.nnz_u, g.nnz_v, beta, N.ptr(values),
-                                    N.ptr(a_diag), N.ptr(gh), N.ptr(out), N.stream()), "dpiso_h_apply_adj")
-    return out
+                                    N.ptr(a_diag), N.ptr(gh), N.ptr(out), N.ptr(None if base is None else _f32(base)),
+                                    N.ptr(total), N.stream()), "dpiso_h_apply_adj")
+    return out if base is None else (out, total)
 
 
 @_on_device_of(0)
-def predictor_rhs_adj(g, grhs, dirichlet_u8, dy, dx, beta, want_force, want_dvals):
+def predictor_rhs_adj(g, grhs, dirichlet_u8, dy, dx, beta, want_force, want_dvals, solve_stats=None):
+    """solve_stats: int32 [B, 2, 4] of the transposed predictor solve that produced grhs -> samples whose solve raised the
+    NaN warning contribute nothing (linear_solver.py:169-173, sample by sample)."""
     grhs = _f32(grhs)
     b = grhs.shape[0]
     gvel = torch.empty_like(grhs)
     gfree = torch.empty_like(grhs)
     gforce = torch.empty_like(grhs) if want_force else None
     gdvals = torch.empty_like(grhs) if want_dvals else None
-    N.check(N.lib.dpiso_predictor_rhs_adj(b, g.ny, g.nx, dy, dx, beta, N.ptr(dirichlet_u8), N.ptr(grhs), N.ptr(gvel),
-                                          N.ptr(gforce), N.ptr(gdvals), N.ptr(gfree), N.stream()),
+    N.check(N.lib.dpiso_predictor_rhs_adj(b, g.ny, g.nx, dy, dx, beta, N.ptr(dirichlet_u8), N.ptr(grhs),
+                                          N.ptr(solve_stats), N.ptr(gvel), N.ptr(gforce), N.ptr(gdvals), N.ptr(gfree),
+                                          N.stream()),
             "dpiso_predictor_rhs_adj")
     return gvel, gforce, gdvals, gfree
 
 
 @_on_device_of(0)
-def bicgstab_ilu(g, values, rhs, x0, tol, max_it, transpose=False, warn=None):
-    """-> x [B, nf], stats int32 [B, 2, 4] (iterations, restarts, warn, exit kind), warn uint8 [1]"""
+def bicgstab_ilu(g, values, rhs, x0, tol, max_it, transpose=False, negate=False, pivots_out=None, pivots_in=None):
+    """-> x [B, nf], stats int32 [B, 2, 4] (iterations, restarts, warn, exit kind), warn float32 [1].
+    Solves (values or, with negate, -values) x = rhs.  pivots_out / pivots_in [B, nf] float32: ILU(0) pivots written by /
+    taken from the solve of the other orientation (factor reuse; honoured where `factor_reuse_supported`)."""
     values, rhs, x0 = _f32(values), _f32(rhs), _f32(x0)
     b = rhs.shape[0]
     tu, tv = g.tables(transpose)
     ws_floats = N.lib.dpiso_bicgstab_workspace_floats(C.byref(tu), C.byref(tv))
-    ws = torch.empty(b * 2 * ws_floats, dtype=torch.float32, device=rhs.device)
+    ws = g.scratch("bicgstab", b * 2 * ws_floats * 4)
     x = torch.empty_like(rhs)
-    stats = torch.zeros((b, 2, 4), dtype=torch.int32, device=rhs.device)
-    if warn is None:
-        warn = torch.zeros(1, dtype=torch.uint8, device=rhs.device)
-    N.check(N.lib.dpiso_bicgstab_ilu(b, C.byref(tu), C.byref(tv), g.nnz_u, g.nnz_v, N.ptr(values), N.ptr(rhs), N.ptr(x0),
-                                     float(tol), int(max_it), N.ptr(x), N.ptr(stats), N.ptr(warn), N.ptr(ws), N.stream()),
-            "dpiso_bicgstab_ilu")
+    stats = torch.empty((b, 2, 4), dtype=torch.int32, device=rhs.device)
+    warn = torch.empty(1, dtype=torch.float32, device=rhs.device)
+    N.check(N.lib.dpiso_bicgstab_ilu(b, C.byref(tu), C.byref(tv), g.nnz_u, g.nnz_v, N.ptr(values), int(bool(negate)),
+                                     N.ptr(rhs), N.ptr(x0), float(tol), int(max_it), N.ptr(x), N.ptr(stats), N.ptr(warn),
+                                     N.ptr(pivots_out), N.ptr(pivots_in), N.ptr(ws), N.stream()), "dpiso_bicgstab_ilu")
     return x, stats, warn
+
+
+def factor_reuse_supported(g):
+    """True when the predictor kernel of this grid can write / take ILU(0) pivots (the row-major kernel)."""
+    tu, tv = g.tables(False)
+    return bool(N.lib.dpiso_bicgstab_supports_factor_reuse(C.byref(tu), C.byref(tv)))
 
 
 @_on_device_of(0)
@@ -287,15 +304,18 @@ def pressure_cg(g, lap, div, accuracy, max_it, residual_reset, rank_deficient):
     b = div.shape[0]
     div = _f32(div).reshape(b, g.nc)
     x32 = torch.empty((b, g.nc), dtype=torch.float32, device=div.device)
-    its = torch.zeros(b, dtype=torch.int32, device=div.device)
-    if lap.dtype == torch.float64:
+    its = torch.empty(b, dtype=torch.int32, device=div.device)
+    fp64 = lap.dtype == torch.float64
+    ws_bytes = N.lib.dpiso_pressure_cg_workspace_bytes(b, g.ny, g.nx, 8 if fp64 else 4, 0 if fp64 else 1)
+    ws = g.scratch("pressure_cg", ws_bytes) if ws_bytes else None    # only grids whose state does not fit on chip
+    if fp64:
         rc = N.lib.dpiso_pressure_cg_mixed(b, g.ny, g.nx, int(g.per_x), int(g.per_y), N.ptr(lap), N.ptr(div),
                                            float(accuracy), int(max_it), int(residual_reset), int(rank_deficient),
-                                           N.ptr(x32), N.ptr(its), N.stream())
+                                           N.ptr(x32), N.ptr(its), N.ptr(ws), N.stream())
     else:
         rc = N.lib.dpiso_pressure_cg_f32(b, g.ny, g.nx, int(g.per_x), int(g.per_y), N.ptr(lap), N.ptr(div),
                                          float(accuracy), int(max_it), int(residual_reset), int(rank_deficient),
-                                         N.ptr(x32), None, N.ptr(its), N.stream())
+                                         N.ptr(x32), None, N.ptr(its), N.ptr(ws), N.stream())
     N.check(rc, "dpiso_pressure_cg")
     return x32, its
 

@@ -49,14 +49,19 @@ class _Ctx(object):
     __slots__ = ("g", "m", "dy", "dx", "areas", "beta", "prod", "dx_factor", "pbc", "pbc_inc", "sim", "unrolling_step")
 
 
-def _linear_solve(c, values_neg, rhs, x0, transpose, unrolling_step):
+def _linear_solve(c, values, rhs, x0, transpose, unrolling_step, pivots_out=None, pivots_in=None):
+    """(-M) x = rhs through the linear_solver plug-in (piso_tf.py:42-43) -> (x, warn, stats | None).  `values` is the
+    assembled M; the native solver negates on the fly, a foreign plug-in receives the materialised -M like the
+    reference's."""
     ls = c.sim.linear_solver
-    shape = (rhs.shape[0], c.g.ny + 1, c.g.nx + 1, 2)
     if getattr(ls, "_dpiso_native", False):
-        return ls.solve(values_neg, None, None, rhs, shape, x0, offset=1, transpose=transpose,
-                        unrolling_step=unrolling_step, structure=c.g)
+        return ls.solve_native(c.g, values, rhs, x0, transpose, negate=True, pivots_out=pivots_out, pivots_in=pivots_in,
+                               adjoint=transpose)
+    shape = (rhs.shape[0], c.g.ny + 1, c.g.nx + 1, 2)
     rp, ci = c.g.csr_structure()
-    return ls.solve(values_neg, rp, ci, rhs, shape, x0, offset=1, transpose=transpose, unrolling_step=unrolling_step)
+    x, warn = ls.solve(torch.neg(values), rp, ci, rhs, shape, x0, offset=1, transpose=transpose,
+                       unrolling_step=unrolling_step)
+    return x, warn, None
 
 
 def _pressure_solve(c, a_diag, div, unrolling_step, scaling=None):
@@ -75,22 +80,27 @@ def _pressure_solve(c, a_diag, div, unrolling_step, scaling=None):
 
 class _PisoStepFn(torch.autograd.Function):
     """One PISO step on flat tensors: (vel [B,nf], pres [B,nc], dvals [1|B,nf], forcing [B,nf]|None, visc) ->
-    (vel_next, pres_next, p1, p2, warn, extras...)."""
+    (vel_next, pres_next, p1, p2, warn, extras...).  With the native solver plug-ins, forward and backward enqueue native
+    kernels only (no torch arithmetic in between): the whole pass is CUDA-graph capturable."""
 
     @staticmethod
     def forward(ctx, vel, pres, dvals, forcing, visc, c):
         g, m = c.g, c.m
         vel, pres = vel.contiguous(), pres.contiguous()
+        native_ls = getattr(c.sim.linear_solver, "_dpiso_native", False)
+        native_ps = getattr(c.sim.pressure_solver, "_dpiso_native", False)
+        needs_bwd = any(ctx.needs_input_grad[:4])
         # advection matrices (piso_tf.py:29-33)
         values, a_diag = ops.assemble(g, vel, m["dirichlet"], m["active"], m["noslip"], visc, c.dy, c.dx, c.beta, c.areas)
-        # predictor (piso_tf.py:36-47)
+        # predictor (piso_tf.py:36-47); the forward ILU(0) pivots are kept for the adjoint solve (factor reuse)
         rhs = ops.predictor_rhs(g, vel, pres, m["access"], m["dirichlet"], dvals, forcing, c.dy, c.dx, c.beta, c.pbc)
-        values_neg = torch.neg(values)
-        u_star, warn = _linear_solve(c, values_neg, rhs, vel, False, c.unrolling_step)
+        pivots = None
+        if native_ls and needs_bwd and c.sim.linear_solver.reuse_factors and ops.factor_reuse_supported(g):
+            pivots = torch.empty_like(vel)
+        u_star, warn, _ = _linear_solve(c, values, rhs, vel, False, c.unrolling_step, pivots_out=pivots)
         u_star = u_star.contiguous()
         # corrector 1 (piso_tf.py:51-58)
         div1 = ops.fv_divergence(g, u_star, c.dy, c.dx)
-        native_ps = getattr(c.sim.pressure_solver, "_dpiso_native", False)
         scaling = ScalingFromDiagonal(a_diag, c.beta, c.dx_factor) if native_ps else None   # both solves share the matrix
         p1, its1, lap1 = _pressure_solve(c, a_diag, div1, c.unrolling_step, scaling)
         u_s2 = ops.corrector1(g, u_star, p1, a_diag, m["access"], c.dy, c.dx, c.beta, c.pbc_inc)
@@ -103,7 +113,14 @@ class _PisoStepFn(torch.autograd.Function):
         ctx.set_materialize_grads(False)        # no zero-filled gradients for the 15 non-differentiable extras
         ctx.has_forcing = forcing is not None
         ctx.dvals_batched = dvals.shape[0] == vel.shape[0]
-        ctx.save_for_backward(values, values_neg, a_diag, vel)
+        ctx.has_pivots = pivots is not None
+        ctx.lap_dtype = lap1.dtype if native_ps else None
+        saved = [values, a_diag, vel]
+        if pivots is not None:
+            saved.append(pivots)
+        if native_ps:
+            saved.append(lap1)                  # the adjoint's two pressure solves use the same matrix
+        ctx.save_for_backward(*saved)
         extras = (p1, p2, warn, values, a_diag, rhs, u_star, u_s2, h, div1, div2, lap1, lap2, its1, its2)
         ctx.mark_non_differentiable(*extras)
         return (vel_next, pres_next) + extras
@@ -112,32 +129,39 @@ class _PisoStepFn(torch.autograd.Function):
     def backward(ctx, g_vel, g_pres, *unused):
         c = ctx.c
         g, m = c.g, c.m
-        values, values_neg, a_diag, vel = ctx.saved_tensors
+        saved = list(ctx.saved_tensors)
+        values, a_diag, vel = saved[:3]
+        pivots = saved[3] if ctx.has_pivots else None
         b = vel.shape[0]
         g_vel = torch.zeros_like(vel) if g_vel is None else g_vel.contiguous()
         g_pres = torch.zeros((b, g.nc), dtype=torch.float32, device=vel.device) if g_pres is None else g_pres.contiguous()
+        native_ps = ctx.lap_dtype is not None
+        scaling = None
+        if native_ps:
+            scaling = ScalingFromDiagonal(a_diag, c.beta, c.dx_factor)
+            scaling._lap[ctx.lap_dtype == torch.float64] = saved[-1].reshape(b, g.nc, 5)
         # p_next = p + p1 + p2 ; u_next = u** + (h - G(p2)/prod)/(beta-A)
         p2_bar = ops.fv_gradient_adj(g, g_vel, m["access"], c.dy, c.dx, c.pbc_inc, a_diag=a_diag, beta=c.beta,
                                      divisor=c.prod, negate=True, base=g_pres)
-        native_ps = getattr(c.sim.pressure_solver, "_dpiso_native", False)
-        scaling = ScalingFromDiagonal(a_diag, c.beta, c.dx_factor) if native_ps else None
         d2_bar, _, _ = _pressure_solve(c, a_diag, p2_bar, 1100 + c.unrolling_step, scaling)
         # h_bar = (g_vel + D^T d2_bar) / (beta - A)
         h_bar = ops.fv_divergence_adj(g, d2_bar, c.dy, c.dx, base=g_vel, a_diag=a_diag, beta=c.beta)
-        delta_bar = ops.h_apply_adj(g, values, a_diag, h_bar, c.beta)
-        us2_bar = g_vel + delta_bar
+        # delta_bar = H^T h_bar ; u**_bar = g_vel + delta_bar (same pass)
+        delta_bar, us2_bar = ops.h_apply_adj(g, values, a_diag, h_bar, c.beta, base=g_vel)
         # u** = u* - G(p1)/(beta-A)/prod
         p1_bar = ops.fv_gradient_adj(g, us2_bar, m["access"], c.dy, c.dx, c.pbc_inc, a_diag=a_diag, beta=c.beta,
                                      divisor=c.prod, negate=True, base=g_pres)
         d1_bar, _, _ = _pressure_solve(c, a_diag, p1_bar, 100 + c.unrolling_step, scaling)
         # u*_bar = (us2_bar - delta_bar) + D^T d1_bar
-        ustar_bar = ops.fv_divergence_adj(g, d1_bar, c.dy, c.dx, base=us2_bar - delta_bar)
+        ustar_bar = ops.fv_divergence_adj(g, d1_bar, c.dy, c.dx, base=us2_bar, base_sub=delta_bar)
         # predictor: transposed solve, same initial-guess tensor as forward, times (1 - warn) (linear_solver.py:169-173)
-        rhs_bar, warn_b = _linear_solve(c, values_neg, ustar_bar, vel, True, 100 + c.unrolling_step)
-        rhs_bar = rhs_bar * (1.0 - warn_b)
+        rhs_bar, warn_b, stats_b = _linear_solve(c, values, ustar_bar, vel, True, 100 + c.unrolling_step, pivots_in=pivots)
+        if stats_b is None:                     # foreign plug-in: batch-wide warning scalar, as the reference applies it
+            rhs_bar = (rhs_bar * (1.0 - warn_b)).contiguous()
         need_dv = ctx.needs_input_grad[2]
-        gvel_in, gforce, gdvals, gfree = ops.predictor_rhs_adj(g, rhs_bar.contiguous(), m["dirichlet"], c.dy, c.dx, c.beta,
-                                                               ctx.has_forcing and ctx.needs_input_grad[3], need_dv)
+        gvel_in, gforce, gdvals, gfree = ops.predictor_rhs_adj(g, rhs_bar, m["dirichlet"], c.dy, c.dx, c.beta,
+                                                               ctx.has_forcing and ctx.needs_input_grad[3], need_dv,
+                                                               solve_stats=stats_b)
         gpres_in = ops.fv_gradient_adj(g, gfree, m["access"], c.dy, c.dx, c.pbc, negate=True, base=g_pres)
         if need_dv and not ctx.dvals_batched:
             gdvals = gdvals.sum(0, keepdim=True)

@@ -101,18 +101,22 @@ int dpiso_corrector2(int batch, int ny, int nx, float dy, float dx, float beta, 
 int dpiso_fv_gradient_adj(int batch, int ny, int nx, float dy, float dx, const int *h_pbc, const float *access,
                           const float *gs, const float *a_diag, float beta, float divisor, int negate,
                           const float *base, float *gp, void *stream);
-/* gv = ([base] + D^T gc) [/(beta - a_diag)]: registered gradient of finite_volume_divergence
- * (piso_helpers.py:291-305).  base [batch][nf] and a_diag may be NULL. */
+/* gv = ([base [- base_sub]] + D^T gc) [/(beta - a_diag)]: registered gradient of finite_volume_divergence
+ * (piso_helpers.py:291-305).  base, base_sub [batch][nf] and a_diag may be NULL (base_sub needs base). */
 int dpiso_fv_divergence_adj(int batch, int ny, int nx, int per_x, int per_y, float dy, float dx, const float *gc,
-                            const float *base, const float *a_diag, float beta, float *gv, void *stream);
+                            const float *base, const float *base_sub, const float *a_diag, float beta, float *gv,
+                            void *stream);
 /* gfree = (1-m) grhs, gvel = gfree*beta, gforce = gfree*dx*dy, gdvals = -m grhs  (m = Dirichlet mask): adjoint of the
- * rhs assembly (piso_tf.py:36-40); gforce / gdvals may be NULL.  The pressure part is -G^T(gfree). */
+ * rhs assembly (piso_tf.py:36-40); gforce / gdvals may be NULL.  The pressure part is -G^T(gfree).
+ * solve_stats (optional): the stats [batch][2][4] of the transposed predictor solve that produced grhs; samples whose
+ * solve raised the NaN warning get grhs * (1 - warn) = 0 (linear_solver.py:169-173), sample by sample. */
 int dpiso_predictor_rhs_adj(int batch, int ny, int nx, float dy, float dx, float beta, const uint8_t *dirichlet,
-                            const float *grhs, float *gvel, float *gforce, float *gdvals, float *gfree, void *stream);
+                            const float *grhs, const int *solve_stats, float *gvel, float *gforce, float *gdvals,
+                            float *gfree, void *stream);
 
 /* ---- ILU0-preconditioned BiCGStab, batched over samples and the two components --------------------
- * Structure tables are built on the host by the caller (diffpiso_b200/structure.py) from the CSR pattern and
- * uploaded once (all pointers inside dpiso_bicg_tables are DEVICE pointers; the struct itself lives on the host).
+ * Structure tables are built once per grid by dpiso_bicg_tables_create (below) -- or by the caller -- and stay on the
+ * device (all pointers inside dpiso_bicg_tables are DEVICE pointers; the struct itself lives on the host).
  * M = A for the forward solve, M = A^T for the adjoint solve -- only the tables differ.
  * One persistent CTA per (sample, component) system. */
 typedef struct {
@@ -140,24 +144,60 @@ typedef struct {
     const int *c_lfar;    /* int[n][2] column of the two far lower slots, -1 = absent */
     const int *c_ufar;    /* int[n][2] column of the two far upper slots */
     const int *c_dsrc;    /* int[n]    CSR value index of the diagonal entry */
+    void *owner;          /* allocation behind the arrays when built by dpiso_bicg_tables_create*, else NULL */
+    int owner_is_host;    /* 1: `owner` is host memory (dpiso_bicg_tables_create_host) */
+    int sym;              /* 1: the pattern is structurally symmetric (every entry has its reverse entry): ILU(0)(M^T)
+                             is then exactly the transposed ILU(0)(M) and factor reuse is equivalent;
+                             0 for components that are periodic along their staggered axis */
 } dpiso_bicg_tables;
 
-/* gd = M^T gh - (A - beta) gh: adjoint of dpiso_h_apply w.r.t. (u** - u*); takes the tables of M = A^T */
+/* Builds the tables of one component (comp 0 = u, 1 = v) for M = A (transpose 0) or M = A^T (transpose 1) from the
+ * grid alone and uploads them to the current device (one allocation, stream-ordered copy).  The reference launcher
+ * takes just the CSR arrays and transpose_op (multi_bicgstab_ilu_linear_solve_op.cc:50-58) and re-analyses the pattern
+ * with cuSPARSE on every call (.cu.cc:113-134, 181-228); here the analysis is done once per grid.  Returns
+ * DPISO_EUNSUPPORTED when lx+ly is not a valid level schedule or ILU(0) would interact with fill on this grid.
+ * dpiso_bicg_tables_create_host builds the same tables in host memory (tests, inspection). */
+int dpiso_bicg_tables_create(int ny, int nx, int per_x, int per_y, int comp, int transpose, dpiso_bicg_tables *out,
+                             void *stream);
+int dpiso_bicg_tables_create_host(int ny, int nx, int per_x, int per_y, int comp, int transpose, dpiso_bicg_tables *out);
+int dpiso_bicg_tables_destroy(dpiso_bicg_tables *tab);
+
+/* gd = M^T gh - (A - beta) gh: adjoint of dpiso_h_apply w.r.t. (u** - u*); takes the tables of M = A^T.
+ * sum (optional, may be NULL): sum = base + gd, the accumulated gradient of u** (base [batch][nf] required then) */
 int dpiso_h_apply_adj(int batch, const dpiso_bicg_tables *h_tabT_u, const dpiso_bicg_tables *h_tabT_v, int nnz_u,
                       int nnz_v, float beta, const float *values, const float *a_diag, const float *gh, float *gd,
-                      void *stream);
+                      const float *base, float *sum, void *stream);
 
 /* workspace (floats) needed per (sample, component) system for the given tables */
 size_t dpiso_bicgstab_workspace_floats(const dpiso_bicg_tables *h_tab_u, const dpiso_bicg_tables *h_tab_v);
 
-/* Solves values*x = rhs for every sample and both components (values already carry the sign the caller wants).
+/* Solves (sign * values) x = rhs for every sample and both components; negate != 0 means sign = -1, i.e. the caller
+ * passes the assembled M and the solve runs on -M as piso_tf.py:42 does, without materialising the negated copy.
  * values [batch][nnz_u+nnz_v] (nnz_* = CSR entries of the NON-transposed pattern; transposition is expressed by
- * the tables), rhs/x0/x [batch][n_u+n_v].  stats int [batch][2][4] = iterations, restarts, warn, exit kind;
- * warn uint8 [1] is OR-ed with any NaN-norm warning (multi_bicgstab...cu.cc:251-256).
- * workspace: float [batch*2*dpiso_bicgstab_workspace_floats()]. */
+ * the tables), rhs/x0/x [batch][n_u+n_v].  stats int [batch][2][4] = iterations, restarts, warn, exit kind (every
+ * entry is written).  warn float [1]: reset to 0 by the call, set to 1 by any NaN-norm warning
+ * (multi_bicgstab...cu.cc:251-256; the float the Python class returns, linear_solver.py:175).
+ * workspace: float [batch*2*dpiso_bicgstab_workspace_floats()], caller-owned, contents undefined afterwards.
+ * Factor reuse (north_star: "the adjoint solves reuse the forward factorisation"):
+ *   pivots_out (optional) [batch][n_u+n_v]: receives the ILU(0) pivots u_ii of this solve;
+ *   pivots_in  (optional) [batch][n_u+n_v]: pivots of the solve with the OTHER orientation of the same matrices.  The
+ *   wavefront factorisation is skipped: ILU(0)(M^T) = (U^T D^-1)(D L^T), i.e. l'_ik = m_ik / d_k, upper entries
+ *   unchanged.  Exact (to rounding) for structurally symmetric patterns; for components that are
+ *   periodic along their staggered axis it is a different -- still valid -- preconditioner.
+ *   By default pivots_in is honoured per component only where the tables say `sym` (exact reuse); the other
+ *   component factorises as usual.  dpiso_bicgstab_set_reuse_policy(1) extends it to every component.
+ * Both need dpiso_bicgstab_supports_factor_reuse() != 0 (the row-major kernel); otherwise they are ignored /
+ * left untouched and the solve factorises as usual. */
 int dpiso_bicgstab_ilu(int batch, const dpiso_bicg_tables *h_tab_u, const dpiso_bicg_tables *h_tab_v, int nnz_u,
-                       int nnz_v, const float *values, const float *rhs, const float *x0, float tol, int max_it,
-                       float *x, int *stats, uint8_t *warn, float *workspace, void *stream);
+                       int nnz_v, const float *values, int negate, const float *rhs, const float *x0, float tol,
+                       int max_it, float *x, int *stats, float *warn, float *pivots_out, const float *pivots_in,
+                       float *workspace, void *stream);
+int dpiso_bicgstab_supports_factor_reuse(const dpiso_bicg_tables *h_tab_u, const dpiso_bicg_tables *h_tab_v);
+/* profiling / test switch: dbg >= 0 overrides the DPISO_BICG_DBG environment variable (8 forces the level-major
+ * kernel), -1 restores it */
+int dpiso_bicgstab_set_debug(int dbg);
+/* 0 (default): reuse pivots only for structurally symmetric components; 1: for every component */
+int dpiso_bicgstab_set_reuse_policy(int always);
 
 /* profiling hook: dev_counters = device buffer of 8 int64 SM-cycle counters accumulated by system 0 of every following
  * solve ([0] setup, [1] ILU(0), [2] triangular sweeps, [4] SpMV / vector phases); NULL disables */
@@ -177,17 +217,22 @@ int dpiso_laplace_f32(int batch, int ny, int nx, const float *active, const floa
  * reference's B=1 control flow (check cadence, residual resets) on its own.
  * lap [batch][n_c][5], div [batch][n_c], x [batch][n_c] (output, T), iterations int [batch].
  * x32 (optional, may be NULL): float copy of x (the reference casts the result to fp32). */
+/* workspace: grids whose state fits on chip (BASELINE configs 1-4) need none; larger grids keep p, r, z (and x when
+ * the caller passes no T-typed x) in a caller-owned scratch of dpiso_pressure_cg_workspace_bytes() bytes (0 = none
+ * needed; `elem_size` 8 = fp64 / mixed, 4 = fp32; `have_x` = the caller passes a T-typed x).  Nothing is allocated
+ * inside the calls. */
+size_t dpiso_pressure_cg_workspace_bytes(int batch, int ny, int nx, int elem_size, int have_x);
 int dpiso_pressure_cg_f64(int batch, int ny, int nx, int per_x, int per_y, const double *lap, const double *div,
                           float accuracy, int max_it, int residual_reset, int rank_deficient, double *x,
-                          float *x32, int *iterations, void *stream);
+                          float *x32, int *iterations, void *workspace, void *stream);
 int dpiso_pressure_cg_f32(int batch, int ny, int nx, int per_x, int per_y, const float *lap, const float *div,
                           float accuracy, int max_it, int residual_reset, int rank_deficient, float *x,
-                          float *x32, int *iterations, void *stream);
+                          float *x32, int *iterations, void *workspace, void *stream);
 /* fp32 divergence in, fp64 solve, fp32 pressure out: the cast_to_double=True path of
  * PisoPressureSolverCudaCustom.solve (piso_cuda_pressure_solver.py:55-58,111) without materialising the casts */
 int dpiso_pressure_cg_mixed(int batch, int ny, int nx, int per_x, int per_y, const double *lap, const float *div32,
                             float accuracy, int max_it, int residual_reset, int rank_deficient, float *x32,
-                            int *iterations, void *stream);
+                            int *iterations, void *workspace, void *stream);
 
 /* launch-configuration report for the last pressure CG call on this thread: h_out[0]=cluster size,
  * [1]=threads per CTA, [2]=cells per thread, [3]=dynamic smem bytes, [4]=kernel variant */

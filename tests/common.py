@@ -102,11 +102,33 @@ def cg_residual_inf(setup, lap, x, b):
 
 
 def cg_iteration_slack(setup, oracle_iterations):
-    """Allowed |GPU - oracle| pressure-CG iteration difference.  Counts are quantised to the 5-iteration check cadence
-     and the stopping test sits on a slowly decaying L-inf residual, so re-associated reductions move them by
-    a few quanta.  With residual_reset = 10 the method is CG restarted every 10 iterations, whose count is far more
-    rounding sensitive (an fp64 numpy transcription of the same loop differs from the C oracle by 10-20 % there; the
-    kernel, which merges the inner products of an iteration into one reduction, by up to ~58 % -- in either direction)."""
+    """Allowed |GPU - oracle| pressure-CG iteration difference = the worst deviation MEASURED on B200 for the reference's
+    own kernels against the oracle plus one quantum (profiles/r02_parity.md, 14 setups x 3 samples).  Counts are
+    quantised to the 5-iteration check cadence and the stopping test sits on a slowly decaying L-inf
+    residual, so any re-association of the dot products (cuBLAS in the reference, warp/cluster trees here, sequential
+    sums in the oracle) moves them by a few quanta:
+      residual_reset 1000: reference kernels up to 25, this kernel up to 30 (merged reduction) / 25 (two reductions)
+                           -> 25 + 5 = 30;
+      residual_reset 10:   CG restarted every 10 iterations is far more rounding sensitive: the reference kernels
+                           differ from the oracle by up to 20, this kernel by up to 200 on counts of 400-700 in EITHER
+                           reduction order (so the merged reduction, deviation D2, is not the cause) -> 45 % of the count.
+    north_star's +-1 is met by the BiCGStab counts (0 over 144 solves); for the CG it is not attainable against a
+    reference whose own count moves by 5-25 with the summation order (and by +935 when a check lands on the wrong side
+    of the threshold just before the reset window closes, test_gpu_reference_pin)."""
     if setup["cg_reset"] <= 10:
-        return max(20, 0.6 * oracle_iterations)
-    return max(15, 0.12 * oracle_iterations)
+        return max(20, 0.45 * oracle_iterations)
+    return 30
+
+
+def field_tolerances(setup):
+    """Relative-L2 bounds (velocity, pressure, pressure increment, gradients) asserted against the oracle: north_star's
+    1e-5 where it is attainable, else 2x the worst case measured on B200 (profiles/r02_parity.md) with the reason:
+      * solvers at 1e-8 (paper setting): velocity, pressure and gradients <= 1e-5 (measured <= 3.5e-6 / 2.5e-6 / 2.6e-7);
+      * solvers at 1e-6 (training setting of the mixing layers): velocity still <= 1e-5 (measured 4.7e-7), but the
+        pressure is only determined to tol / lambda_min(L): both sides stop on an ABSOLUTE L-inf residual of 1e-6 at
+        different iterates -> pressure 3e-4 (measured 1.44e-4), gradients 1.5e-4 (measured 6.7e-5);
+      * the pressure INCREMENT p' is ~1e-3..1e-4 of p in magnitude and carries the same absolute error -> 4e-4
+        (measured 1.8e-4 on the 264 x 256 grid, 9.1e-5 on the 33 x 32 cavity)."""
+    if setup["cg_tol"] <= 1e-8:
+        return dict(vel=1e-5, pres=1e-5, p_inc=4e-4, grad=1e-5)
+    return dict(vel=1e-5, pres=3e-4, p_inc=4e-4, grad=1.5e-4)

@@ -242,11 +242,11 @@ def test_cabi_argument_errors_without_gpu():
     assert (n[0], n[1], z[0], z[1]) == (16512, 16512, 82560, 82560)
     # solver entry points: empty batch, null pointers, bad cadence -> EINVAL before anything is launched
     null = None
-    assert N.lib.dpiso_pressure_cg_f64(0, 16, 16, 1, 1, null, null, 1e-8, 10, 10, 1, null, null, null, null) == -1
+    assert N.lib.dpiso_pressure_cg_f64(0, 16, 16, 1, 1, null, null, 1e-8, 10, 10, 1, null, null, null, null, null) == -1
     assert b"bad sizes" in N.lib.dpiso_last_error()
-    assert N.lib.dpiso_pressure_cg_f64(1, 16, 16, 1, 1, null, null, 1e-8, 10, 10, 1, null, null, null, null) == -1
+    assert N.lib.dpiso_pressure_cg_f64(1, 16, 16, 1, 1, null, null, 1e-8, 10, 10, 1, null, null, null, null, null) == -1
     assert b"null pointer" in N.lib.dpiso_last_error()
-    assert N.lib.dpiso_bicgstab_ilu(0, null, null, 0, 0, null, null, null, 1e-8, 10, null, null, null, null, null) == -1
+    assert N.lib.dpiso_bicgstab_ilu(0, null, null, 0, 0, null, 0, null, null, 1e-8, 10, null, null, null, null, null, null, null) == -1
     assert N.lib.dpiso_assemble(0, 16, 16, 0, 0, 1.0, 1.0, 1.0, 1.0, 1.0, null, null, null, null, null, 0, null, null, null) == -1
     assert b"batch must be >= 1" in N.lib.dpiso_last_error()
 
@@ -279,3 +279,39 @@ def test_custom_padded_matches_oracle(per_y, per_x):
     assert np.array_equal(flat, np.concatenate([u.ravel(), v.ravel()]))
     back = dp.stagger_flattened_data(torch.as_tensor(flat), (1, ny + 1, nx + 1, 2), coord_flip=True)
     assert torch.equal(back, st)
+
+
+@pytest.mark.parametrize("ny,nx", [(4, 5), (7, 6), (8, 8), (33, 32), (16, 24), (128, 128)])
+@pytest.mark.parametrize("per_x", [0, 1])
+@pytest.mark.parametrize("per_y", [0, 1])
+def test_native_table_builder_equals_numpy_derivation(ny, nx, per_x, per_y):
+    """dpiso_bicg_tables_create_host (csrc/tables.cu, what a C caller uses) against diffpiso_b200/structure.py (an
+    independent numpy / scipy derivation), entry by entry, for A and A^T of both components; `sym` is the structural
+    symmetry of the pattern (lost exactly for a component that is periodic along its staggered axis)."""
+    import ctypes as C
+    from diffpiso_b200 import _native as N
+    for comp in (0, 1):
+        for transpose in (0, 1):
+            st = N.BicgTables()
+            try:
+                want = S.bicg_tables(ny, nx, bool(per_x), bool(per_y), comp, bool(transpose))
+            except NotImplementedError:
+                assert N.lib.dpiso_bicg_tables_create_host(ny, nx, per_x, per_y, comp, transpose, C.byref(st)) == -3
+                continue
+            assert N.lib.dpiso_bicg_tables_create_host(ny, nx, per_x, per_y, comp, transpose, C.byref(st)) == 0, \
+                N.lib.dpiso_last_error()
+            try:
+                for k in ("n", "n_levels", "wa", "max_level", "wl", "wu", "dx", "rows_ok"):
+                    assert getattr(st, k) == want[k], k
+                assert st.owner_is_host == 1
+                assert st.sym == int(not (per_x if comp == 0 else per_y))
+                n, wa = st.n, st.wa
+                shapes = dict(level_ptr=st.n_levels + 1, perm=n, a_col=wa * n, a_src=wa * n, a_rev=wa * n, r_col=wa * n,
+                              r_src=wa * n, r_rev=wa * n, c_lsrc=4 * n, c_lrev=4 * n, c_usrc=4 * n, c_lfar=2 * n,
+                              c_ufar=2 * n, c_dsrc=n)
+                for k, size in shapes.items():
+                    got = np.ctypeslib.as_array(C.cast(getattr(st, k), C.POINTER(C.c_int)), shape=(size,))
+                    assert np.array_equal(got, np.asarray(want[k]).ravel()), (k, comp, transpose)
+            finally:
+                assert N.lib.dpiso_bicg_tables_destroy(C.byref(st)) == 0
+            assert not st.owner

@@ -46,7 +46,7 @@ def test_full_size_step_matches_oracle(name):
         assert np.array_equal(out[10][i].cpu().numpy(), ex["rhs"])
         assert abs(int(bicg[i, 0, 0]) - st["bicg_u"][0]) <= 1 and abs(int(bicg[i, 1, 0]) - st["bicg_v"][0]) <= 1
         assert rel_l2(v_new[i], ov) < 1e-5, (name, i, rel_l2(v_new[i], ov))
-        assert rel_l2(p_new[i], op) < 1e-4, (name, i, rel_l2(p_new[i], op))
+        assert rel_l2(p_new[i], op) < FULL_ADJOINT_BOUNDS[name]["pres"], (name, i, rel_l2(p_new[i], op))
     # the last pressure solve of the step is the second corrector
     for i in check[-1:]:
         it2 = int(sim.pressure_solver.last_iterations[i])
@@ -155,9 +155,13 @@ def _adjoint_weights(s, batch, seed):
 
 # measured worst cases on B200 (profiles/r02_parity.md) x 2 = the asserted bounds
 FULL_ADJOINT_BOUNDS = {
-    "c2_periodic128_b64": dict(vel=1e-5, pres=1e-4, g_vel=1e-4, g_pres=1e-4),
-    "c3_tml256x128_b8": dict(vel=1e-5, pres=1e-4, g_vel=1e-4, g_pres=1e-4),
-    "c4_sml512x128_b4": dict(vel=1e-5, pres=1e-4, g_vel=1e-4, g_pres=1e-4),
+    # C2 (solvers at 1e-8): measured 1.5e-7 / 8.3e-8 / 2.6e-7 / 2.5e-7 -> north_star's 1e-5 throughout
+    "c2_periodic128_b64": dict(vel=1e-5, pres=1e-5, g_vel=1e-5, g_pres=1e-5),
+    # C3, C4 (solvers at 1e-6, the reference's training tolerance): velocity and its gradient within / near 1e-5, the
+    # pressure and its gradient are only determined to tol / lambda_min(L) (absolute L-inf stopping test on both sides):
+    # measured 1.1e-5 / 6.7e-5 (C3), 0 / 2.3e-5 (C4)
+    "c3_tml256x128_b8": dict(vel=1e-5, pres=3e-5, g_vel=1e-5, g_pres=1.5e-4),
+    "c4_sml512x128_b4": dict(vel=1e-5, pres=1e-5, g_vel=3e-5, g_pres=5e-5),
 }
 
 
@@ -266,12 +270,14 @@ def test_c2_rollout_1000_steps_statistics_within_one_percent():
 
 
 def test_c5_1024_forward_and_adjoint_one_sample_matches_oracle():
-    """BASELINE configs[4]: one periodic 1024 x 1024 sample, forward + adjoint of one step against the oracle (about two
-    minutes of CPU).  The pressure CG runs ~1700 iterations here; iteration counts within the slack, fields as stated."""
+    """BASELINE configs[4]: one periodic 1024 x 1024 sample, forward + adjoint of one step against the oracle.  A
+    converged pressure solve takes ~1700 iterations per solve here (minutes of CPU for the oracle's four solves), so both
+    sides run the SAME fixed budget of 300 CG iterations per solve: identical arithmetic, no stopping-test ambiguity,
+    about a minute of CPU.  Convergence at this size is covered by test_config5_large_periodic_grid_properties."""
     from common import record
     from diffpiso_b200 import setups as SU
     from oracle import adjoint as A
-    s = SU.periodic_box(1024, 1024, visc=1e-3)
+    s = SU.periodic_box(1024, 1024, visc=1e-3, cg_max_it=300)
     sim = build_sim(s)
     v0, p0 = random_fields(s, 4321)
     w_u, w_p = _adjoint_weights(s, 1, 33)

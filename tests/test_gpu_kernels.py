@@ -151,7 +151,8 @@ def test_pressure_cg_matches_oracle(name, fp64):
             assert abs(int(its[i]) - oit) <= cg_iteration_slack(s, oit), (name, i, int(its[i]), oit)
             assert abs(int(its2[i]) - oit) <= cg_iteration_slack(s, oit), (name, i, int(its2[i]), oit, "two reductions")
             # both sides stop on |r|_inf < tol at (possibly) different iterates: error in x ~ tol * cond
-            slack = 2e-4 if s["cg_reset"] <= 10 else 3e-5      # restarted CG stops further from the fixed point
+            # measured worst cases (profiles/r02_parity.md): 9.0e-6 (reset 1000), 7.4e-5 (reset 10), 5.0e-4 at tol 1e-6
+            slack = 1.5e-4 if s["cg_reset"] <= 10 else 2e-5    # restarted CG stops further from the fixed point
             assert rel_l2(x[i], ox.astype(np.float32)) < max(slack, 1000 * tol), (name, i)
             # x is returned in fp32 (the reference casts the fp64 result), which bounds the attainable residual
             bound = 10 * tol + 2e-6 * np.abs(x[i]).max() * np.abs(lap_h[i][:, 2]).max()
@@ -257,8 +258,7 @@ def test_bicgstab_level_major_fallback_agrees_with_row_major(name, transpose):
     """The two predictor kernels (row-major default, level-major fallback forced with DPISO_BICG_DBG=8) share the
     per-row arithmetic; their dot products associate differently, so they agree to rounding, with iteration counts
     within +-1."""
-    import os
-    from diffpiso_b200 import ops
+    from diffpiso_b200 import _native as N, ops
     s = ALL_SETUPS[name]()
     g, m = _geom(s), _masks(s)
     vels = np.stack([random_fields(s, 80 + i)[0] for i in range(2)])
@@ -267,10 +267,10 @@ def test_bicgstab_level_major_fallback_agrees_with_row_major(name, transpose):
     neg = torch.neg(values)
     rhs = _t(vels) * _beta(s)
     x_rows, st_rows, _ = ops.bicgstab_ilu(g, neg, rhs, _t(vels), s["bicg_tol"], s["bicg_max_it"], transpose)
-    os.environ["DPISO_BICG_DBG"] = "8"
+    N.lib.dpiso_bicgstab_set_debug(8)
     try:
         x_lm, st_lm, _ = ops.bicgstab_ilu(g, neg, rhs, _t(vels), s["bicg_tol"], s["bicg_max_it"], transpose)
     finally:
-        del os.environ["DPISO_BICG_DBG"]
+        N.lib.dpiso_bicgstab_set_debug(-1)
     assert int((st_rows[:, :, 0] - st_lm[:, :, 0]).abs().max()) <= 1
     assert rel_l2(x_rows.cpu().numpy(), x_lm.cpu().numpy()) < 1e-5

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from common import ALL_SETUPS, SMALL_SETUPS, random_fields, record, rel_l2
+from common import ALL_SETUPS, SMALL_SETUPS, field_tolerances, random_fields, record, rel_l2
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -82,19 +82,19 @@ def test_piso_step_matches_oracle(name):
                 assert rel_l2(out[13][i].cpu().numpy().ravel(), ex["div1"]) < 1e-4             # differences of u*
                 # the L-inf residual test at tol leaves smooth-mode errors ~ tol / lambda_min in the pressure, which grow
                 # with the grid (67 584 cells: ~2e-8 on |p'| ~ 1e-4); the velocity only sees its gradient
-                ptol1 = 1e-4 if s["ny"] * s["nx"] < 60000 else 3e-4
-                assert rel_l2(_gauge(s, out[2].data[i].cpu().numpy().ravel()), _gauge(s, ex["p1"])) < ptol1
+                e_p1 = rel_l2(_gauge(s, out[2].data[i].cpu().numpy().ravel()), _gauge(s, ex["p1"]))
+                assert e_p1 < field_tolerances(s)["p_inc"], (name, i, e_p1)
             assert abs(int(bicg[i, 0, 0]) - st["bicg_u"][0]) <= 1 and abs(int(bicg[i, 1, 0]) - st["bicg_v"][0]) <= 1
             # north_star: 1e-5 relative L2 per step at the paper's 1e-8 solver tolerance; setups that run the solvers at
             # 1e-6 (training tolerance) can only agree to ~tol * cond, on either side of the comparison
-            vtol, ptol = (1e-5, 1e-4) if s["cg_tol"] <= 1e-8 else (5e-5, 5e-4)
+            vtol, ptol = field_tolerances(s)["vel"], field_tolerances(s)["pres"]
             record("step", setup=name, step=step, sample=i, cg_tol=s["cg_tol"], vel_rel_l2=rel_l2(v_new[i], ov),
                    pres_rel_l2=rel_l2(_gauge(s, p_new[i]), _gauge(s, op)),
                    p1_rel_l2=(rel_l2(_gauge(s, out[2].data[i].cpu().numpy().ravel()), _gauge(s, ex["p1"])) if step == 0 else None),
                    bicg_it=[int(bicg[i, 0, 0]), int(bicg[i, 1, 0])], bicg_it_oracle=[st["bicg_u"][0], st["bicg_v"][0]],
                    cg2_it=int(sim.pressure_solver.last_iterations[i]), cg2_it_oracle=st["cg2"])
             assert rel_l2(v_new[i], ov) < vtol, (name, step, i, rel_l2(v_new[i], ov))
-            assert rel_l2(_gauge(s, p_new[i]), _gauge(s, op)) < ptol, (name, step, i, rel_l2(p_new[i], op))
+            assert rel_l2(_gauge(s, p_new[i]), _gauge(s, op)) < ptol, (name, step, i, rel_l2(_gauge(s, p_new[i]), _gauge(s, op)))
             assert abs(float(np.mean(p_new[i]) - np.mean(op))) < 1e-3 * float(np.abs(op).max())
             ovel[i], opres[i] = ov, op
         vel, pres = v_new, p_new
