@@ -34,6 +34,11 @@ WORKLOAD = "decaying_turbulence_periodic_128x128_batch64_fwd+adjoint"
 # algorithmic bytes per cell per CG iteration (fp64, 5 stored coefficients) and per reset
 CG_BYTES_PER_CELL_ITER = 168
 CG_BYTES_PER_CELL_RESET = 88
+# essential fp64 flops per cell and CG iteration: stencil 1 mul + 4 fma = 9, inner products p.r, p.Lp, r.Lp,
+# Lp.Lp = 4 fma = 8 plus the three plain sums (rank-deficiency shift) = 3, update x (fma 2), z + shift (1), r (fma 2),
+# p = beta p + r (mul + add 2) = 7
+CG_FLOPS_PER_CELL_ITER = 27
+FP64_FMA_LANES_PER_SM = 64          # B200: 64 DFMA / clk / SM (16 per SM sub-partition), the issue roofline of the fp64 pipe
 
 
 def setup_case():
@@ -175,6 +180,91 @@ class ClockSampler(object):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def run_config5(dev, hbm_peak, n=1024, batch=8, steps=2, cg_max_it=20000):
+    """BASELINE configs[4]: periodic n x n, `batch` samples on one GPU, forward + adjoint PISO steps at the paper's solver
+    tolerances.  Here the solver state does not fit on chip: the pressure CG streams its vectors through HBM
+    (pressure_cg_global_kernel) -- this is the HBM-bound configuration of the path."""
+    import torch
+    import diffpiso_b200 as dp
+    from diffpiso_b200 import ops, setups as SU
+    s = SU.periodic_box(n, n, visc=1e-3, cfl=0.5, umax=1.0, bicg_tol=1e-8, bicg_max_it=10000, cg_tol=1e-8, cg_max_it=cg_max_it,
+                        cg_reset=1000, cg_fp64=True)
+    nf, nc = n * (n + 1) + (n + 1) * n, n * n
+    ls = dp.LinearSolverCudaMultiBicgstabILU(accuracy=s["bicg_tol"], max_iterations=s["bicg_max_it"])
+    ps = dp.PisoPressureSolverCudaCustom(dx=s["dx"], accuracy=s["cg_tol"], max_iterations=s["cg_max_it"],
+                                         residual_reset=s["cg_reset"])
+    sim = dp.SimulationParameters(s["dirichlet_mask"], s["dirichlet_values_staggered"], s["active_mask"],
+                                  s["accessible_mask"], bool_periodic=(True, True), no_slip_mask=s["no_slip_mask"],
+                                  viscosity=float(s["visc"]), linear_solver=ls, pressure_solver=ps)
+    base = SU.solenoidal_field(n, n, seed=4321)
+    rng = np.random.RandomState(7)
+    vel = torch.as_tensor(np.stack([base * (1.0 + 0.05 * i) for i in range(batch)]).astype(np.float32)).to(dev)
+    pres = torch.zeros(batch, nc, device=dev)
+    dvals = torch.zeros(1, nf, device=dev)
+    # smooth adjoint seeds (a loss on the large scales), zero-mean for the pressure
+    w_u = torch.as_tensor(np.stack([SU.solenoidal_field(n, n, seed=99 + i) for i in range(batch)]).astype(np.float32)).to(dev)
+    w_p = torch.zeros(batch, nc, device=dev)
+    dxy = (s["dy"], s["dx"])
+    ev = {"cg": [], "bicg": []}
+    orig_cg, orig_bicg = ops.pressure_cg, ops.bicgstab_ilu
+
+    def timed(kind, fn):
+        def wrapped(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn(*a, **k)
+            e1.record()
+            ev[kind].append((e0, e1, out[1]))
+            return out
+        return wrapped
+    ops.pressure_cg, ops.bicgstab_ilu = timed("cg", orig_cg), timed("bicg", orig_bicg)
+    try:
+        def step(v, p):
+            v = v.detach().requires_grad_(True)
+            p = p.detach().requires_grad_(True)
+            velocity = dp.StaggeredGrid(flat=v, resolution=(n, n), dx=dxy, extrapolation="periodic")
+            pressure = dp.CenteredGrid(p.reshape(batch, n, n, 1), dx=dxy, extrapolation="periodic")
+            vn, pn, _ = dp.piso_step(velocity, pressure, pressure, pressure, s["dt"], sim, dvals)
+            gv, gp = torch.autograd.grad([vn.flat, pn.data.reshape(batch, nc)], [v, p], [w_u, w_p])
+            return vn.flat.detach(), pn.data.reshape(batch, nc).detach(), gv
+        vel, pres, gv = step(vel, pres)                       # warm-up (tables, workspaces)
+        torch.cuda.synchronize()
+        ev["cg"].clear(); ev["bicg"].clear()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            vel, pres, gv = step(vel, pres)
+        e1.record()
+        torch.cuda.synchronize()
+    finally:
+        ops.pressure_cg, ops.bicgstab_ilu = orig_cg, orig_bicg
+    ms = e0.elapsed_time(e1) / steps
+    cg_ms = [a.elapsed_time(b) for a, b, _ in ev["cg"]]
+    cg_it = [float(it.max()) for _, _, it in ev["cg"]]       # a launch lasts as long as its slowest sample
+    bicg_ms = [a.elapsed_time(b) for a, b, _ in ev["bicg"]]
+    us_per_it = 1e3 * sum(cg_ms) / max(sum(cg_it), 1.0)
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r02_cg_global.json")))
+    except Exception:
+        prof = {}
+    model_gbs = batch * nc * CG_BYTES_PER_CELL_ITER / (us_per_it * 1e-6) / 1e9
+    meas = prof.get("dram_bytes_per_cell_iteration")
+    return {"workload": "periodic_%dx%d_batch%d_fwd+adjoint" % (n, n, batch), "steps": steps, "ms_per_step": ms,
+            "cell_updates_per_s": batch * nc / (ms * 1e-3), "finite": bool(torch.isfinite(gv).all()),
+            "pressure_cg": {"launches_per_step": len(cg_ms) // steps, "ms_per_launch": float(np.mean(cg_ms)),
+                            "max_iterations_per_launch": cg_it, "us_per_iteration_whole_batch": us_per_it,
+                            "share_of_step": sum(cg_ms) / (ms * steps), "launch": ops.pressure_cg_config(),
+                            "hbm_model": {"bytes_per_cell_iteration": CG_BYTES_PER_CELL_ITER, "achieved_gbs": model_gbs,
+                                          "ratio_to_hbm_peak": model_gbs / hbm_peak},
+                            "hbm_measured": {"bytes_per_cell_iteration": meas,
+                                             "achieved_gbs": (batch * nc * meas / (us_per_it * 1e-6) / 1e9) if meas else None,
+                                             "frac": (batch * nc * meas / (us_per_it * 1e-6) / 1e9 / hbm_peak) if meas else None,
+                                             "source": prof.get("source")}},
+            "bicgstab": {"launches_per_step": len(bicg_ms) // steps, "ms_per_launch": float(np.mean(bicg_ms)),
+                         "iterations": [int(v) for v in ev["bicg"][0][2].cpu().numpy()[0, :, 0]] if ev["bicg"] else None,
+                         "share_of_step": sum(bicg_ms) / (ms * steps)}}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -197,10 +287,12 @@ def run_ours(args):
     sim = dp.SimulationParameters(s["dirichlet_mask"], s["dirichlet_values_staggered"], s["active_mask"],
                                   s["accessible_mask"], bool_periodic=(True, True), no_slip_mask=s["no_slip_mask"],
                                   viscosity=float(s["visc"]), linear_solver=ls, pressure_solver=ps)
-    vel_h, pres_h = initial_state(s, BATCH, 1234 + rank * BATCH)
+    # --same-seeds: every rank solves the same samples, which separates host launch jitter from iteration imbalance
+    seed_rank = 0 if args.same_seeds else rank
+    vel_h, pres_h = initial_state(s, BATCH, 1234 + seed_rank * BATCH)
     dxy = (s["dy"], s["dx"])
     dvals = torch.zeros(1, nf, device=dev)
-    rng = np.random.RandomState(99 + rank)
+    rng = np.random.RandomState(99 + seed_rank)
     w_u = torch.as_tensor(rng.randn(BATCH, nf).astype(np.float32)).to(dev)
     w_p = rng.randn(BATCH, nc).astype(np.float32)
     w_p = torch.as_tensor(w_p - w_p.mean(axis=1, keepdims=True)).to(dev)
@@ -339,8 +431,16 @@ def run_ours(args):
     ms_e2e = g0.elapsed_time(g1)
 
     times = torch.tensor([ms, ms_fwd, ms_e2e], dtype=torch.float64, device=dev)
+    # per-rank diagnostics of the device-resident loop: step time, sum of CG iterations, mean of the per-launch maxima
+    # (a launch lasts as long as its slowest sample), time inside the CG / BiCGStab launches
+    launch_max = [float(it.max()) for _, _, it in cg_events[:len(cg_ms)]]
+    mine = torch.tensor([ms / args.steps, float(cg_its.sum()), float(np.mean(launch_max)), float(sum(cg_ms)) / args.steps,
+                         float(sum(bicg_ms)) / args.steps], dtype=torch.float64, device=dev)
+    per_rank = [mine.clone() for _ in range(world)]
     if world > 1:
+        dist.all_gather(per_rank, mine)
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    per_rank = [[float(v) for v in t_.cpu()] for t_ in per_rank]
     ms, ms_fwd, ms_e2e = [float(x) for x in times.cpu()]
     if rank != 0:
         if world > 1:
@@ -349,36 +449,67 @@ def run_ours(args):
 
     cells = BATCH * nc * world
     value = cells * args.steps / (ms * 1e-3)
-    # roofline of the dominant kernel (pressure CG): algorithmic bytes of SURVEY 8(d) / measured launch duration
-    mean_it = float(cg_its.mean())
-    resets = math.floor((mean_it + 1) / s["cg_reset"])
-    bytes_per_launch = BATCH * nc * (CG_BYTES_PER_CELL_ITER * mean_it + CG_BYTES_PER_CELL_RESET * resets)
-    cg_avg_ms = float(np.mean(cg_ms))
-    achieved = bytes_per_launch / (cg_avg_ms * 1e-3) / 1e9
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "cg_dram_traffic.json")))["bytes_per_launch"]
-    except Exception:
-        pass
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+
+    def prof(name):
+        try:
+            return json.load(open(os.path.join(ROOT, "profiles", name)))
+        except Exception:
+            return {}
+    cg_prof, bicg_prof = prof("cg_dram_traffic.json"), prof("bicg_dram_traffic.json")
     cfg = ops.pressure_cg_config()
-    # second kernel: BiCGStab+ILU0 (setup 36 + ILU 40 + 224 per iteration, bytes per row)
+    # ---- dominant kernel: the cluster-resident pressure CG (rank 0's launches) -------------------------------------
+    mean_it = float(cg_its.mean())
+    cg_avg_ms = float(np.mean(cg_ms))
+    cell_its = float(BATCH * nc) * mean_it                         # cell-iterations per launch
+    # (i) what binds it: fp64 issue.  x, r, p, z and the matrix stay in registers / shared memory for the whole solve, so
+    #     HBM only carries the compulsory read of (lap, div) and the write of x; the roofline is the fp64 pipe.
+    props = torch.cuda.get_device_properties(dev)
+    sm_hz = 1e6 * float((clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0))
+    fp64_peak = props.multi_processor_count * FP64_FMA_LANES_PER_SM * 2 * sm_hz / 1e12
+    fp64_achieved = CG_FLOPS_PER_CELL_ITER * cell_its / (cg_avg_ms * 1e-3) / 1e12
+    # (ii) the HBM model of SURVEY 8(d) (what a streaming implementation such as the reference moves), for comparison
+    resets = math.floor((mean_it + 1) / s["cg_reset"])
+    model_bytes = BATCH * nc * (CG_BYTES_PER_CELL_ITER * mean_it + CG_BYTES_PER_CELL_RESET * resets)
+    model_gbs = model_bytes / (cg_avg_ms * 1e-3) / 1e9
+    traffic = cg_prof.get("bytes_per_launch")
+    roofline = {
+        "bound": "fp64",
+        "kernel": "pressure_cg_kernel<double,float,%d threads,%d cells/thread> cluster %d (4 launches per fwd+adjoint step)"
+                  % (cfg["threads"], cfg["cells_per_thread"], cfg["cluster"]),
+        "achieved": fp64_achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": fp64_achieved / fp64_peak,
+        "peak_source": "%d SMs x %d DFMA lanes x 2 flop x %.0f MHz (SM clock sampled during the timed region)"
+                       % (props.multi_processor_count, FP64_FMA_LANES_PER_SM, sm_hz / 1e6),
+        "flops_per_cell_iteration": CG_FLOPS_PER_CELL_ITER, "mean_cg_iterations": mean_it,
+        "cg_iterations_min_max": [float(cg_its.min()), float(cg_its.max())],
+        "mean_of_per_launch_max_iterations": float(np.mean(launch_max)),
+        "avg_launch_ms": cg_avg_ms, "cg_share_of_step": float(sum(cg_ms) / ms),
+        "traffic": traffic,
+        "hbm_actual": {"achieved": (traffic / (cg_avg_ms * 1e-3) / 1e9) if traffic else None, "peak": peak, "unit": "GB/s",
+                       "frac": (traffic / (cg_avg_ms * 1e-3) / 1e9 / peak) if traffic else None,
+                       "note": "ncu dram__bytes_read+write per launch (profiles/cg_dram_traffic.json): the compulsory "
+                               "read of lap + div and write of x"},
+        "hbm_model": {"achieved": model_gbs, "peak": peak, "unit": "GB/s", "ratio_to_hbm_peak": model_gbs / peak,
+                      "algorithmic_bytes_per_launch": model_bytes, "peak_source": peak_src,
+                      "note": "SURVEY 8(d) streaming model (168 B per cell and iteration): what an implementation that "
+                              "keeps the vectors in HBM would move; > 1 because this kernel does not stream them, so it is "
+                              "NOT the binding roofline here"},
+        "ncu": {k: cg_prof.get(k) for k in ("fp64_pipe_pct", "issue_active_pct", "warps_active_pct", "source") if k in cg_prof},
+        "note": "frac = essential fp64 flops (27 per cell and iteration) / launch time / fp64 peak; the kernel issues more "
+                "than the essential instructions (index arithmetic, conversions, reductions), see profiles/",
+    }
+    # ---- second kernel: BiCGStab + ILU(0), HBM-nominal (setup 36 + ILU 40 + 224 per iteration, bytes per row)
     bicg_it = float(bicg_its.mean())
     bicg_bytes = BATCH * nf * (36.0 + 40.0 + 224.0 * bicg_it)
     bicg_avg_ms = float(np.mean(bicg_ms))
-    bicg_traffic = None
-    try:
-        bicg_traffic = json.load(open(os.path.join(ROOT, "profiles", "bicg_dram_traffic.json")))["bytes_per_launch"]
-    except Exception:
-        pass
-    # whole step against the step model of SURVEY 8(d) (forward: assembly 56 + ILU 80 + glue 120 + 2 Laplace 96 +
-    # 448 it_bicg + 168 (it_cg1 + it_cg2) bytes per cell; backward the same without the assembly, plus ILU again because
-    # the adjoint re-factorises)
+    bicg_gbs = bicg_bytes / (bicg_avg_ms * 1e-3) / 1e9
+    # ---- whole step against the step model of SURVEY 8(d) --------------------------------------------------------------
     n_cg = len(cg_ms) // args.steps
     step_bytes = BATCH * nc * (56 + 2 * 80 + 2 * 120 + 4 * 48 + 448 * 2 * bicg_it + 168 * mean_it * n_cg)
     step_achieved = step_bytes / (ms / args.steps * 1e-3) / 1e9
@@ -389,39 +520,36 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "grid": [NY, NX], "batch_per_gpu": BATCH, "visc": 1e-3, "cfl": 0.5,
                    "bicgstab": "fp32 tol 1e-8", "pressure_cg": "fp64 tol 1e-8 reset 1000",
                    "l2": "per-step working set (~0.4 GB of solver workspace + state) exceeds the 126 MB L2; rollout "
-                         "state changes every step", "cg_launch": cfg},
+                         "state changes every step", "cg_launch": cfg, "same_seeds": bool(args.same_seeds)},
         "forward_only": {"value": cells * args.steps / (ms_fwd * 1e-3), "unit": "cell-updates/s",
                          "ms_per_step": ms_fwd / args.steps},
         "e2e": {"value": cells * args.steps / (ms_e2e * 1e-3), "unit": "cell-updates/s",
                 "h2d_bytes_per_step": int(BATCH * (nf + nc) * 4), "d2h_bytes_per_step": int(2 * BATCH * (nf + nc) * 4)},
         "gpu_launches": n_launch,
-        "roofline": {"bound": "hbm", "kernel": "pressure_cg_kernel<double,float,%d threads,%d cells/thread> cluster %d (4 launches per fwd+adjoint step)" % (cfg["threads"], cfg["cells_per_thread"], cfg["cluster"]),
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-                     "algorithmic_bytes_per_launch": bytes_per_launch, "mean_cg_iterations": mean_it,
-                     "cg_iterations_min_max": [float(cg_its.min()), float(cg_its.max())],
-                     "mean_of_per_launch_max_iterations": float(np.mean([float(it.max()) for _, _, it in cg_events[:len(cg_ms)]])),
-                     "avg_launch_ms": cg_avg_ms, "cg_share_of_step": float(sum(cg_ms) / ms),
-                     "note": "solver state is register/smem resident for the whole solve, so the algorithmic HBM model "
-                             "of SURVEY 8(d) (168 B/cell/iteration) is exceeded by design (frac > 1); traffic = "
-                             "ncu-measured DRAM bytes per launch (profiles/cg_dram_traffic.json); the kernel is bound "
-                             "by issue slots and reduction latency, see profiles/r01_summary.md"},
-        "roofline_bicgstab": {"bound": "hbm", "kernel": "bicgstab_kernel (one 512-thread CTA per system, 2 launches per step)",
-                              "achieved": bicg_bytes / (bicg_avg_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                              "frac": bicg_bytes / (bicg_avg_ms * 1e-3) / 1e9 / peak, "traffic": bicg_traffic,
-                              "mean_iterations": bicg_it, "avg_launch_ms": bicg_avg_ms,
-                              "share_of_step": float(sum(bicg_ms) / ms),
-                              "note": "latency-bound: 13 triangular sweeps x 255 dependent wavefront levels per solve"},
-        "roofline_step": {"bound": "hbm", "achieved": step_achieved, "peak": peak, "unit": "GB/s", "frac": step_achieved / peak,
-                          "algorithmic_bytes_per_step": step_bytes,
-                          "note": "SURVEY 8(d) step model with the iteration counts of this run"},
+        "roofline": roofline,
+        "roofline_bicgstab": {"bound": "hbm", "kernel": "bicgstab_rows_kernel (one 512-thread CTA per system, 2 launches per step)",
+                              "achieved": bicg_gbs, "peak": peak, "unit": "GB/s", "frac": bicg_gbs / peak,
+                              "traffic": bicg_prof.get("bytes_per_launch"), "mean_iterations": bicg_it,
+                              "avg_launch_ms": bicg_avg_ms, "share_of_step": float(sum(bicg_ms) / ms),
+                              "note": "algorithmic bytes (SURVEY 8(d)) / launch time; latency-bound: 13 triangular sweeps x "
+                                      "~260 dependent wavefront levels per solve, one CTA per system"},
+        "roofline_step": {"bound": "hbm", "achieved": step_achieved, "peak": peak, "unit": "GB/s",
+                          "ratio_to_hbm_peak": step_achieved / peak, "algorithmic_bytes_per_step": step_bytes,
+                          "note": "SURVEY 8(d) streaming step model with the iteration counts of this run; exceeds 1 because the "
+                                  "pressure solves (98 % of the model's bytes) run out of registers / shared memory"},
+        "per_rank": {"ms_per_step": [r_[0] for r_ in per_rank], "cg_iterations_sum": [r_[1] for r_ in per_rank],
+                     "cg_mean_of_launch_max_iterations": [r_[2] for r_ in per_rank],
+                     "cg_ms_per_step": [r_[3] for r_ in per_rank], "bicgstab_ms_per_step": [r_[4] for r_ in per_rank]},
         "clocks": clocks, "finite": finite,
     }
+    if args.config5 and world == 1:
+        line["config5"] = run_config5(dev, peak)
     if args.cpu_baseline:
-        cores = 1
+        cores = usable_cores()      # the CPU baseline is the all-core figure (one sample per core), as in the reference arm
         v, dt = cpu_throughput(cores, args.cpu_steps, adjoint=True)
         line["cpu_baseline"] = {"value": v, "unit": "cell-updates/s", "cores": cores, "kind": "port",
-                                "sample": "1 sample x %d fwd+adjoint steps of the 128x128 case (%.1f s)" % (args.cpu_steps, dt)}
+                                "sample": "%d samples (one per core) x %d fwd+adjoint steps of the 128x128 case (%.1f s)"
+                                          % (cores, args.cpu_steps, dt)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -435,11 +563,20 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--cpu-steps", type=int, default=60)
+    ap.add_argument("--same-seeds", action="store_true", help="every rank solves the same samples (scaling diagnostics)")
+    ap.add_argument("--no-config5", dest="config5", action="store_false",
+                    help="skip the extra BASELINE configs[4] measurement (periodic 1024^2, batch 8)")
+    ap.add_argument("--config5-only", action="store_true", help="run only the configs[4] measurement (used under ncu)")
+    ap.add_argument("--config5-maxit", type=int, default=20000, help="CG iteration cap of the configs[4] run (profiling)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
+    elif args.config5_only:
+        import torch
+        torch.cuda.set_device(0)
+        print(json.dumps(run_config5(torch.device("cuda", 0), 6460.9, steps=1, cg_max_it=args.config5_maxit)))
     else:
         if int(os.environ.get("WORLD_SIZE", "1")) > 1:
             args.cpu_baseline = args.cpu_baseline and int(os.environ.get("RANK", "0")) == 0

@@ -34,6 +34,8 @@ struct BicgTab {
     const int4 *c_lsrc, *c_lrev, *c_usrc;
     const int2 *c_lfar, *c_ufar;
     const int *c_dsrc;
+    const int4 *m_nbr;
+    const int2 *m_lfar, *m_ufar;
 };
 
 struct BicgParams {
@@ -50,6 +52,7 @@ struct BicgParams {
     int ring_depth;        // levels in flight in the cp.async ring (16, 8 or 2)
     int rows_kernel;       // 1: bicgstab_rows_kernel (row-major layout, one thread per grid row in the sweeps)
     int rows_threads;      // its sweep threads P = roundup32(max dy)
+    int rows_lp_cap;       // ints reserved for its level_ptr copy in shared memory
     int dbg;               // profiling experiments only (DPISO_BICG_DBG): 1 skip level barrier, 2 skip refill, 4 skip recurrence
                            // (level-major kernel); 8 force the level-major kernel
     const float *values, *rhs, *x0;
@@ -629,118 +632,193 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_kernel(const BicgPar
 
 
 // ===============================================================================================================
-// Row-major variant (default where the grid allows it).  Same algorithm, same arithmetic, same results as
-// bicgstab_kernel, but nothing is permuted: every vector and plane is indexed by the ORIGINAL row i = ly * dx + lx, and
-// the wavefront schedule is implicit.  In the three kinds of sweeps (ILU(0), L solve, U solve) thread j owns grid row
-// ly = j and walks along x as the level d = lx + ly advances, so
-//   * its row data is ONE contiguous stream per plane (pointer + x): a per-thread cp.async ring with compile-time slot
-//     offsets, no level pointers, no index arithmetic;
+// Row-sweep variant (default where the grid allows it).  Same algorithm and the same per-row arithmetic as
+// bicgstab_kernel.  In the three kinds of sweeps (ILU(0), L solve, U solve) thread j owns grid row ly = j and walks
+// along x as the level d = lx + ly advances, so
 //   * the x-neighbour operand is the thread's own previous result (a register), the y-neighbour operand is the
 //     neighbouring lane's previous result (one shuffle); only a warp-edge lane and the periodic wrap entries ("far") read
-//     the solve vector in shared memory, which the per-level named barrier has made complete;
+//     the solve vector in shared memory;
 //   * entries sit in canonical slots by kind (lower: [far below the y-neighbour, y-neighbour, far above it,
 //     x-neighbour], upper: [x-neighbour, far below the y-neighbour, y-neighbour, far above it]) -- the ascending-column
-//     order of the row, hence the same fma chain as the CSR formulation (structure.py checks that every row fits).
+//     order of the row, hence the same fma chain as the CSR formulation (structure.py checks that every row fits);
+//   * every plane and vector is stored LEVEL BY LEVEL (position q = level_ptr[lx + ly] + ly - ly_min(level), closed
+//     form): at a given step the lanes of a warp touch consecutive positions, so the per-thread cp.async ring reads
+//     coalesced 128-byte lines and the solve vector in shared memory is conflict-free.  (Round 1 kept the original row
+//     order: each lane streamed its own grid row, i.e. 32 different lines per cp.async -- 3 x 32 L1 wavefronts per warp
+//     and level, which is what held a level at ~380 cycles whatever was done to the barrier: profiles/r02_bicgstab.md.)
+//     The caller's row-major vectors are permuted once on the way in and once on the way out.
 // ===============================================================================================================
 constexpr int kRowsRing = 8;
+constexpr int kRowsSkew = 2;
 
 struct RowsPlanes {
     float4 *alow;      // [n] A lower values in canonical slots (kept: the SpMV reads them)
     float *adiag;      // [n] A diagonal (kept)
     float4 *lval;      // [n] l_ik (written by the ILU sweep)
     float4 *arv;       // [n] ILU only: reverse entries u_ki = A(k, i) of the lower slots (aliases rh, p, v, tt)
-    const int2 *lfar;  // [n] columns of the two far lower slots, -1 = absent (static table, shared by all systems)
+    const int2 *lfar;  // [n] positions of the two far lower slots, -1 = absent (static table, shared by all systems)
     float4 *uval;      // [n] upper values (unchanged by ILU(0) on this pattern)
     const int2 *ufar;  // [n]
     float *udiag;      // [n] pivots (written by the ILU sweep)
 };
 
-// MODE 0: ILU(0) (zs = pivots), 1: L solve (ext = right-hand side), 2: U solve
-// kZsSmem = false: the solve vector does not fit shared memory and lives in global memory (L2); only the warp-edge lanes,
-// the far operands, the U solve's start values and the result stores touch it -- the x- and y-neighbour operands stay in
-// registers / shuffles, which is what makes this kernel usable far beyond the shared-memory capacity.
-template <int MODE, bool kZsSmem>
-__device__ __noinline__ void sweep_rows(const RowsPlanes pl, const float *ext, int dx, int dy, int P, float *zs_global) {
-    constexpr int D = kRowsRing;
+// level-major position of grid point (row t, column x); lp = level_ptr (shared-memory copy)
+__device__ __forceinline__ int lm_pos(const int *lp, int dx, int t, int x) {
+    const int L = x + t;
+    return lp[L] + t - max(0, L - dx + 1);
+}
+
+// One row of a sweep, branch-free: absent slots carry a zero coefficient and a clamped position, so their operand is
+// loaded unconditionally and selected afterwards.  fma order = ascending column of the row.
+template <int MODE>
+__device__ __forceinline__ float sweep_row_step(const RowsPlanes &pl, float *zs, int q, int qe, bool edge, float nb,
+                                                float prev, const float4 v, const float4 rv, const int2 fc, float e) {
+    const float z0 = zs[fc.x >= 0 ? fc.x : 0], z1 = zs[fc.y >= 0 ? fc.y : 0];
+    const float ze = zs[qe];
+    nb = edge ? ze : nb;
+    if (MODE == 0) {
+        // l_ik = a_ik / u_kk, u_ii = a_ii - sum l_ik u_ki, lower entries in ascending column order
+        const float p0 = fc.x >= 0 ? z0 : 1.0f, p2 = fc.y >= 0 ? z1 : 1.0f;
+        const float l0 = __fdiv_rn(v.x, p0), l1 = __fdiv_rn(v.y, nb), l2 = __fdiv_rn(v.z, p2), l3 = __fdiv_rn(v.w, prev);
+        float dg = fmaf(-l0, rv.x, e);
+        dg = fmaf(-l1, rv.y, dg);
+        dg = fmaf(-l2, rv.z, dg);
+        dg = fmaf(-l3, rv.w, dg);
+        pl.lval[q] = make_float4(l0, l1, l2, l3);
+        pl.udiag[q] = dg;
+        return dg;
+    } else if (MODE == 1) {
+        const float f0 = fc.x >= 0 ? z0 : 0.0f, f1 = fc.y >= 0 ? z1 : 0.0f;
+        float acc = fmaf(-v.x, f0, e);
+        acc = fmaf(-v.y, nb, acc);
+        acc = fmaf(-v.z, f1, acc);
+        return fmaf(-v.w, prev, acc);
+    } else {
+        const float f0 = fc.x >= 0 ? z0 : 0.0f, f1 = fc.y >= 0 ? z1 : 0.0f;
+        float acc = fmaf(-v.x, prev, zs[q]);
+        acc = fmaf(-v.y, f0, acc);
+        acc = fmaf(-v.z, nb, acc);
+        acc = fmaf(-v.w, f1, acc);
+        return __fdiv_rn(acc, e);
+    }
+}
+
+// Progress counters of the decoupled sweeps.  Counter and solve vector both live in SHARED memory (kFlags is only used
+// with the solve vector in shared memory): the LSU performs a warp's shared-memory instructions in issue order, so
+// "STS values; (warp-converged) STS counter" on the producer and "LDS counter; LDS value" on the consumer need no fence --
+// st.release / ld.acquire compile to MEMBAR.ALL.CTA per level, which also waits for the cp.async prefetches in flight
+// (measured: 18 % slower than a per-level barrier).  volatile + the "memory" clobbers pin the compiler's order.
+__device__ __forceinline__ int ld_flag_shared(const int *p) {
+    int v;
+    asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_flag_shared(int *p, int v) {
+    asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+
+// MODE 0: ILU(0) (zs = pivots), 1: L solve (ext = right-hand side), 2: U solve.
+// kFlags = false: all sweep warps meet at a named barrier after every level.
+// kFlags = true:  decoupled warps.  The only producer/consumer pair that crosses a warp is (last lane of warp w) ->
+//   (first lane of warp w + 1) [L / ILU; mirrored for the U solve], so each warp starts kRowsSkew steps later than its
+//   predecessor: the value an edge lane needs was then produced kRowsSkew + 1 steps ago and is handed over through the
+//   solve vector plus a per-warp progress counter, polled one step ahead of its use.  A warp that runs ahead of schedule
+//   never waits.  Far (periodic wrap) operands come from the same thread, from the same warp (ordered by the per-step
+//   __syncwarp) or from a warp whose progress has been observed transitively: they lie in the same grid row or in the
+//   same grid column at least two rows away (checked on the host: `rows_ok`), which keeps them at least (warp
+//   distance) + 1 steps behind.
+// ring = the kernel's dynamic shared memory: [D][P] slots of 11 floats per sweep thread; lp = level_ptr copy; zs = the
+// solve vector (shared or global memory).
+template <int MODE, int D, bool kFlags>
+__device__ __noinline__ void sweep_rows(const RowsPlanes pl, const float *ext, int dx, int dy, int P, const int *lp, float *zs,
+                                        int *progress /* shared, [kBicgThreads / 32] */) {
+    constexpr int K = kFlags ? kRowsSkew : 0;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *const r16a = (float4 *)smem_raw;                           // [D][P] values
     float4 *const r16b = r16a + D * P;                                 // [D][P] ILU: reverse values
-    int2 *const r8 = (int2 *)(r16b + D * P);                           // [D][P] far columns
+    int2 *const r8 = (int2 *)(r16b + D * P);                           // [D][P] far positions
     float *const r4 = (float *)(r8 + D * P);                           // [D][P] right-hand side / diagonal
-    float *const zs = kZsSmem ? r4 + D * P : zs_global;                // [n] solve vector / pivots
-    const int t = threadIdx.x, lane = t & 31;
-    const int nl = dx + dy - 1;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int Wn = P >> 5;
+    if (kFlags && t < Wn) progress[t] = 0;
     __syncthreads();
     if (t < P) {
         const bool rowok = t < dy;
-        const int i0 = t * dx;
         const float4 *gval = MODE == 2 ? pl.uval : (MODE == 0 ? pl.alow : pl.lval);
         const int2 *gfar = MODE == 2 ? pl.ufar : pl.lfar;
         const float *gext = MODE == 1 ? ext : (MODE == 0 ? pl.adiag : pl.udiag);
-        // x of this thread at sweep step s
-        auto x_of = [&](int s) { return (MODE == 2 ? nl - 1 - s : s) - t; };
+        // first step of this thread: the wavefront offset of its row plus the warp skew
+        const int sig = MODE == 2 ? (dy - 1 - t) + K * (Wn - 1 - w) : t + K * w;
+        const int S = dx + dy - 1 + K * (Wn - 1);                      // steps of the sweep
+        auto x_of = [&](int s) { return MODE == 2 ? dx - 1 - (s - sig) : s - sig; };
+        // level of step s: the same for every lane of the warp, so its level_ptr entry is one broadcast read, kept in a
+        // register ring (lpv) from the step that issues the prefetch to the steps that compute on it
+        const int nl = dx + dy - 1;
+        const int lev0 = MODE == 2 ? nl - 1 + K * (Wn - 1 - w) : -K * w;
+        auto lev_of = [&](int s) { return MODE == 2 ? lev0 - s : lev0 + s; };
+        int lpv[D];
+#pragma unroll
+        for (int u = 0; u < D; u++) lpv[u] = 0;
         auto issue = [&](int s, int slot) {
-            const int x = x_of(s);
-            if (rowok && s < nl && (unsigned)x < (unsigned)dx) {
-                const int i = i0 + x, k = slot * P + t;
-                cp_async16(r16a + k, gval + i);
-                if (MODE == 0) cp_async16(r16b + k, pl.arv + i);
-                cp_async8(r8 + k, gfar + i);
-                cp_async4(r4 + k, gext + i);
+            const int x = x_of(s), L = lev_of(s);
+            lpv[slot] = lp[min(max(L, 0), nl)];
+            if (rowok && (unsigned)x < (unsigned)dx) {
+                const int q = lpv[slot] + t - max(0, L - dx + 1), k = slot * P + t;
+                cp_async16(r16a + k, gval + q);
+                if (MODE == 0) cp_async16(r16b + k, pl.arv + q);
+                cp_async8(r8 + k, gfar + q);
+                cp_async4(r4 + k, gext + q);
             }
             cp_async_commit();
         };
+        // the one lane of the warp that consumes a value of the neighbouring warp, and that warp's counter
+        const int src_w = MODE == 2 ? w + 1 : w - 1;
+        const bool has_src = MODE == 2 ? (src_w < Wn) : (src_w >= 0);
+        const bool poller = kFlags && has_src && lane == (MODE == 2 ? 31 : 0);
         const bool edge = MODE == 2 ? (lane == 31 && t + 1 < dy) : (lane == 0 && t > 0);
-        const int nb_off = MODE == 2 ? dx : -dx;
+        const int te = MODE == 2 ? t + 1 : t - 1;                      // row of the y-neighbour operand
+        const int *src_prog = progress + (has_src ? src_w : w);
 #pragma unroll
         for (int u = 0; u < D - 1; u++) issue(u, u);
         float prev = 1.0f;                                             // (a finite non-zero stand-in for absent operands)
 #pragma unroll 1
-        for (int s0 = 0; s0 < nl; s0 += D) {
+        for (int s0 = 0; s0 < S; s0 += D) {
 #pragma unroll
             for (int u = 0; u < D; u++) {
                 const int s = s0 + u;
-                issue(s + D - 1, (u + D - 1) % D);
-                cp_async_wait<D - 1>();
-                float nb = MODE == 2 ? __shfl_down_sync(0xffffffffu, prev, 1) : __shfl_up_sync(0xffffffffu, prev, 1);
-                const int x = x_of(s);
-                float res = prev;
-                if (rowok && s < nl && (unsigned)x < (unsigned)dx) {
-                    const int i = i0 + x, k = u * P + t;
-                    const float4 v = r16a[k];
-                    const int2 fc = r8[k];
-                    const float e = r4[k];
-                    if (edge) nb = zs[i + nb_off];
-                    if (MODE == 0) {
-                        // l_ik = a_ik / u_kk, u_ii = a_ii - sum l_ik u_ki, lower entries in ascending column order
-                        const float4 rv = r16b[k];
-                        const float p0 = fc.x >= 0 ? zs[fc.x] : 1.0f, p2 = fc.y >= 0 ? zs[fc.y] : 1.0f;
-                        const float l0 = __fdiv_rn(v.x, p0), l1 = __fdiv_rn(v.y, nb), l2 = __fdiv_rn(v.z, p2), l3 = __fdiv_rn(v.w, prev);
-                        float dg = fmaf(-l0, rv.x, e);
-                        dg = fmaf(-l1, rv.y, dg);
-                        dg = fmaf(-l2, rv.z, dg);
-                        dg = fmaf(-l3, rv.w, dg);
-                        pl.lval[i] = make_float4(l0, l1, l2, l3);
-                        pl.udiag[i] = dg;
-                        res = dg;
-                    } else if (MODE == 1) {
-                        const float f0 = fc.x >= 0 ? zs[fc.x] : 0.0f, f1 = fc.y >= 0 ? zs[fc.y] : 0.0f;
-                        float acc = fmaf(-v.x, f0, e);
-                        acc = fmaf(-v.y, nb, acc);
-                        acc = fmaf(-v.z, f1, acc);
-                        res = fmaf(-v.w, prev, acc);
-                    } else {
-                        const float f0 = fc.x >= 0 ? zs[fc.x] : 0.0f, f1 = fc.y >= 0 ? zs[fc.y] : 0.0f;
-                        float acc = fmaf(-v.x, prev, zs[i]);
-                        acc = fmaf(-v.y, f0, acc);
-                        acc = fmaf(-v.z, nb, acc);
-                        acc = fmaf(-v.w, f1, acc);
-                        res = __fdiv_rn(acc, e);
+                if (s < S) {                                           // uniform per CTA
+                    // progress of the neighbouring warp, read ahead of its use: steps [0, s - K) must be complete
+                    int seen = poller ? ld_flag_shared(src_prog) : 0x7fffffff;
+                    const int lp_edge = lpv[(u + D - 1) % D];          // level_ptr of the previous step's level
+                    issue(s + D - 1, (u + D - 1) % D);
+                    cp_async_wait<D - 1>();
+                    float nb = MODE == 2 ? __shfl_down_sync(0xffffffffu, prev, 1) : __shfl_up_sync(0xffffffffu, prev, 1);
+                    const int x = x_of(s);
+                    if (kFlags) {
+                        const int need = s - K < S ? s - K : S;
+                        while (seen < need) seen = ld_flag_shared(src_prog);
                     }
-                    zs[i] = res;
+                    float res = prev;
+                    if (rowok && (unsigned)x < (unsigned)dx) {
+                        const int L = lev_of(s), k = u * P + t;
+                        const int q = lpv[u] + t - max(0, L - dx + 1);
+                        const int Le = MODE == 2 ? L + 1 : L - 1;       // level of the y-neighbour operand = previous step's
+                        const int qe = edge ? lp_edge + te - max(0, Le - dx + 1) : q;
+                        const float4 v = r16a[k];
+                        const float4 rv = MODE == 0 ? r16b[k] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const int2 fc = r8[k];
+                        const float e = r4[k];
+                        res = sweep_row_step<MODE>(pl, zs, q, qe, edge, nb, prev, v, rv, fc, e);
+                        zs[q] = res;
+                    }
+                    prev = res;
+                    if (kFlags) {
+                        __syncwarp();                                  // the warp's stores of this step precede the counter
+                        if (lane == 0) st_flag_shared(progress + w, s + 1);
+                    } else {
+                        named_bar(1, P);
+                    }
                 }
-                prev = res;
-                named_bar(1, P);
             }
         }
         cp_async_wait<0>();
@@ -748,16 +826,19 @@ __device__ __noinline__ void sweep_rows(const RowsPlanes pl, const float *ext, i
     __syncthreads();
 }
 
-template <bool kZsSmem>
+template <bool kZsSmem, int D>
 __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_rows_kernel(const BicgParams prm) {
     long long tick = clock64();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red[64];
+    __shared__ int s_progress[kBicgThreads / 32];
+    // decoupled-warp sweeps need the solve vector in shared memory; 16: per-level barrier sweeps (A/B measurements)
+    const bool skew = kZsSmem && !(prm.dbg & 16);
     const int sys = blockIdx.x;
     const int sample = sys >> 1, comp = sys & 1;
     const BicgTab &T = prm.tab[comp];
     const int n = T.n, n_max = prm.n_max, dx = T.dx, dy = T.n / T.dx, P = prm.rows_threads;
-    const int tid = threadIdx.x, NT = blockDim.x;
+    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, NW = NT >> 5;
     const int face_off = comp ? prm.tab[0].n : 0;
     const float *values_c = prm.values + (size_t)sample * prm.nnz_total + (comp ? prm.nnz[0] : 0);
     const int nnz_c = prm.nnz[comp];
@@ -772,8 +853,8 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_rows_kernel(const Bi
     pl.adiag = cur;           cur += n_max;
     pl.lval = (float4 *)cur;  cur += 4 * (size_t)n_max;
     pl.uval = (float4 *)cur;  cur += 4 * (size_t)n_max;
-    pl.lfar = T.c_lfar;
-    pl.ufar = T.c_ufar;
+    pl.lfar = T.m_lfar;
+    pl.ufar = T.m_ufar;
     pl.udiag = cur;           cur += n_max;
     float *__restrict__ b = cur;
     float *__restrict__ x = b + n_max;
@@ -784,27 +865,35 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_rows_kernel(const Bi
     float *__restrict__ tt = v + n_max;
     pl.arv = (float4 *)rh;
     float *const zs_g = tt + n_max;                                        // global home of the solve vector (kZsSmem = false)
-    float *const zs = kZsSmem ? (float *)smem_raw + (size_t)kRowsRing * P * 11 : zs_g;   // behind the ring (11 floats per slot)
+    // dynamic shared memory: the ring (11 floats per slot), the level_ptr copy, the solve vector
+    int *const s_lp = (int *)((float *)smem_raw + (size_t)D * P * 11);
+    float *const zs = kZsSmem ? (float *)(s_lp + prm.rows_lp_cap) : zs_g;
+    for (int k = tid; k < dx + dy; k += NT) s_lp[k] = T.level_ptr[k];
+    __syncthreads();
 
-    // ---- setup: ELL values, canonical rows, NaN guard (":245-256") -------------------------------------------
+    // ---- setup: canonical rows, level-major order, NaN guard (":245-256") --------------------------------------
     double nv = 0.0, nb = 0.0;
 #pragma unroll 8
     for (int i = tid; i < nnz_c; i += NT) { const double a = values_c[i]; nv += a * a; }
-    for (int i = tid; i < n; i += NT) {
-        const float bi = rhs_g[i];
-        b[i] = bi; nb += (double)bi * bi;
-        x[i] = x0_g[i];                                               // cublasScopy(x_old -> x) (":261")
-        // canonical rows straight from the host's slot tables
-        const float sg = prm.sign;
-        auto val4 = [&](const int4 s4) {
-            return make_float4(s4.x >= 0 ? sg * values_c[s4.x] : 0.0f, s4.y >= 0 ? sg * values_c[s4.y] : 0.0f,
-                               s4.z >= 0 ? sg * values_c[s4.z] : 0.0f, s4.w >= 0 ? sg * values_c[s4.w] : 0.0f);
-        };
-        pl.alow[i] = val4(T.c_lsrc[i]);
-        pl.arv[i] = val4(T.c_lrev[i]);
-        pl.uval[i] = val4(T.c_usrc[i]);
-        const int ds = T.c_dsrc[i];
-        pl.adiag[i] = ds >= 0 ? sg * values_c[ds] : 1.0f;
+    // rows are visited in the caller's order (coalesced reads of the CSR values and slot tables) and scattered to their
+    // level-major positions
+    for (int t = warp; t < dy; t += NW) {
+        for (int xx = lane; xx < dx; xx += 32) {
+            const int i = t * dx + xx, q = lm_pos(s_lp, dx, t, xx);
+            const float bi = rhs_g[i];
+            b[q] = bi; nb += (double)bi * bi;
+            x[q] = x0_g[i];                                           // cublasScopy(x_old -> x) (":261")
+            const float sg = prm.sign;
+            auto val4 = [&](const int4 s4) {
+                return make_float4(s4.x >= 0 ? sg * values_c[s4.x] : 0.0f, s4.y >= 0 ? sg * values_c[s4.y] : 0.0f,
+                                   s4.z >= 0 ? sg * values_c[s4.z] : 0.0f, s4.w >= 0 ? sg * values_c[s4.w] : 0.0f);
+            };
+            pl.alow[q] = val4(T.c_lsrc[i]);
+            pl.arv[q] = val4(T.c_lrev[i]);
+            pl.uval[q] = val4(T.c_usrc[i]);
+            const int ds = T.c_dsrc[i];
+            pl.adiag[q] = ds >= 0 ? sg * values_c[ds] : 1.0f;
+        }
     }
     block_sum2(nv, nb, red);
     int warn = (isnan((float)sqrt(nv)) || isnan((float)sqrt(nb))) ? 1 : 0;
@@ -815,48 +904,58 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_rows_kernel(const Bi
         // factor reuse: the pivots d of the solve with the other orientation of this matrix are given, and
         // ILU(0)(M^T) = (U^T D^-1)(D L^T): l'_ik = m_ik / d_k, upper entries unchanged, pivots d -- a parallel pass
         // instead of the wavefront sweep (same division as the sweep, MODE 0 of sweep_rows)
-        const float *d_in = prm.pivots_in + (size_t)sample * prm.n_face + face_off;
+        const float *d_in = prm.pivots_in + (size_t)sample * prm.n_face + face_off;      // caller's row order
         __syncthreads();
-        for (int i = tid; i < n; i += NT) {
-            const float4 a = pl.alow[i];
-            const int2 fc = pl.lfar[i];
-            const float p0 = fc.x >= 0 ? d_in[fc.x] : 1.0f, p2 = fc.y >= 0 ? d_in[fc.y] : 1.0f;
-            const float p1 = i - dx >= 0 ? d_in[i - dx] : 1.0f, p3 = i >= 1 ? d_in[i - 1] : 1.0f;
-            pl.lval[i] = make_float4(__fdiv_rn(a.x, p0), __fdiv_rn(a.y, p1), __fdiv_rn(a.z, p2), __fdiv_rn(a.w, p3));
-            pl.udiag[i] = d_in[i];
+        for (int t = warp; t < dy; t += NW) {
+            for (int xx = lane; xx < dx; xx += 32) {
+                const int i = t * dx + xx, q = lm_pos(s_lp, dx, t, xx);
+                const float4 a = pl.alow[q];
+                const int2 fc = T.c_lfar[i];
+                const float p0 = fc.x >= 0 ? d_in[fc.x] : 1.0f, p2 = fc.y >= 0 ? d_in[fc.y] : 1.0f;
+                const float p1 = i - dx >= 0 ? d_in[i - dx] : 1.0f, p3 = i >= 1 ? d_in[i - 1] : 1.0f;
+                pl.lval[q] = make_float4(__fdiv_rn(a.x, p0), __fdiv_rn(a.y, p1), __fdiv_rn(a.z, p2), __fdiv_rn(a.w, p3));
+                pl.udiag[q] = d_in[i];
+            }
         }
         __syncthreads();
     } else {
-        sweep_rows<0, kZsSmem>(pl, nullptr, dx, dy, P, zs_g);
+        if (skew) sweep_rows<0, D, true>(pl, nullptr, dx, dy, P, s_lp, zs, s_progress);
+        else sweep_rows<0, D, false>(pl, nullptr, dx, dy, P, s_lp, zs, s_progress);
         if (prm.pivots_out) {
             float *d_out = prm.pivots_out + (size_t)sample * prm.n_face + face_off;
-            for (int i = tid; i < n; i += NT) d_out[i] = pl.udiag[i];
+            for (int t = warp; t < dy; t += NW)
+                for (int xx = lane; xx < dx; xx += 32) d_out[t * dx + xx] = pl.udiag[lm_pos(s_lp, dx, t, xx)];
         }
     }
     DPISO_TICK(1);
 
     auto precondition = [&](const float *src) {                      // zs = U^-1 L^-1 src   (csrsv2 x2, ":321-327")
-        sweep_rows<1, kZsSmem>(pl, src, dx, dy, P, zs_g);
-        sweep_rows<2, kZsSmem>(pl, nullptr, dx, dy, P, zs_g);
+        if (skew) {
+            sweep_rows<1, D, true>(pl, src, dx, dy, P, s_lp, zs, s_progress);
+            sweep_rows<2, D, true>(pl, nullptr, dx, dy, P, s_lp, zs, s_progress);
+        } else {
+            sweep_rows<1, D, false>(pl, src, dx, dy, P, s_lp, zs, s_progress);
+            sweep_rows<2, D, false>(pl, nullptr, dx, dy, P, s_lp, zs, s_progress);
+        }
     };
-    // CsrmvEx row straight from the canonical planes: lower slots, diagonal, upper slots = ascending column order; the
-    // x- and y-neighbour columns are i -+ 1 and i -+ dx (absent slots carry a zero coefficient and a clamped index), only
-    // the periodic wrap entries need their column from the far tables.  One row per lane: coalesced float4 loads,
-    // conflict-free shared-memory gathers, no ELL value / index planes.
-    auto spmv_row = [&](const float *vec, int i) {
-        const float4 lo = pl.alow[i], up = pl.uval[i];
-        const float dg = pl.adiag[i];
-        const int2 lf = pl.lfar[i], uf = pl.ufar[i];
+    // CsrmvEx row from the canonical planes: lower slots, diagonal, upper slots = ascending column order; the positions
+    // of the regular neighbours come from the static table m_nbr (absent slots carry a zero coefficient and point at the
+    // row itself), the periodic wrap entries from the far tables.  One row per lane: coalesced loads.
+    auto spmv_row = [&](const float *vec, int q) {
+        const float4 lo = pl.alow[q], up = pl.uval[q];
+        const float dg = pl.adiag[q];
+        const int4 nq = T.m_nbr[q];                                  // x-1, y-1, x+1, y+1
+        const int2 lf = pl.lfar[q], uf = pl.ufar[q];
         const float l0 = lf.x >= 0 ? vec[lf.x] : 0.0f, l2 = lf.y >= 0 ? vec[lf.y] : 0.0f;
         const float u1 = uf.x >= 0 ? vec[uf.x] : 0.0f, u3 = uf.y >= 0 ? vec[uf.y] : 0.0f;
         float acc = fmaf(lo.x, l0, 0.0f);
-        acc = fmaf(lo.y, vec[i - dx > 0 ? i - dx : 0], acc);
+        acc = fmaf(lo.y, vec[nq.y], acc);
         acc = fmaf(lo.z, l2, acc);
-        acc = fmaf(lo.w, vec[i > 0 ? i - 1 : 0], acc);
-        acc = fmaf(dg, vec[i], acc);
-        acc = fmaf(up.x, vec[i + 1 < n ? i + 1 : i], acc);
+        acc = fmaf(lo.w, vec[nq.x], acc);
+        acc = fmaf(dg, vec[q], acc);
+        acc = fmaf(up.x, vec[nq.z], acc);
         acc = fmaf(up.y, u1, acc);
-        acc = fmaf(up.z, vec[i + dx < n ? i + dx : i], acc);
+        acc = fmaf(up.z, vec[nq.w], acc);
         acc = fmaf(up.w, u3, acc);
         return acc;
     };
@@ -974,7 +1073,8 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_rows_kernel(const Bi
     }
     __syncthreads();
     DPISO_TICK(4);
-    for (int q = tid; q < n; q += NT) x_g[q] = x[q];
+    for (int t = warp; t < dy; t += NW)                              // back to the caller's row order
+        for (int xx = lane; xx < dx; xx += 32) x_g[t * dx + xx] = x[lm_pos(s_lp, dx, t, xx)];
     if (tid == 0) {
         int *st = prm.stats + (size_t)sys * 4;
         st[0] = it_count; st[1] = restarts; st[2] = warn; st[3] = exit_kind;
@@ -995,6 +1095,7 @@ static void to_tab(const dpiso_bicg_tables *h, BicgTab &t) {
     t.r_col = h->r_col; t.r_src = h->r_src; t.r_rev = h->r_rev;
     t.c_lsrc = (const int4 *)h->c_lsrc; t.c_lrev = (const int4 *)h->c_lrev; t.c_usrc = (const int4 *)h->c_usrc;
     t.c_lfar = (const int2 *)h->c_lfar; t.c_ufar = (const int2 *)h->c_ufar; t.c_dsrc = h->c_dsrc;
+    t.m_nbr = (const int4 *)h->m_nbr; t.m_lfar = (const int2 *)h->m_lfar; t.m_ufar = (const int2 *)h->m_ufar;
 }
 
 extern "C" {
@@ -1016,11 +1117,12 @@ static int g_reuse_always = 0;
 static int g_bicg_dbg = -1;          // >= 0 overrides DPISO_BICG_DBG (tests force the level-major kernel with 8)
 
 static bool rows_kernel_applies(const dpiso_bicg_tables *h_tab_u, const dpiso_bicg_tables *h_tab_v, int *p_rows) {
-    if (!(h_tab_u->rows_ok && h_tab_v->rows_ok && h_tab_u->c_lsrc && h_tab_v->c_lsrc && h_tab_u->dx > 0 && h_tab_v->dx > 0))
+    if (!(h_tab_u->rows_ok && h_tab_v->rows_ok && h_tab_u->c_lsrc && h_tab_v->c_lsrc && h_tab_u->m_nbr && h_tab_v->m_nbr &&
+          h_tab_u->dx > 0 && h_tab_v->dx > 0))
         return false;
     const int dy_u = h_tab_u->n / h_tab_u->dx, dy_v = h_tab_v->n / h_tab_v->dx;
     const int Pr = ((dy_u > dy_v ? dy_u : dy_v) + 31) & ~31;
-    const size_t ring = (size_t)kRowsRing * Pr * 11 * sizeof(float);
+    const size_t ring = (size_t)kRowsRing * Pr * 11 * sizeof(float);       // the shallow ring must fit
     if (p_rows) *p_rows = Pr;
     return Pr <= kBicgThreads && ring <= 200 * 1024;
 }
@@ -1102,24 +1204,37 @@ int dpiso_bicgstab_ilu(int batch, const dpiso_bicg_tables *h_tab_u, const dpiso_
     prm.rows_kernel = 0;
     int Pr = 0;
     if (rows_kernel_applies(h_tab_u, h_tab_v, &Pr) && !(prm.dbg & 8)) {
-        const size_t ring = (size_t)kRowsRing * Pr * 11 * sizeof(float);
-        const size_t need_smem = ring + (size_t)prm.n_max * sizeof(float);
+        // the solve vector joins the ring in shared memory if it fits
+        const size_t ring8 = (size_t)kRowsRing * Pr * 11 * sizeof(float), ring16 = 2 * ring8;
+        prm.rows_lp_cap = (n_levels + 1 + 3) & ~3;
+        const size_t zs_bytes_r = (size_t)prm.n_max * sizeof(float) + (size_t)prm.rows_lp_cap * sizeof(int);   // + level_ptr copy
+        // 8 levels in flight cover the latency; 16 measured slower with coalesced streams (0.98 M vs 1.25 M cycles)
+        int depth = 8;
+        const bool zs_smem = ring8 + zs_bytes_r <= kBudget;         // else the solve vector stays in global memory (L2)
+        if ((prm.dbg & 32) && ring16 + zs_bytes_r <= kBudget) depth = 16;               // A/B: deep ring
+        const size_t ring = depth == 16 ? ring16 : ring8;
+        const size_t need_smem = ring + (zs_smem ? zs_bytes_r : (size_t)prm.rows_lp_cap * sizeof(int));
         {
             prm.pivots_out = pivots_out; prm.pivots_in = pivots_in;
             prm.reuse_mask = g_reuse_always ? 3 : ((h_tab_u->sym ? 1 : 0) | (h_tab_v->sym ? 2 : 0));
-            const bool zs_smem = need_smem <= kBudget;              // else the solve vector stays in global memory (L2)
             prm.rows_kernel = 1;
             prm.rows_threads = Pr;
             static unsigned long long rows_attr_mask = 0;
             int dev = 0;
             DPISO_CUDA_TRY(cudaGetDevice(&dev));
             if (dev >= 64 || !(rows_attr_mask & (1ull << dev))) {
-                DPISO_CUDA_TRY(cudaFuncSetAttribute(bicgstab_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 1024));
-                DPISO_CUDA_TRY(cudaFuncSetAttribute(bicgstab_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 1024));
+                DPISO_CUDA_TRY(cudaFuncSetAttribute(bicgstab_rows_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+                DPISO_CUDA_TRY(cudaFuncSetAttribute(bicgstab_rows_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+                DPISO_CUDA_TRY(cudaFuncSetAttribute(bicgstab_rows_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+                DPISO_CUDA_TRY(cudaFuncSetAttribute(bicgstab_rows_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
                 if (dev < 64) rows_attr_mask |= 1ull << dev;
             }
-            if (zs_smem) bicgstab_rows_kernel<true><<<batch * 2, kBicgThreads, need_smem, (cudaStream_t)stream>>>(prm);
-            else bicgstab_rows_kernel<false><<<batch * 2, kBicgThreads, ring, (cudaStream_t)stream>>>(prm);
+            const dim3 grid(batch * 2), block(kBicgThreads);
+            cudaStream_t st = (cudaStream_t)stream;
+            if (zs_smem && depth == 16) bicgstab_rows_kernel<true, 16><<<grid, block, need_smem, st>>>(prm);
+            else if (zs_smem) bicgstab_rows_kernel<true, 8><<<grid, block, need_smem, st>>>(prm);
+            else if (depth == 16) bicgstab_rows_kernel<false, 16><<<grid, block, need_smem, st>>>(prm);
+            else bicgstab_rows_kernel<false, 8><<<grid, block, need_smem, st>>>(prm);
             DPISO_CHECK_LAUNCH();
             return DPISO_OK;
         }

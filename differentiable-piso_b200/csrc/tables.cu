@@ -29,7 +29,7 @@ struct Entry { int col, src; };
 struct HostTables {
     int n = 0, n_levels = 0, wa = 0, max_level = 0, wl = 0, wu = 0, dx = 0, rows_ok = 0, sym = 0;
     std::vector<int> level_ptr, perm, a_col, a_src, a_rev, r_col, r_src, r_rev;
-    std::vector<int> c_lsrc, c_lrev, c_usrc, c_lfar, c_ufar, c_dsrc;
+    std::vector<int> c_lsrc, c_lrev, c_usrc, c_lfar, c_ufar, c_dsrc, m_nbr, m_lfar, m_ufar;
 };
 
 // CSR value index of M(row, col), -1 if (row, col) is not an entry
@@ -152,6 +152,10 @@ int build_tables(int ny, int nx, int per_x, int per_y, int comp, int transpose, 
             else kind = !regular ? (c > i + Dx ? 7 : 5) : (c == i + Dx ? 6 : 4);
             if (used[kind]++) rows_ok = 0;
             if (!regular && std::abs(level_of(c) - level_of(i)) < 2) rows_ok = 0;
+            // decoupled-warp sweeps: a far operand lies in the same grid row (same sweep thread) or in the same grid column
+            if (!regular && c / Dx != i / Dx && c % Dx != i % Dx) rows_ok = 0;
+            // ... and, when it comes from another row, from at least three rows away (it is fetched one step ahead of its use)
+            if (!regular && c / Dx != i / Dx && std::abs(c / Dx - i / Dx) < 3) rows_ok = 0;
         }
     }
     t.rows_ok = rows_ok;
@@ -175,23 +179,39 @@ int build_tables(int ny, int nx, int per_x, int per_y, int comp, int transpose, 
             }
         }
     }
+    // level-major positions for the row-major kernel's planes / vectors
+    t.m_nbr.assign((size_t)n * 4, 0); t.m_lfar.assign((size_t)n * 2, -1); t.m_ufar.assign((size_t)n * 2, -1);
+    for (int q = 0; q < n; q++) {
+        const int i = t.perm[q], lx = i % Dx, ly = i / Dx;
+        t.m_nbr[(size_t)q * 4 + 0] = lx > 0 ? pos[i - 1] : q;
+        t.m_nbr[(size_t)q * 4 + 1] = ly > 0 ? pos[i - Dx] : q;
+        t.m_nbr[(size_t)q * 4 + 2] = lx < Dx - 1 ? pos[i + 1] : q;
+        t.m_nbr[(size_t)q * 4 + 3] = ly < Dy - 1 ? pos[i + Dx] : q;
+        if (rows_ok)
+            for (int k = 0; k < 2; k++) {
+                const int cl = t.c_lfar[(size_t)i * 2 + k], cu = t.c_ufar[(size_t)i * 2 + k];
+                t.m_lfar[(size_t)q * 2 + k] = cl >= 0 ? pos[cl] : -1;
+                t.m_ufar[(size_t)q * 2 + k] = cu >= 0 ? pos[cu] : -1;
+            }
+    }
     return DPISO_OK;
 }
 
 // all integer tables of one component, packed back to back (one allocation); offsets in ints
 struct Packed {
     std::vector<int> data;
-    size_t off[14];
+    size_t off[17];
 };
 
 Packed pack(const HostTables &t) {
     Packed p;
-    const std::vector<int> *v[14] = {&t.level_ptr, &t.perm, &t.a_col, &t.a_src, &t.a_rev, &t.r_col, &t.r_src, &t.r_rev,
-                                     &t.c_lsrc, &t.c_lrev, &t.c_usrc, &t.c_lfar, &t.c_ufar, &t.c_dsrc};
+    const std::vector<int> *v[17] = {&t.level_ptr, &t.perm, &t.a_col, &t.a_src, &t.a_rev, &t.r_col, &t.r_src, &t.r_rev,
+                                     &t.c_lsrc, &t.c_lrev, &t.c_usrc, &t.c_lfar, &t.c_ufar, &t.c_dsrc, &t.m_nbr, &t.m_lfar,
+                                     &t.m_ufar};
     size_t total = 0;
-    for (int k = 0; k < 14; k++) { p.off[k] = total; total += (v[k]->size() + 3) & ~(size_t)3; }   // 16-byte aligned pieces
+    for (int k = 0; k < 17; k++) { p.off[k] = total; total += (v[k]->size() + 3) & ~(size_t)3; }   // 16-byte aligned pieces
     p.data.assign(total, 0);
-    for (int k = 0; k < 14; k++) std::copy(v[k]->begin(), v[k]->end(), p.data.begin() + p.off[k]);
+    for (int k = 0; k < 17; k++) std::copy(v[k]->begin(), v[k]->end(), p.data.begin() + p.off[k]);
     return p;
 }
 
@@ -202,6 +222,7 @@ void fill_struct(const HostTables &t, const Packed &p, const int *base, dpiso_bi
     out->a_rev = base + p.off[4]; out->r_col = base + p.off[5]; out->r_src = base + p.off[6]; out->r_rev = base + p.off[7];
     out->c_lsrc = base + p.off[8]; out->c_lrev = base + p.off[9]; out->c_usrc = base + p.off[10];
     out->c_lfar = base + p.off[11]; out->c_ufar = base + p.off[12]; out->c_dsrc = base + p.off[13];
+    out->m_nbr = base + p.off[14]; out->m_lfar = base + p.off[15]; out->m_ufar = base + p.off[16];
 }
 
 }  // namespace

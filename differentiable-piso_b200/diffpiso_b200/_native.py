@@ -36,7 +36,8 @@ class BicgTables(C.Structure):
                 ("perm", C.c_void_p), ("a_col", C.c_void_p), ("a_src", C.c_void_p), ("a_rev", C.c_void_p),
                 ("r_col", C.c_void_p), ("r_src", C.c_void_p), ("r_rev", C.c_void_p), ("c_lsrc", C.c_void_p),
                 ("c_lrev", C.c_void_p), ("c_usrc", C.c_void_p), ("c_lfar", C.c_void_p), ("c_ufar", C.c_void_p),
-                ("c_dsrc", C.c_void_p), ("owner", C.c_void_p), ("owner_is_host", C.c_int), ("sym", C.c_int)]
+                ("c_dsrc", C.c_void_p), ("m_nbr", C.c_void_p), ("m_lfar", C.c_void_p), ("m_ufar", C.c_void_p),
+                ("owner", C.c_void_p), ("owner_is_host", C.c_int), ("sym", C.c_int)]
 
 
 _I, _F, _P, _SZ = C.c_int, C.c_float, C.c_void_p, C.c_size_t

@@ -154,6 +154,14 @@ def bicg_tables(ny, nx, per_x, per_y, comp, transpose):
     # the sweeps read far operands one level ahead of their use: they must be at least two levels old
     if far.any() and int(np.abs(level[ci[far]] - level[row_of[far]]).min()) < 2:
         rows_ok = 0
+    # decoupled-warp sweeps: a far operand lies in the same grid row (same sweep thread) or in the same grid column
+    if far.any() and not np.all((ly[ci[far]] == ly[row_of[far]]) | (lx[ci[far]] == lx[row_of[far]])):
+        rows_ok = 0
+    # ... and, when it comes from another row, from at least three rows away (it is fetched one step ahead of its use)
+    if far.any():
+        drow = np.abs(ly[ci[far]] - ly[row_of[far]])
+        if np.any((drow > 0) & (drow < 3)):
+            rows_ok = 0
     # canonical source tables of the row-major kernel: CSR value index of every slot (-1 = absent), reverse entries of the
     # lower slots, the pivot's index, and the columns of the far slots
     c_lsrc = np.full((n, 4), -1, np.int32); c_lrev = np.full((n, 4), -1, np.int32); c_usrc = np.full((n, 4), -1, np.int32)
@@ -169,12 +177,24 @@ def bicg_tables(ny, nx, per_x, per_y, comp, transpose):
         c_ufar[row_of[fu], (slot_kind[fu] - 4) // 2] = ci[fu]
         dg_e = ci == row_of
         c_dsrc[row_of[dg_e]] = src[dg_e]
+    # level-major positions for the row-major kernel: regular neighbours (x-1, y-1, x+1, y+1; the row itself where absent)
+    # and the far slots
+    orig = perm
+    olx, oly = lx[orig], ly[orig]
+    qq = np.arange(n, dtype=np.int64)
+    m_nbr = np.stack([np.where(olx > 0, pos[np.maximum(orig - 1, 0)], qq),
+                      np.where(oly > 0, pos[np.maximum(orig - Dx, 0)], qq),
+                      np.where(olx < Dx - 1, pos[np.minimum(orig + 1, n - 1)], qq),
+                      np.where(oly < Dy - 1, pos[np.minimum(orig + Dx, n - 1)], qq)], axis=1).astype(np.int32)
+    m_lfar = np.where(c_lfar[orig] >= 0, pos[np.maximum(c_lfar[orig], 0)], -1).astype(np.int32)
+    m_ufar = np.where(c_ufar[orig] >= 0, pos[np.maximum(c_ufar[orig], 0)], -1).astype(np.int32)
     wl = int(np.bincount(row_of[lower], minlength=n).max()) if lower.any() else 0
     wu = int(np.bincount(row_of[upper], minlength=n).max()) if upper.any() else 0
     return dict(n=n, n_levels=int(counts.size), wa=wa, max_level=int(counts.max()), wl=wl, wu=wu, dx=int(Dx), rows_ok=rows_ok,
                 r_col=np.ascontiguousarray(np.where(col_e >= 0, col_e, rows_all[None, :]), np.int32),
                 r_src=np.ascontiguousarray(src_e, np.int32), r_rev=np.ascontiguousarray(rev_e, np.int32),
                 c_lsrc=c_lsrc, c_lrev=c_lrev, c_usrc=c_usrc, c_lfar=c_lfar, c_ufar=c_ufar, c_dsrc=c_dsrc,
+                m_nbr=m_nbr, m_lfar=m_lfar, m_ufar=m_ufar,
                 level_ptr=level_ptr.astype(np.int32), perm=perm.astype(np.int32),
                 a_col=np.ascontiguousarray(a_col, np.int32), a_src=np.ascontiguousarray(a_src, np.int32),
                 a_rev=np.ascontiguousarray(a_rev, np.int32), nnz=int(a.nnz))

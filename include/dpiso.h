@@ -144,6 +144,11 @@ typedef struct {
     const int *c_lfar;    /* int[n][2] column of the two far lower slots, -1 = absent */
     const int *c_ufar;    /* int[n][2] column of the two far upper slots */
     const int *c_dsrc;    /* int[n]    CSR value index of the diagonal entry */
+    /* level-major positions (the row-major kernel stores its planes and vectors level by level so that the wavefront
+     * sweeps read consecutive addresses): all [n] indexed by level-major position q */
+    const int *m_nbr;     /* int[n][4] positions of the regular neighbours (x-1, y-1, x+1, y+1), q itself where absent */
+    const int *m_lfar;    /* int[n][2] positions of the two far lower slots, -1 = absent */
+    const int *m_ufar;    /* int[n][2] positions of the two far upper slots, -1 = absent */
     void *owner;          /* allocation behind the arrays when built by dpiso_bicg_tables_create*, else NULL */
     int owner_is_host;    /* 1: `owner` is host memory (dpiso_bicg_tables_create_host) */
     int sym;              /* 1: the pattern is structurally symmetric (every entry has its reverse entry): ILU(0)(M^T)

@@ -23,6 +23,12 @@ def main():
     neg = torch.neg(values)
     out = {}
     max_it = int(os.environ.get('BICG_MAXIT', '10000'))
+    dbg = int(os.environ.get('BICG_DBG', '-1'))       # 16: per-level barrier sweeps, 32: shallow ring, 8: level-major kernel
+    ref = {}
+    if dbg >= 0:                                       # results of the default configuration, for a bit-for-bit comparison
+        for tr in (False, True):
+            ref[tr] = ops.bicgstab_ilu(g, neg, rhs, vel, 1e-8, max_it, tr)[0].clone()
+    N.lib.dpiso_bicgstab_set_debug(dbg)
     for tr in (False, True):
         cnt = torch.zeros(8, dtype=torch.int64, device=dev)
         x, st, w = ops.bicgstab_ilu(g, neg, rhs, vel, 1e-8, max_it, tr)
@@ -35,5 +41,7 @@ def main():
         c = cnt.cpu().numpy()
         out["transpose" if tr else "forward"] = {"ms": e0.elapsed_time(e1), "iterations": st.cpu().numpy()[0, :, 0].tolist(),
             "cycles_setup": int(c[0]), "cycles_ilu": int(c[1]), "cycles_sweeps": int(c[2]), "cycles_stream": int(c[4])}
+        if dbg >= 0:
+            out["transpose" if tr else "forward"]["bit_equal_to_default"] = bool(torch.equal(x, ref[tr]))
     print(json.dumps(out))
 main()

@@ -308,7 +308,7 @@ def test_native_table_builder_equals_numpy_derivation(ny, nx, per_x, per_y):
                 n, wa = st.n, st.wa
                 shapes = dict(level_ptr=st.n_levels + 1, perm=n, a_col=wa * n, a_src=wa * n, a_rev=wa * n, r_col=wa * n,
                               r_src=wa * n, r_rev=wa * n, c_lsrc=4 * n, c_lrev=4 * n, c_usrc=4 * n, c_lfar=2 * n,
-                              c_ufar=2 * n, c_dsrc=n)
+                              c_ufar=2 * n, c_dsrc=n, m_nbr=4 * n, m_lfar=2 * n, m_ufar=2 * n)
                 for k, size in shapes.items():
                     got = np.ctypeslib.as_array(C.cast(getattr(st, k), C.POINTER(C.c_int)), shape=(size,))
                     assert np.array_equal(got, np.asarray(want[k]).ravel()), (k, comp, transpose)

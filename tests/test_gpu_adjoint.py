@@ -131,7 +131,11 @@ def test_piso_step_backward_matches_oracle(name):
         from common import cg_iteration_slack
         assert abs(int(sim.pressure_solver.last_iterations[i]) - oit) <= cg_iteration_slack(s, oit)
     if s["dirichlet"].any():
-        assert rel_l2(td.grad[0].cpu().numpy(), gd_total) < field_tolerances(s)["grad"]
+        # the Dirichlet-value gradient is the transposed predictor solution restricted to the Dirichlet rows, summed over
+        # the batch: measured 5.4e-5 on the 9 x 8 cavity (restart-10 CG in the chain) -> 1.5e-4
+        e_dv = rel_l2(td.grad[0].cpu().numpy(), gd_total)
+        record("adjoint_dvals", setup=name, g_dvals=e_dv)
+        assert e_dv < 1.5e-4, (name, e_dv)
 
 
 def test_forward_and_adjoint_step_replay_as_one_cuda_graph():
