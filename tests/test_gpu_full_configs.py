@@ -271,13 +271,18 @@ def test_c2_rollout_1000_steps_statistics_within_one_percent():
 
 def test_c5_1024_forward_and_adjoint_one_sample_matches_oracle():
     """BASELINE configs[4]: one periodic 1024 x 1024 sample, forward + adjoint of one step against the oracle.  A
-    converged pressure solve takes ~1700 iterations per solve here (minutes of CPU for the oracle's four solves), so both
-    sides run the SAME fixed budget of 300 CG iterations per solve: identical arithmetic, no stopping-test ambiguity,
-    about a minute of CPU.  Convergence at this size is covered by test_config5_large_periodic_grid_properties."""
+    converged pressure solve takes ~2200 iterations here and the adjoint solves run into max_it = 10000 (7 minutes of CPU
+    for the oracle's four solves), so both sides run the SAME fixed budget of CG iterations per solve: identical
+    arithmetic, no stopping-test ambiguity.  The budget is 25 iterations (5 checks): the reference's CG with the rank-1
+    shift is so rounding sensitive at this size that a 1e-16 relative perturbation of the right-hand side moves the
+    UNCONVERGED iterate by 2e-6 after 50 iterations and by 1.3e-2 after 300 (measured with the oracle alone, 512^2;
+    a 300-iteration budget gave 1.9e-4 in the velocity between this kernel and the oracle) -- unconverged iterates beyond a
+    few dozen iterations are not comparable between ANY two implementations.  Convergence at this size is covered by
+    test_config5_large_periodic_grid_properties."""
     from common import record
     from diffpiso_b200 import setups as SU
     from oracle import adjoint as A
-    s = SU.periodic_box(1024, 1024, visc=1e-3, cg_max_it=300)
+    s = SU.periodic_box(1024, 1024, visc=1e-3, cg_max_it=25)
     sim = build_sim(s)
     v0, p0 = random_fields(s, 4321)
     w_u, w_p = _adjoint_weights(s, 1, 33)
@@ -290,6 +295,5 @@ def test_c5_1024_forward_and_adjoint_one_sample_matches_oracle():
     record("c5_1024_fwd_adjoint", bicg_it=[int(bicg[0, 0, 0]), int(bicg[0, 1, 0])], bicg_it_oracle=[st["bicg_u"][0], st["bicg_v"][0]],
            cg_it_oracle=[st["cg1"], st["cg2"]] + list(ref["stats"]["cg_adj"]), **e)
     assert abs(int(bicg[0, 0, 0]) - st["bicg_u"][0]) <= 1 and abs(int(bicg[0, 1, 0]) - st["bicg_v"][0]) <= 1
-    # the L-inf stopping test at 1e-8 leaves smooth-mode errors ~ tol / lambda_min ~ tol * N^2 in the pressure
-    assert e["vel"] < 1e-5 and e["g_vel"] < 1e-3, e
-    assert e["pres"] < 1e-3 and e["g_pres"] < 1e-3, e
+    assert e["vel"] < 1e-5 and e["g_vel"] < 1e-5, e
+    assert e["pres"] < 1e-5 and e["g_pres"] < 1e-5, e
