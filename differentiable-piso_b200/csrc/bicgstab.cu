@@ -21,74 +21,9 @@
 // factorises again, ":113-134"); the kernels are identical.
 #include <cstdlib>
 
-#include "rows.cuh"
+#include "bicgstab.cuh"
 
 namespace dpiso {
-
-constexpr int kBicgThreads = 512;
-constexpr int kMaxWa = 6;
-
-struct BicgTab {
-    int n, n_levels, wa, max_level, wl, wu, dx, rows_ok;
-    const int *level_ptr, *perm, *a_col, *a_src, *a_rev, *r_col, *r_src, *r_rev;
-    const int4 *c_lsrc, *c_lrev, *c_usrc;
-    const int2 *c_lfar, *c_ufar;
-    const int *c_dsrc;
-    const int4 *m_nbr;
-    const int2 *m_lfar, *m_ufar;
-};
-
-struct BicgParams {
-    BicgTab tab[2];
-    int nnz[2];            // CSR entries of component 0, 1
-    int n_face;            // n_u + n_v
-    int nnz_total;
-    int n_max;             // max(n_u, n_v): plane stride inside the workspace
-    int zs_in_smem;
-    size_t ws_floats;      // per system
-    int stage_rows;        // rows per stage buffer (0 = staged fast path disabled)
-    int lp_cap;            // ints reserved for the level_ptr copy in smem
-    int compact;           // rows have <= 4 lower and <= 4 upper entries: compact triangular sweeps
-    int ring_depth;        // levels in flight in the cp.async ring (16, 8 or 2)
-    int rows_kernel;       // 1: bicgstab_rows_kernel (row-major layout, one thread per grid row in the sweeps)
-    int rows_threads;      // its sweep threads P = roundup32(max dy)
-    int rows_lp_cap;       // ints reserved for its level_ptr copy in shared memory
-    int dbg;               // profiling experiments only (DPISO_BICG_DBG): 1 skip level barrier, 2 skip refill, 4 skip recurrence
-                           // (level-major kernel); 8 force the level-major kernel
-    const float *values, *rhs, *x0;
-    float sign;            // +1 / -1: the solve runs on sign * values (piso_tf.py:42 passes -M)
-    float *x;
-    int *stats;
-    float *warn;
-    float *pivots_out;     // optional [batch][n_face]: ILU(0) pivots of this solve (row-major kernel)
-    const float *pivots_in; // optional [batch][n_face]: pivots of the other orientation -> no factorisation sweep
-    int reuse_mask;        // bit c: component c takes pivots_in
-    float *workspace;
-    float tol;
-    int max_it;
-    long long *timing;     // optional [8] cycle counters of system 0 (debug / profiling), may be NULL
-};
-
-__device__ __forceinline__ double warp_sum_d(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-// block-wide sum of two doubles, result broadcast to every thread (2 barriers)
-__device__ __forceinline__ void block_sum2(double &a, double &b, double *scratch /* [64] */) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    a = warp_sum_d(a); b = warp_sum_d(b);
-    __syncthreads();                      // scratch free (previous result consumed)
-    if (lane == 0) { scratch[warp] = a; scratch[32 + warp] = b; }
-    __syncthreads();
-    double va = lane < nw ? scratch[lane] : 0.0, vb = lane < nw ? scratch[32 + lane] : 0.0;
-    a = warp_sum_d(va); b = warp_sum_d(vb);
-}
-
-__device__ __forceinline__ void named_bar(int id, int count) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
 
 struct RowRegs {
     int q;                 // row (level-major position) handled by this thread in this level, -1 = none
@@ -307,18 +242,6 @@ struct CompactPlanes {
     const float4 *lval, *uval;      // [n]
     const float *udiag;             // [n]
 };
-
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <int MODE, bool kZsSmem, int D>
 __device__ __noinline__ void wavefront_ring(const BicgTab &T, int lp_cap, const CompactPlanes cp, const float *in,
@@ -650,23 +573,6 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_kernel(const BicgPar
 // ===============================================================================================================
 constexpr int kRowsRing = 8;
 constexpr int kRowsSkew = 2;
-
-struct RowsPlanes {
-    float4 *alow;      // [n] A lower values in canonical slots (kept: the SpMV reads them)
-    float *adiag;      // [n] A diagonal (kept)
-    float4 *lval;      // [n] l_ik (written by the ILU sweep)
-    float4 *arv;       // [n] ILU only: reverse entries u_ki = A(k, i) of the lower slots (aliases rh, p, v, tt)
-    const int2 *lfar;  // [n] positions of the two far lower slots, -1 = absent (static table, shared by all systems)
-    float4 *uval;      // [n] upper values (unchanged by ILU(0) on this pattern)
-    const int2 *ufar;  // [n]
-    float *udiag;      // [n] pivots (written by the ILU sweep)
-};
-
-// level-major position of grid point (row t, column x); lp = level_ptr (shared-memory copy)
-__device__ __forceinline__ int lm_pos(const int *lp, int dx, int t, int x) {
-    const int L = x + t;
-    return lp[L] + t - max(0, L - dx + 1);
-}
 
 // One row of a sweep, branch-free: absent slots carry a zero coefficient and a clamped position, so their operand is
 // loaded unconditionally and selected afterwards.  fma order = ascending column of the row.
@@ -1129,7 +1035,7 @@ static bool rows_kernel_applies(const dpiso_bicg_tables *h_tab_u, const dpiso_bi
 
 int dpiso_bicgstab_supports_factor_reuse(const dpiso_bicg_tables *h_tab_u, const dpiso_bicg_tables *h_tab_v) {
     if (!h_tab_u || !h_tab_v) return 0;
-    return rows_kernel_applies(h_tab_u, h_tab_v, nullptr) ? 1 : 0;
+    return (rows_kernel_applies(h_tab_u, h_tab_v, nullptr) || (h_tab_u->band_ok && h_tab_v->band_ok)) ? 1 : 0;
 }
 
 int dpiso_bicgstab_set_debug(int dbg) {
@@ -1203,6 +1109,13 @@ int dpiso_bicgstab_ilu(int batch, const dpiso_bicg_tables *h_tab_u, const dpiso_
     // row-major kernel: every row in canonical slots, one sweep thread per grid row, ring + solve vector in shared memory
     prm.rows_kernel = 0;
     int Pr = 0;
+    if ((prm.dbg & 64) && !(prm.dbg & 8)) {                     // A/B: the cluster-per-system kernel on a grid that fits one CTA
+        prm.pivots_out = pivots_out; prm.pivots_in = pivots_in;
+        prm.reuse_mask = g_reuse_always ? 3 : ((h_tab_u->sym ? 1 : 0) | (h_tab_v->sym ? 2 : 0));
+        const int rc = launch_bicgstab_band(prm, h_tab_u, h_tab_v, batch, stream);
+        if (rc != DPISO_EUNSUPPORTED) return rc;
+        prm.pivots_out = nullptr; prm.pivots_in = nullptr; prm.reuse_mask = 0;
+    }
     if (rows_kernel_applies(h_tab_u, h_tab_v, &Pr) && !(prm.dbg & 8)) {
         // the solve vector joins the ring in shared memory if it fits
         const size_t ring8 = (size_t)kRowsRing * Pr * 11 * sizeof(float), ring16 = 2 * ring8;
@@ -1238,6 +1151,13 @@ int dpiso_bicgstab_ilu(int batch, const dpiso_bicg_tables *h_tab_u, const dpiso_
             DPISO_CHECK_LAUNCH();
             return DPISO_OK;
         }
+    }
+    if (!(prm.dbg & 8)) {   // grids beyond one CTA's reach (BASELINE config #5): one cluster per system
+        prm.pivots_out = pivots_out; prm.pivots_in = pivots_in;
+        prm.reuse_mask = g_reuse_always ? 3 : ((h_tab_u->sym ? 1 : 0) | (h_tab_v->sym ? 2 : 0));
+        const int rc = launch_bicgstab_band(prm, h_tab_u, h_tab_v, batch, stream);
+        if (rc != DPISO_EUNSUPPORTED) return rc;
+        prm.pivots_out = nullptr; prm.pivots_in = nullptr; prm.reuse_mask = 0;
     }
     {   // the attribute is per device: remember which devices of this process have it
         static unsigned long long attr_set_mask = 0;

@@ -27,7 +27,8 @@ constexpr int kMaxWaHost = 6;
 struct Entry { int col, src; };
 
 struct HostTables {
-    int n = 0, n_levels = 0, wa = 0, max_level = 0, wl = 0, wu = 0, dx = 0, rows_ok = 0, sym = 0;
+    int n = 0, n_levels = 0, wa = 0, max_level = 0, wl = 0, wu = 0, dx = 0, rows_ok = 0, sym = 0, band_ok = 0;
+    int far[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
     std::vector<int> level_ptr, perm, a_col, a_src, a_rev, r_col, r_src, r_rev;
     std::vector<int> c_lsrc, c_lrev, c_usrc, c_lfar, c_ufar, c_dsrc, m_nbr, m_lfar, m_ufar;
 };
@@ -179,6 +180,41 @@ int build_tables(int ny, int nx, int per_x, int per_y, int comp, int transpose, 
             }
         }
     }
+    // Cluster-per-system kernel (bicgstab_band.cu): the far operands in closed form.  Lower entries: canonical slot 2 is
+    // an in-row wrap (every row takes, at column xa, its own value of column xb), slot 0 an in-column wrap (grid row ya
+    // takes row yb's value of the same column); upper entries: slot 1 in-row, slot 3 in-column.  band_ok = the four
+    // numbers per direction describe EVERY far entry of the pattern, and nothing else.
+    t.band_ok = rows_ok;
+    for (int k = 0; k < 8; k++) t.far[k] = -1;
+    if (rows_ok) {
+        auto note = [&](int slot_a, int slot_b, int a, int b) {
+            if (t.far[slot_a] < 0) { t.far[slot_a] = a; t.far[slot_b] = b; }
+            else if (t.far[slot_a] != a || t.far[slot_b] != b) t.band_ok = 0;
+        };
+        for (int i = 0; i < n; i++) {
+            const int lx = i % Dx, ly = i / Dx;
+            for (int dir = 0; dir < 2; dir++) {
+                const std::vector<int> &cf = dir ? t.c_ufar : t.c_lfar;
+                // lower: [0] = slot 0 (in-column), [1] = slot 2 (in-row); upper: [0] = slot 1 (in-row), [1] = slot 3 (in-column)
+                const int c_row = cf[(size_t)i * 2 + (dir ? 0 : 1)], c_col = cf[(size_t)i * 2 + (dir ? 1 : 0)];
+                if (c_row >= 0) { if (c_row / Dx != ly) t.band_ok = 0; note(4 * dir + 0, 4 * dir + 1, lx, c_row % Dx); }
+                if (c_col >= 0) { if (c_col % Dx != lx) t.band_ok = 0; note(4 * dir + 2, 4 * dir + 3, ly, c_col / Dx); }
+            }
+        }
+        for (int i = 0; i < n && t.band_ok; i++) {                 // ... and every row the description names has the entry
+            const int lx = i % Dx, ly = i / Dx;
+            for (int dir = 0; dir < 2; dir++) {
+                const std::vector<int> &cf = dir ? t.c_ufar : t.c_lfar;
+                const bool has_row = cf[(size_t)i * 2 + (dir ? 0 : 1)] >= 0, has_col = cf[(size_t)i * 2 + (dir ? 1 : 0)] >= 0;
+                if (has_row != (lx == t.far[4 * dir + 0]) || has_col != (ly == t.far[4 * dir + 2])) t.band_ok = 0;
+            }
+        }
+        // sweep order: the lower sweeps walk x and the rows upwards, the upper sweep downwards
+        if (t.far[0] >= 0 && !(t.far[1] < t.far[0])) t.band_ok = 0;
+        if (t.far[2] >= 0 && !(t.far[3] < t.far[2])) t.band_ok = 0;
+        if (t.far[4] >= 0 && !(t.far[5] > t.far[4])) t.band_ok = 0;
+        if (t.far[6] >= 0 && !(t.far[7] > t.far[6])) t.band_ok = 0;
+    }
     // level-major positions for the row-major kernel's planes / vectors
     t.m_nbr.assign((size_t)n * 4, 0); t.m_lfar.assign((size_t)n * 2, -1); t.m_ufar.assign((size_t)n * 2, -1);
     for (int q = 0; q < n; q++) {
@@ -217,7 +253,8 @@ Packed pack(const HostTables &t) {
 
 void fill_struct(const HostTables &t, const Packed &p, const int *base, dpiso_bicg_tables *out) {
     out->n = t.n; out->n_levels = t.n_levels; out->wa = t.wa; out->max_level = t.max_level; out->wl = t.wl; out->wu = t.wu;
-    out->dx = t.dx; out->rows_ok = t.rows_ok; out->sym = t.sym;
+    out->dx = t.dx; out->rows_ok = t.rows_ok; out->sym = t.sym; out->band_ok = t.band_ok;
+    for (int k = 0; k < 8; k++) out->far[k] = t.far[k];
     out->level_ptr = base + p.off[0]; out->perm = base + p.off[1]; out->a_col = base + p.off[2]; out->a_src = base + p.off[3];
     out->a_rev = base + p.off[4]; out->r_col = base + p.off[5]; out->r_src = base + p.off[6]; out->r_rev = base + p.off[7];
     out->c_lsrc = base + p.off[8]; out->c_lrev = base + p.off[9]; out->c_usrc = base + p.off[10];

@@ -37,7 +37,8 @@ class BicgTables(C.Structure):
                 ("r_col", C.c_void_p), ("r_src", C.c_void_p), ("r_rev", C.c_void_p), ("c_lsrc", C.c_void_p),
                 ("c_lrev", C.c_void_p), ("c_usrc", C.c_void_p), ("c_lfar", C.c_void_p), ("c_ufar", C.c_void_p),
                 ("c_dsrc", C.c_void_p), ("m_nbr", C.c_void_p), ("m_lfar", C.c_void_p), ("m_ufar", C.c_void_p),
-                ("owner", C.c_void_p), ("owner_is_host", C.c_int), ("sym", C.c_int)]
+                ("owner", C.c_void_p), ("owner_is_host", C.c_int), ("sym", C.c_int), ("band_ok", C.c_int),
+                ("far", C.c_int * 8)]
 
 
 _I, _F, _P, _SZ = C.c_int, C.c_float, C.c_void_p, C.c_size_t
@@ -64,6 +65,7 @@ _SIGS = {
     "dpiso_bicgstab_set_timing": ([_P], _I),
     "dpiso_bicgstab_set_debug": ([_I], _I),
     "dpiso_bicgstab_set_reuse_policy": ([_I], _I),
+    "dpiso_bicgstab_set_band_cluster": ([_I], _I),
     "dpiso_bicgstab_supports_factor_reuse": ([_P, _P], _I),
     "dpiso_bicgstab_ilu": ([_I, _P, _P, _I, _I, _P, _I, _P, _P, _F, _I, _P, _P, _P, _P, _P, _P, _P], _I),
     "dpiso_laplace_f64": ([_I, _I, _I, _P, _P, _P, _I, _F, _F, _P, _P], _I),

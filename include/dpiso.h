@@ -154,6 +154,12 @@ typedef struct {
     int sym;              /* 1: the pattern is structurally symmetric (every entry has its reverse entry): ILU(0)(M^T)
                              is then exactly the transposed ILU(0)(M) and factor reuse is equivalent;
                              0 for components that are periodic along their staggered axis */
+    int band_ok;          /* 1: every far (periodic wrap) entry is described by `far` below: the cluster-per-system kernel
+                             for large grids applies */
+    int far[8];           /* closed form of the far operands, lower entries then upper entries: {xa, xb, ya, yb} -- a row
+                             takes, at column xa, its own value of column xb (in-row wrap, canonical slot 2 / 1), and
+                             grid row ya takes the value of grid row yb in the same column (in-column wrap, slot 0 / 3);
+                             -1 = no such entry */
 } dpiso_bicg_tables;
 
 /* Builds the tables of one component (comp 0 = u, 1 = v) for M = A (transpose 0) or M = A^T (transpose 1) from the
@@ -203,6 +209,8 @@ int dpiso_bicgstab_supports_factor_reuse(const dpiso_bicg_tables *h_tab_u, const
 int dpiso_bicgstab_set_debug(int dbg);
 /* 0 (default): reuse pivots only for structurally symmetric components; 1: for every component */
 int dpiso_bicgstab_set_reuse_policy(int always);
+/* tuning hook of the cluster-per-system kernel (grids with more than 512 rows per component): CTAs per system, 0 = heuristic */
+int dpiso_bicgstab_set_band_cluster(int cluster);
 
 /* profiling hook: dev_counters = device buffer of 8 int64 SM-cycle counters accumulated by system 0 of every following
  * solve ([0] setup, [1] ILU(0), [2] triangular sweeps, [4] SpMV / vector phases); NULL disables */

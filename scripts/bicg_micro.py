@@ -29,6 +29,7 @@ def main():
         for tr in (False, True):
             ref[tr] = ops.bicgstab_ilu(g, neg, rhs, vel, 1e-8, max_it, tr)[0].clone()
     N.lib.dpiso_bicgstab_set_debug(dbg)
+    N.lib.dpiso_bicgstab_set_band_cluster(int(os.environ.get('BAND_CLUSTER', '0')))
     for tr in (False, True):
         cnt = torch.zeros(8, dtype=torch.int64, device=dev)
         x, st, w = ops.bicgstab_ilu(g, neg, rhs, vel, 1e-8, max_it, tr)

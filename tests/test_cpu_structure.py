@@ -305,6 +305,27 @@ def test_native_table_builder_equals_numpy_derivation(ny, nx, per_x, per_y):
                     assert getattr(st, k) == want[k], k
                 assert st.owner_is_host == 1
                 assert st.sym == int(not (per_x if comp == 0 else per_y))
+                # closed form of the periodic wrap operands (cluster-per-system kernel): {xa, xb, ya, yb} lower, upper
+                if want["rows_ok"]:
+                    Dx, Dy, sx, sy = S.comp_dims(ny, nx, comp)
+                    if not transpose:
+                        exp = [Dx - 1, sx, Dy - 1, sy, 0, Dx - 1 - sx, 0, Dy - 1 - sy]
+                    else:
+                        exp = [Dx - 1 - sx, 0, Dy - 1 - sy, 0, sx, Dx - 1, sy, Dy - 1]
+                    for k in range(0, 8, 2):
+                        if not (per_x if k % 4 == 0 else per_y):
+                            exp[k] = exp[k + 1] = -1
+                    assert st.band_ok == 1 and list(st.far) == exp, (list(st.far), exp, comp, transpose)
+                    # ... and it describes every far entry of the numpy derivation, and only those
+                    ly_, lx_ = np.divmod(np.arange(st.n), Dx)
+                    for d, cf in enumerate((want["c_lfar"], want["c_ufar"])):
+                        row_k, col_k = (1, 0) if d == 0 else (0, 1)
+                        f = exp[4 * d:4 * d + 4]
+                        assert np.array_equal(cf[:, row_k] >= 0, lx_ == f[0]) and np.array_equal(cf[:, col_k] >= 0, ly_ == f[2])
+                        hr, hc = cf[:, row_k] >= 0, cf[:, col_k] >= 0
+                        assert np.array_equal(cf[hr, row_k], ly_[hr] * Dx + f[1]) and np.array_equal(cf[hc, col_k], f[3] * Dx + lx_[hc])
+                else:
+                    assert st.band_ok == 0
                 n, wa = st.n, st.wa
                 shapes = dict(level_ptr=st.n_levels + 1, perm=n, a_col=wa * n, a_src=wa * n, a_rev=wa * n, r_col=wa * n,
                               r_src=wa * n, r_rev=wa * n, c_lsrc=4 * n, c_lrev=4 * n, c_usrc=4 * n, c_lfar=2 * n,

@@ -274,3 +274,70 @@ def test_bicgstab_level_major_fallback_agrees_with_row_major(name, transpose):
         N.lib.dpiso_bicgstab_set_debug(-1)
     assert int((st_rows[:, :, 0] - st_lm[:, :, 0]).abs().max()) <= 1
     assert rel_l2(x_rows.cpu().numpy(), x_lm.cpu().numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("name,cluster", [("periodic24x20", 1), ("ldc8", 1), ("tml16x24", 1), ("obstacle16x24", 1),
+                                          ("periodic64", 2), ("tml64x128", 2), ("sml32x128", 1), ("periodic128", 4),
+                                          ("ldc_like64", 2), ("periodic264x256", 8)])
+@pytest.mark.parametrize("transpose", [False, True])
+def test_bicgstab_cluster_kernel_matches_oracle(name, cluster, transpose):
+    """The cluster-per-system predictor kernel (bicgstab_band.cu; default for grids with more than 512 rows per component,
+    forced here on small grids with debug flag 64 and an explicit cluster size so that warp-to-warp, CTA-to-CTA and
+    periodic wrap hand-overs are all exercised): iteration counts within +-1 of the oracle, restarts / warn identical,
+    solution within 1e-5 relative L2, for A and A^T."""
+    from diffpiso_b200 import _native as N, ops
+    s = ALL_SETUPS[name]()
+    g, m = _geom(s), _masks(s)
+    vels = np.stack([random_fields(s, 50 + i)[0] for i in range(2)])
+    visc = _t(np.atleast_1d(s["visc"]))
+    values, _ = ops.assemble(g, _t(vels), m["dirichlet"], m["active"], m["noslip"], visc, s["dy"], s["dx"], _beta(s))
+    neg = torch.neg(values)
+    rhs = (vels * _beta(s)).astype(np.float32)
+    N.lib.dpiso_bicgstab_set_debug(64)
+    N.lib.dpiso_bicgstab_set_band_cluster(cluster)
+    try:
+        x, stats, warn = ops.bicgstab_ilu(g, neg, _t(rhs), _t(vels), s["bicg_tol"], s["bicg_max_it"], transpose)
+    finally:
+        N.lib.dpiso_bicgstab_set_debug(-1)
+        N.lib.dpiso_bicgstab_set_band_cluster(0)
+    x, stats = x.cpu().numpy(), stats.cpu().numpy()
+    assert int(warn.item()) == 0
+    orp, oci = O.csr_structure(s["ny"], s["nx"], s["per_x"], s["per_y"])
+    negh = neg.cpu().numpy()
+    for i in range(2):
+        for comp, (r0, r1, z0, z1, rp) in enumerate(((0, g.n_u, 0, g.nnz_u, orp[:g.n_u + 1]),
+                                                     (g.n_u, g.nf, g.nnz_u, g.nnz, orp[g.n_u + 1:]))):
+            ox, st = O.bicgstab_ilu(rp, oci[z0:z1], negh[i, z0:z1], rhs[i, r0:r1], vels[i, r0:r1], s["bicg_tol"],
+                                    s["bicg_max_it"], transpose)
+            got = stats[i, comp]
+            assert abs(int(got[0]) - st["iterations"]) <= 1, (name, i, comp, got, st)
+            assert int(got[1]) == st["restarts"] and int(got[2]) == st["warn"], (name, i, comp, got, st)
+            assert rel_l2(x[i, r0:r1], ox) < 1e-5, (name, i, comp, rel_l2(x[i, r0:r1], ox), got, st)
+
+
+def test_bicgstab_cluster_kernel_factor_reuse_and_pivots():
+    """Pivots written by the cluster kernel equal the row-major kernel's bit for bit (same per-row arithmetic and operand
+    order), and a transposed solve that reuses them converges to the same solution as one that factorises."""
+    from diffpiso_b200 import _native as N, ops
+    s = ALL_SETUPS["periodic64"]()
+    g, m = _geom(s), _masks(s)
+    vels = np.stack([random_fields(s, 60 + i)[0] for i in range(2)])
+    values, _ = ops.assemble(g, _t(vels), m["dirichlet"], m["active"], m["noslip"], _t(np.atleast_1d(s["visc"])), s["dy"],
+                             s["dx"], _beta(s))
+    rhs = _t((vels * _beta(s)).astype(np.float32))
+    piv_rows = torch.zeros(2, g.nf, device=DEV)
+    x_rows, st_rows, _ = ops.bicgstab_ilu(g, values, rhs, _t(vels), s["bicg_tol"], s["bicg_max_it"], False, negate=True,
+                                         pivots_out=piv_rows)
+    N.lib.dpiso_bicgstab_set_debug(64)
+    N.lib.dpiso_bicgstab_set_band_cluster(2)
+    try:
+        piv = torch.zeros(2, g.nf, device=DEV)
+        x, st, _ = ops.bicgstab_ilu(g, values, rhs, _t(vels), s["bicg_tol"], s["bicg_max_it"], False, negate=True, pivots_out=piv)
+        xt, stt, _ = ops.bicgstab_ilu(g, values, rhs, _t(vels), s["bicg_tol"], s["bicg_max_it"], True, negate=True, pivots_in=piv)
+        xt2, stt2, _ = ops.bicgstab_ilu(g, values, rhs, _t(vels), s["bicg_tol"], s["bicg_max_it"], True, negate=True)
+    finally:
+        N.lib.dpiso_bicgstab_set_debug(-1)
+        N.lib.dpiso_bicgstab_set_band_cluster(0)
+    assert torch.equal(piv, piv_rows)
+    assert int((st[:, :, 0] - st_rows[:, :, 0]).abs().max()) <= 1 and rel_l2(x.cpu().numpy(), x_rows.cpu().numpy()) < 1e-5
+    assert int((stt[:, :, 0] - stt2[:, :, 0]).abs().max()) <= 1 and rel_l2(xt.cpu().numpy(), xt2.cpu().numpy()) < 1e-5
