@@ -1016,7 +1016,8 @@ int dpiso_bicgstab_set_timing(long long *dev_counters) {
 size_t dpiso_bicgstab_workspace_floats(const dpiso_bicg_tables *h_tab_u, const dpiso_bicg_tables *h_tab_v) {
     const size_t n_max = (size_t)(h_tab_u->n > h_tab_v->n ? h_tab_u->n : h_tab_v->n);
     const size_t n_pad = (n_max + 3) & ~(size_t)3;
-    return (3 * (size_t)kMaxWa + 8) * n_pad + 17 * n_pad;
+    const size_t base = (3 * (size_t)kMaxWa + 8) * n_pad + 17 * n_pad, tile = tile_workspace_floats(h_tab_u, h_tab_v);
+    return base > tile ? base : tile;
 }
 
 static int g_reuse_always = 0;
@@ -1109,6 +1110,13 @@ int dpiso_bicgstab_ilu(int batch, const dpiso_bicg_tables *h_tab_u, const dpiso_
     // row-major kernel: every row in canonical slots, one sweep thread per grid row, ring + solve vector in shared memory
     prm.rows_kernel = 0;
     int Pr = 0;
+    if (!(prm.dbg & (8 | 64 | 128))) {                          // default: register-tiled wavefront sweeps (bicgstab_tile.cu)
+        prm.pivots_out = pivots_out; prm.pivots_in = pivots_in;
+        prm.reuse_mask = g_reuse_always ? 3 : ((h_tab_u->sym ? 1 : 0) | (h_tab_v->sym ? 2 : 0));
+        const int rc = launch_bicgstab_tile(prm, h_tab_u, h_tab_v, batch, stream);
+        if (rc != DPISO_EUNSUPPORTED) return rc;
+        prm.pivots_out = nullptr; prm.pivots_in = nullptr; prm.reuse_mask = 0;
+    }
     if ((prm.dbg & 64) && !(prm.dbg & 8)) {                     // A/B: the cluster-per-system kernel on a grid that fits one CTA
         prm.pivots_out = pivots_out; prm.pivots_in = pivots_in;
         prm.reuse_mask = g_reuse_always ? 3 : ((h_tab_u->sym ? 1 : 0) | (h_tab_v->sym ? 2 : 0));

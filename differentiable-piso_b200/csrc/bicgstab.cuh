@@ -105,4 +105,9 @@ __device__ __forceinline__ int lm_pos(const int *lp, int dx, int t, int x) {
 int launch_bicgstab_band(BicgParams &prm, const dpiso_bicg_tables *h_tab_u, const dpiso_bicg_tables *h_tab_v, int batch,
                          void *stream);
 
+// bicgstab_tile.cu: register-tiled wavefront sweeps, one cluster per system (default kernel); same return convention.
+int launch_bicgstab_tile(BicgParams &prm, const dpiso_bicg_tables *h_tab_u, const dpiso_bicg_tables *h_tab_v, int batch,
+                         void *stream);
+size_t tile_workspace_floats(const dpiso_bicg_tables *h_tab_u, const dpiso_bicg_tables *h_tab_v);
+
 }  // namespace dpiso

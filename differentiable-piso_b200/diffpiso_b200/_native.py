@@ -66,6 +66,7 @@ _SIGS = {
     "dpiso_bicgstab_set_debug": ([_I], _I),
     "dpiso_bicgstab_set_reuse_policy": ([_I], _I),
     "dpiso_bicgstab_set_band_cluster": ([_I], _I),
+    "dpiso_bicgstab_set_tile_cluster": ([_I], _I),
     "dpiso_bicgstab_supports_factor_reuse": ([_P, _P], _I),
     "dpiso_bicgstab_ilu": ([_I, _P, _P, _I, _I, _P, _I, _P, _P, _F, _I, _P, _P, _P, _P, _P, _P, _P], _I),
     "dpiso_laplace_f64": ([_I, _I, _I, _P, _P, _P, _I, _F, _F, _P, _P], _I),

@@ -211,6 +211,9 @@ int dpiso_bicgstab_set_debug(int dbg);
 int dpiso_bicgstab_set_reuse_policy(int always);
 /* tuning hook of the cluster-per-system kernel (grids with more than 512 rows per component): CTAs per system, 0 = heuristic */
 int dpiso_bicgstab_set_band_cluster(int cluster);
+/* tuning hook of the default (register-tiled) kernel: CTAs per system, 0 = heuristic; values below the minimum the grid
+ * needs are ignored */
+int dpiso_bicgstab_set_tile_cluster(int cluster);
 
 /* profiling hook: dev_counters = device buffer of 8 int64 SM-cycle counters accumulated by system 0 of every following
  * solve ([0] setup, [1] ILU(0), [2] triangular sweeps, [4] SpMV / vector phases); NULL disables */

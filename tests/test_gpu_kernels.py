@@ -341,3 +341,49 @@ def test_bicgstab_cluster_kernel_factor_reuse_and_pivots():
     assert torch.equal(piv, piv_rows)
     assert int((st[:, :, 0] - st_rows[:, :, 0]).abs().max()) <= 1 and rel_l2(x.cpu().numpy(), x_rows.cpu().numpy()) < 1e-5
     assert int((stt[:, :, 0] - stt2[:, :, 0]).abs().max()) <= 1 and rel_l2(xt.cpu().numpy(), xt2.cpu().numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("name,cluster", [("periodic24x20", 0), ("ldc8", 0), ("tml16x24", 2), ("obstacle16x24", 0),
+                                          ("periodic64", 2), ("tml64x128", 3), ("sml32x128", 0), ("periodic128", 0),
+                                          ("periodic128", 4), ("ldc_like64", 2), ("periodic264x256", 0), ("periodic264x256", 5)])
+@pytest.mark.parametrize("transpose", [False, True])
+def test_bicgstab_tile_kernel_matches_oracle_and_row_kernel(name, cluster, transpose):
+    """The default predictor kernel (bicgstab_tile.cu: 4 x 4 register tiles per sweep step, packets between warps and
+    CTAs) with the heuristic and with forced cluster sizes: iteration counts within +-1 of the oracle, restarts / warn
+    identical, solution within 1e-5 relative L2, for A and A^T; and the ILU(0) pivots equal those of the row-per-thread
+    kernel bit for bit (same fma / division chain per row)."""
+    from diffpiso_b200 import _native as N, ops
+    s = ALL_SETUPS[name]()
+    g, m = _geom(s), _masks(s)
+    vels = np.stack([random_fields(s, 50 + i)[0] for i in range(2)])
+    visc = _t(np.atleast_1d(s["visc"]))
+    values, _ = ops.assemble(g, _t(vels), m["dirichlet"], m["active"], m["noslip"], visc, s["dy"], s["dx"], _beta(s))
+    rhs = (vels * _beta(s)).astype(np.float32)
+    piv = torch.zeros(2, g.nf, device=DEV)
+    N.lib.dpiso_bicgstab_set_tile_cluster(cluster)
+    try:
+        x, stats, warn = ops.bicgstab_ilu(g, values, _t(rhs), _t(vels), s["bicg_tol"], s["bicg_max_it"], transpose, negate=True,
+                                          pivots_out=piv)
+    finally:
+        N.lib.dpiso_bicgstab_set_tile_cluster(0)
+    if name != "periodic264x256":                                  # the row-per-thread kernel covers at most 512 rows
+        piv_rows = torch.zeros(2, g.nf, device=DEV)
+        N.lib.dpiso_bicgstab_set_debug(128)
+        try:
+            ops.bicgstab_ilu(g, values, _t(rhs), _t(vels), s["bicg_tol"], s["bicg_max_it"], transpose, negate=True, pivots_out=piv_rows)
+        finally:
+            N.lib.dpiso_bicgstab_set_debug(-1)
+        assert torch.equal(piv, piv_rows)
+    x, stats = x.cpu().numpy(), stats.cpu().numpy()
+    assert int(warn.item()) == 0
+    orp, oci = O.csr_structure(s["ny"], s["nx"], s["per_x"], s["per_y"])
+    negh = -values.cpu().numpy()
+    for i in range(2):
+        for comp, (r0, r1, z0, z1, rp) in enumerate(((0, g.n_u, 0, g.nnz_u, orp[:g.n_u + 1]),
+                                                     (g.n_u, g.nf, g.nnz_u, g.nnz, orp[g.n_u + 1:]))):
+            ox, st = O.bicgstab_ilu(rp, oci[z0:z1], negh[i, z0:z1], rhs[i, r0:r1], vels[i, r0:r1], s["bicg_tol"],
+                                    s["bicg_max_it"], transpose)
+            got = stats[i, comp]
+            assert abs(int(got[0]) - st["iterations"]) <= 1, (name, i, comp, got, st)
+            assert int(got[1]) == st["restarts"] and int(got[2]) == st["warn"], (name, i, comp, got, st)
+            assert rel_l2(x[i, r0:r1], ox) < 1e-5, (name, i, comp, rel_l2(x[i, r0:r1], ox), got, st)
