@@ -585,7 +585,7 @@ __device__ __forceinline__ float sweep_row_step(const RowsPlanes &pl, float *zs,
     if (MODE == 0) {
         // l_ik = a_ik / u_kk, u_ii = a_ii - sum l_ik u_ki, lower entries in ascending column order
         const float p0 = fc.x >= 0 ? z0 : 1.0f, p2 = fc.y >= 0 ? z1 : 1.0f;
-        const float l0 = __fdiv_rn(v.x, p0), l1 = __fdiv_rn(v.y, nb), l2 = __fdiv_rn(v.z, p2), l3 = __fdiv_rn(v.w, prev);
+        const float l0 = ilu_div(v.x, p0), l1 = ilu_div(v.y, nb), l2 = ilu_div(v.z, p2), l3 = ilu_div(v.w, prev);
         float dg = fmaf(-l0, rv.x, e);
         dg = fmaf(-l1, rv.y, dg);
         dg = fmaf(-l2, rv.z, dg);
@@ -819,7 +819,7 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_rows_kernel(const Bi
                 const int2 fc = T.c_lfar[i];
                 const float p0 = fc.x >= 0 ? d_in[fc.x] : 1.0f, p2 = fc.y >= 0 ? d_in[fc.y] : 1.0f;
                 const float p1 = i - dx >= 0 ? d_in[i - dx] : 1.0f, p3 = i >= 1 ? d_in[i - 1] : 1.0f;
-                pl.lval[q] = make_float4(__fdiv_rn(a.x, p0), __fdiv_rn(a.y, p1), __fdiv_rn(a.z, p2), __fdiv_rn(a.w, p3));
+                pl.lval[q] = make_float4(ilu_div(a.x, p0), ilu_div(a.y, p1), ilu_div(a.z, p2), ilu_div(a.w, p3));
                 pl.udiag[q] = d_in[i];
             }
         }
@@ -1109,8 +1109,16 @@ int dpiso_bicgstab_ilu(int batch, const dpiso_bicg_tables *h_tab_u, const dpiso_
     }
     // row-major kernel: every row in canonical slots, one sweep thread per grid row, ring + solve vector in shared memory
     prm.rows_kernel = 0;
+    // Kernel choice.  Up to 512 rows per component: bicgstab_rows_kernel (one CTA per system, one sweep thread per grid
+    // row: 1.2-1.3 ms per solve of 128 systems of 128^2).  Larger grids: one cluster per system -- bicgstab_band_kernel
+    // (a row per sweep thread; 1024^2 x 8: 15-20 ms) up to ~1100 rows, bicgstab_tile_kernel (4 x 4 register tiles per sweep
+    // step, sweep-image storage; 2048^2 x 4: 30 ms against 44 ms) beyond.  Debug bits force a kernel: 8 level-major,
+    // 64 band, 128 rows, 256 tile.
     int Pr = 0;
-    if (!(prm.dbg & (8 | 64 | 128))) {                          // default: register-tiled wavefront sweeps (bicgstab_tile.cu)
+    const bool rows_fit = rows_kernel_applies(h_tab_u, h_tab_v, &Pr);
+    const int dy_u_ = h_tab_u->dx > 0 ? h_tab_u->n / h_tab_u->dx : 0, dy_v_ = h_tab_v->dx > 0 ? h_tab_v->n / h_tab_v->dx : 0;
+    const bool tile_first = (prm.dbg & 256) || (!rows_fit && !(prm.dbg & (8 | 64 | 128)) && (dy_u_ > 1100 || dy_v_ > 1100));
+    if (tile_first) {
         prm.pivots_out = pivots_out; prm.pivots_in = pivots_in;
         prm.reuse_mask = g_reuse_always ? 3 : ((h_tab_u->sym ? 1 : 0) | (h_tab_v->sym ? 2 : 0));
         const int rc = launch_bicgstab_tile(prm, h_tab_u, h_tab_v, batch, stream);
@@ -1124,7 +1132,7 @@ int dpiso_bicgstab_ilu(int batch, const dpiso_bicg_tables *h_tab_u, const dpiso_
         if (rc != DPISO_EUNSUPPORTED) return rc;
         prm.pivots_out = nullptr; prm.pivots_in = nullptr; prm.reuse_mask = 0;
     }
-    if (rows_kernel_applies(h_tab_u, h_tab_v, &Pr) && !(prm.dbg & 8)) {
+    if (rows_fit && !(prm.dbg & 8)) {
         // the solve vector joins the ring in shared memory if it fits
         const size_t ring8 = (size_t)kRowsRing * Pr * 11 * sizeof(float), ring16 = 2 * ring8;
         prm.rows_lp_cap = (n_levels + 1 + 3) & ~3;

@@ -66,6 +66,11 @@ __device__ __forceinline__ void block_sum2(double &a, double &b, double *scratch
     a = warp_sum_d(va); b = warp_sum_d(vb);
 }
 
+// a / b as the ILU(0) sweeps need it: most lower slots of a row are absent (zero coefficient), and __fdiv_rn sends a zero
+// numerator down its slow path (FCHK flags the exponent; measured: 64 such divisions made an ILU step 3x longer than the
+// rest of it).  0 * b has the sign of 0 / b, so the product is bit-identical for every finite non-zero b.
+__device__ __forceinline__ float ilu_div(float a, float b) { return a == 0.0f ? __fmul_rn(a, b) : __fdiv_rn(a, b); }
+
 __device__ __forceinline__ void named_bar(int id, int count) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }

@@ -72,7 +72,7 @@ __device__ __forceinline__ unsigned long long ld_packet(uint32_t cta_addr) {
 //   boxes  [Rc / 32][dxmax] warp inboxes | [dxmax] in-column wrap inbox (lower sweeps) | [dxmax] (U solve); 8-byte packets
 //   lp     level offsets: position of (row t, column x) = lp[x + t] + t
 struct BandCtx {
-    int dx, dy, Rc, C, rank, dxmax;
+    int dx, dy, Rc, C, rank, dxmax, dbg;
 };
 template <int D> __device__ __forceinline__ size_t band_off_boxes(int Rc) { return (size_t)D * Rc * 40; }
 template <int D> __device__ __forceinline__ size_t band_off_lp(int Rc, int dxmax) {
@@ -87,7 +87,7 @@ __device__ __forceinline__ float band_row_step(const float4 v, const float4 rv, 
                                                bool has_col, float fcol, bool has_row, float frow, float4 &l_out) {
     if (MODE == 0) {
         const float p0 = has_col ? fcol : 1.0f, p2 = has_row ? frow : 1.0f;
-        const float l0 = __fdiv_rn(v.x, p0), l1 = __fdiv_rn(v.y, nb), l2 = __fdiv_rn(v.z, p2), l3 = __fdiv_rn(v.w, prev);
+        const float l0 = ilu_div(v.x, p0), l1 = ilu_div(v.y, nb), l2 = ilu_div(v.z, p2), l3 = ilu_div(v.w, prev);
         float dg = fmaf(-l0, rv.x, e);
         dg = fmaf(-l1, rv.y, dg);
         dg = fmaf(-l2, rv.z, dg);
@@ -162,7 +162,7 @@ __device__ __noinline__ void band_sweep(const BandCtx c, const RowsPlanes pl, co
         const bool warp_wrap = __any_sync(0xffffffffu, wrapc || wrapp);
         const uint32_t wrap_box = kUp ? wrap_u : wrap_l;
         const uint32_t wrapp_addr = wrapp ? band_mapa(wrap_box, (uint32_t)(far.ya / Rc)) : 0u;
-        const bool full_warp = t0 + 31 < dy;
+        const bool full_warp = t0 + 31 < dy && !(c.dbg & 512);
         auto issue = [&](int u) {
             const int x = x_of(u);
             if (rowok && (unsigned)x < (unsigned)dx) {
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_band_kernel(const Ba
 
     // dynamic shared memory: ring | warp inboxes | wrap inboxes | level offsets (see BandCtx)
     BandCtx c;
-    c.dx = dx; c.dy = dy; c.Rc = Rc; c.C = C; c.rank = rank; c.dxmax = bp.dxmax;
+    c.dx = dx; c.dy = dy; c.Rc = Rc; c.C = C; c.rank = rank; c.dxmax = bp.dxmax; c.dbg = prm.dbg;
     unsigned long long *const boxes = (unsigned long long *)(smem_raw + band_off_boxes<D>(Rc));
     const int n_box = (Rc >> 5) + 2;
     int *const s_lp = (int *)(smem_raw + band_off_lp<D>(Rc, bp.dxmax));
@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_band_kernel(const Ba
                 const int2 fc = T.c_lfar[i];
                 const float p0 = fc.x >= 0 ? d_in[fc.x] : 1.0f, p2 = fc.y >= 0 ? d_in[fc.y] : 1.0f;
                 const float p1 = i - dx >= 0 ? d_in[i - dx] : 1.0f, p3 = i >= 1 ? d_in[i - 1] : 1.0f;
-                pl.lval[q] = make_float4(__fdiv_rn(a.x, p0), __fdiv_rn(a.y, p1), __fdiv_rn(a.z, p2), __fdiv_rn(a.w, p3));
+                pl.lval[q] = make_float4(ilu_div(a.x, p0), ilu_div(a.y, p1), ilu_div(a.z, p2), ilu_div(a.w, p3));
                 pl.udiag[q] = d_in[i];
             }
         }
@@ -428,6 +428,7 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_band_kernel(const Ba
             rhop = rho;
             rho = rho_next;
             beta = __fmul_rn(__fdiv_rn(rho, rhop), __fdiv_rn(alpha, omega));
+            __syncthreads();                                         // first iteration: rh, p, v were set by other threads
 #pragma unroll 2
             for (int q = q_lo + tid * 4; q < q4_hi; q += NT * 4) {   // p = r + beta (p - omega v)  (":315-317")
                 const float4 vv = ld4(v + q), rr = ld4(r + q);
@@ -563,8 +564,10 @@ int launch_bicgstab_band(BicgParams &prm, const dpiso_bicg_tables *h_tab_u, cons
     for (int cand = 1; cand <= kBandMaxCluster; cand *= 2)
         if (feasible(cand, 8)) { C = cand; break; }
     if (!C) return DPISO_EUNSUPPORTED;
-    // more CTAs per system while the whole batch still fits one wave: the SpMV / vector phases scale with the CTAs
-    while (C * 2 <= 8 && feasible(C * 2, 8) && rows_of(C * 2) >= 64 && batch * 2 * C * 2 <= 148) C *= 2;
+    // more CTAs per system (the SpMV / vector phases scale with them) only while the batch stays within half the GPU:
+    // every CTA boundary adds a DSMEM hand-over to the sweep pipeline (measured 1024^2 x 8: 4 CTAs per system 14-16 ms,
+    // 8 CTAs 18-20 ms)
+    while (C * 2 <= 8 && feasible(C * 2, 8) && rows_of(C * 2) >= 64 && batch * 2 * C * 2 <= 74) C *= 2;
     if (g_band_cluster && feasible(g_band_cluster, 8)) C = g_band_cluster;
     bp.C = C; bp.Rc = rows_of(C);
     bp.p = prm;

@@ -15,17 +15,22 @@
 //     over as 8-byte packets {value, sweep id} stored into the CONSUMER warp's inbox (shared memory of the consumer's
 //     CTA: a plain store inside the CTA, a DSMEM store across the CTAs of the cluster).  Value and tag travel in one
 //     atomic word, so no fence is needed; the consumer polls the tags one step ahead of their use;
-//   * planes and vectors stay in the caller's ROW-MAJOR order (row stride padded to a multiple of 4, so every access of
-//     a sweep is a 16-byte vector and the coefficients of a tile row are 64 contiguous bytes); there is no permutation,
-//     no index table: neighbours are q -+ 1, q -+ stride, and the periodic wrap operands are four numbers per sweep
-//     direction (dpiso_bicg_tables::far, proven by the table builder to describe every far entry of the pattern):
-//     the in-row wrap is a register per row, the in-column wrap one more inbox pushed by the thread that owns the source row;
-//   * coefficient tiles are streamed D steps ahead with cp.async.cg into a per-lane, bank-conflict-free ring;
-//   * SpMVs, vector updates and dot products run on all threads of all CTAs of the cluster over contiguous row blocks;
-//     dot products are completed through DSMEM (rank-ordered, bitwise identical in every CTA); barrier.cluster
-//     publishes the global-memory vectors between the phases.
-// Padded cells (x >= dx, rows >= dy) carry zero off-diagonals, a unit diagonal and zero vector entries: they stay zero
-// through every phase and take part in no sum.
+//   * STORAGE = the image of the sweep.  Tile (tr, tc) of warp group g = tr / 32, lane l = tr % 32 is consumed at step
+//     sigma = tc + l of the group's L sweep (and at step ntile + 30 - sigma of its U sweep), so every plane and every
+//     vector is stored as blocks [g][sigma][item][lane] of 16-byte items: what the 32 lanes of a warp need in one step is
+//     one contiguous block, every load / cp.async / store of a sweep is fully coalesced (512 bytes per instruction) and
+//     lands conflict-free in the shared-memory ring, which has the same [item][lane] layout.  (A first version kept
+//     row-major planes: 20 cp.async per step that each touched 32 different lines cost ~2600 cycles per step.)
+//     Slots of a block whose lane is outside the grid at that step are never touched;
+//   * there is no index table: the neighbours of a tile are the blocks sigma -+ 1 (same lane: x-neighbours; lane -+ 1:
+//     y-neighbours), and the periodic wrap operands are four numbers per sweep direction (dpiso_bicg_tables::far, proven
+//     by the table builder to describe every far entry of the pattern): the in-row wrap is a register per row, the
+//     in-column wrap one more inbox pushed by the thread that owns the source row;
+//   * SpMVs, vector updates and dot products run block-wise on all warps of all CTAs of the cluster (they are
+//     element-wise in the image layout; the SpMV reads the neighbouring blocks); dot products are completed through DSMEM
+//     (rank-ordered, bitwise identical in every CTA); barrier.cluster publishes the global-memory vectors between phases.
+// Padded cells (x >= dx, rows >= dy inside a tile) carry zero off-diagonals, a unit diagonal and zero vector entries:
+// they stay zero through every phase and contribute nothing to any sum.
 #include <cooperative_groups.h>
 
 #include "bicgstab.cuh"
@@ -38,22 +43,40 @@ constexpr int kTileMaxCluster = 16;
 constexpr int kTM = 4, kTK = 4;                    // rows per sweep thread, columns per step
 constexpr int kTileRingBytes = 48 * 1024;          // ring per sweep warp
 constexpr int kTileMaxWarps = 4;                   // sweep warps per CTA
+constexpr int kTileBlockFloats = 11264;            // workspace floats per block: 3 coefficient images + 10 vector images
 
 struct TileFar { int xa, xb, ya, yb; };            // -1 = absent
 
 struct TileParams {
     BicgParams p;
     int C, Wc;                 // CTAs per system, sweep warps per CTA
-    int dxp[2], dyp[2];        // padded row stride (multiple of 4) and padded row count (multiple of 4) per component
+    int dxp[2], dyp[2];        // padded row length / row count (multiples of 4) per component
     int dxp_max;               // packets per inbox
-    size_t np_max;             // plane stride inside the workspace (floats): max over components of dxp * dyp
+    size_t blocks_max;         // blocks per image (max over the components): plane stride inside the workspace
     TileFar far_l[2], far_u[2];
 };
 
 struct TilePlanes {
-    float4 *alow, *uval, *lval, *arv;   // [np] canonical lower / upper slots of A, l_ik, reverse entries (ILU only)
-    float *adiag, *udiag;               // [np] diagonal of A, pivots
+    float4 *alow, *uval, *lval, *arv;   // coefficient images [blocks][16][32]: canonical lower / upper slots of A, l_ik,
+                                        // reverse entries (ILU only)
+    float4 *adiag, *udiag;              // vector images [blocks][4][32]: diagonal of A, pivots
 };
+
+// geometry of one component's image
+struct TileGeo {
+    int dx, dy, ntile, ntr, G, S;       // faces per row / rows, tile columns / rows, warp groups, steps per sweep
+};
+__device__ __forceinline__ size_t vimg(int blk, int i, int lane) { return ((size_t)blk * 4 + i) * 32 + lane; }
+__device__ __forceinline__ size_t cimg(int blk, int item, int lane) { return ((size_t)blk * 16 + item) * 32 + lane; }
+// float index of cell (t, x) inside a vector image
+__device__ __forceinline__ size_t vcell(const TileGeo &g, int t, int x) {
+    const int tr = t >> 2, tc = x >> 2;
+    return vimg((tr >> 5) * g.S + tc + (tr & 31), t & 3, tr & 31) * 4 + (x & 3);
+}
+__device__ __forceinline__ size_t ccell(const TileGeo &g, int t, int x) {
+    const int tr = t >> 2, tc = x >> 2;
+    return cimg((tr >> 5) * g.S + tc + (tr & 31), (t & 3) * 4 + (x & 3), tr & 31);
+}
 
 __device__ __forceinline__ uint32_t tile_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t tile_mapa(uint32_t addr, uint32_t rank) {
@@ -83,7 +106,8 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 }
 
 struct TileCtx {
-    int dx, dy, dxp, Wc, rank, dxp_max;
+    TileGeo g;
+    int Wc, rank, dxp_max;
 };
 
 // One cell of a sweep; fma order = ascending column of the row (lower slots: [column wrap, y-neighbour, row wrap,
@@ -93,7 +117,7 @@ template <int MODE>
 __device__ __forceinline__ float tile_cell(const float4 v, const float4 rv, float e, float start, float nb, float prev,
                                            float fcol, float frow, float4 &l_out) {
     if (MODE == 0) {
-        const float l0 = __fdiv_rn(v.x, fcol), l1 = __fdiv_rn(v.y, nb), l2 = __fdiv_rn(v.z, frow), l3 = __fdiv_rn(v.w, prev);
+        const float l0 = ilu_div(v.x, fcol), l1 = ilu_div(v.y, nb), l2 = ilu_div(v.z, frow), l3 = ilu_div(v.w, prev);
         float dg = fmaf(-l0, rv.x, e);
         dg = fmaf(-l1, rv.y, dg);
         dg = fmaf(-l2, rv.z, dg);
@@ -122,34 +146,32 @@ template <int MODE> struct TileRing {
     static_assert(kItems * 512 * kDepth <= kTileRingBytes, "ring does not fit");
 };
 
-// MODE 0: ILU(0) (writes lval, udiag), 1: L solve (ext = right-hand side, writes zs), 2: U solve (zs in place).
+// MODE 0: ILU(0) (writes lval, udiag), 1: L solve (ext = right-hand side image, writes zs), 2: U solve (zs in place).
 // sid = sweep id (tag of this sweep's packets); the caller separates sweeps by barrier.cluster.
 template <int MODE>
-__device__ __noinline__ void tile_sweep(const TileCtx c, const TilePlanes pl, const TileFar far, const float *ext, float *zs,
+__device__ __noinline__ void tile_sweep(const TileCtx c, const TilePlanes pl, const TileFar far, const float4 *ext, float4 *zs,
                                         unsigned sid) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr bool kUp = MODE == 2;
     constexpr int NI = TileRing<MODE>::kItems, D = TileRing<MODE>::kDepth;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int Wc = c.Wc, dx = c.dx, dy = c.dy, dxp = c.dxp;
-    const int gw = c.rank * Wc + w;                                   // sweep warp of the system
-    const int r0 = (gw * 32 + lane) * kTM;                             // first grid row of this thread
-    const int wr0 = gw * 32 * kTM;                                     // first grid row of this warp
-    if (w < Wc && wr0 < dy) {                                          // warps without rows take no part
+    const int Wc = c.Wc, ntile = c.g.ntile, ntr = c.g.ntr, G = c.g.G, S = c.g.S;
+    const int g = c.rank * Wc + w;                                    // warp group of the system swept by this warp
+    const int tr = g * 32 + lane;                                      // tile row of this thread
+    if (w < Wc && g < G) {                                             // warps without rows take no part
         const uint32_t ring = tile_smem_u32(smem_raw) + (uint32_t)w * kTileRingBytes + (uint32_t)lane * 16u;
         const uint32_t inbox0 = tile_smem_u32(smem_raw) + (uint32_t)Wc * kTileRingBytes;
         const uint32_t wrap_l = inbox0 + (uint32_t)(Wc * c.dxp_max) * 8u, wrap_u = wrap_l + (uint32_t)c.dxp_max * 8u;
-        const bool rowok = r0 < dy;
+        const bool rowok = tr < ntr;
         const float4 *gval = kUp ? pl.uval : (MODE == 0 ? pl.alow : pl.lval);
-        const float *gext = MODE == 1 ? ext : (MODE == 0 ? pl.adiag : pl.udiag);
-        const int ntile = dxp / kTK;
-        const int nsteps = ntile + 31;
-        // lane l works on tile column tc(u) at local step u: the wavefront inside the warp
-        const int tcoff = kUp ? ntile - 1 + (31 - lane) : -lane;
-        auto tc_of = [&](int u) { return kUp ? tcoff - u : tcoff + u; };
+        const float4 *gext = MODE == 1 ? ext : (MODE == 0 ? pl.adiag : pl.udiag);
+        const int nsteps = S;
+        // block (g, sigma) is consumed at local step u = sigma (lower sweeps) / u = S - 1 - sigma (U solve)
+        auto blk_of = [&](int u) { return g * S + (kUp ? S - 1 - u : u); };
+        auto tc_of = [&](int u) { return (kUp ? S - 1 - u : u) - lane; };
         // consumer of the neighbouring warp's edge row / producer for the other neighbour
-        const bool poller = kUp ? (lane == 31 && wr0 + 32 * kTM < dy) : (lane == 0 && wr0 > 0);
-        const bool producer = kUp ? (lane == 0 && wr0 > 0) : (lane == 31 && r0 + kTM < dy);
+        const bool poller = kUp ? (lane == 31 && g + 1 < G) : (lane == 0 && g > 0);
+        const bool producer = kUp ? (lane == 0 && g > 0) : (lane == 31 && tr + 1 < ntr);
         const uint32_t my_inbox = inbox0 + (uint32_t)(w * c.dxp_max) * 8u;
         uint32_t prod_addr = 0;
         bool prod_remote = false;
@@ -162,35 +184,39 @@ __device__ __noinline__ void tile_sweep(const TileCtx c, const TilePlanes pl, co
             if (prod_remote) prod_addr = tile_mapa(prod_addr, (uint32_t)trank);
         }
         // in-column wrap: the thread that owns grid row ya consumes what the owner of row yb pushes into the inbox of ya's CTA
-        const bool wrapc = rowok && far.ya >= r0 && far.ya < r0 + kTM;
-        const bool wrapp = rowok && far.ya >= 0 && far.yb >= r0 && far.yb < r0 + kTM;
+        const bool wrapc = rowok && far.ya >= 0 && (far.ya >> 2) == tr;
+        const bool wrapp = rowok && far.ya >= 0 && (far.yb >> 2) == tr;
         const bool warp_wrap = __any_sync(0xffffffffu, wrapc || wrapp);
         const uint32_t wrap_box = kUp ? wrap_u : wrap_l;
         uint32_t wrapp_addr = 0;
         bool wrapp_remote = false;
         if (wrapp) {
-            const int trank = far.ya / (Wc * 32 * kTM);
+            const int trank = (far.ya >> 7) / Wc;                      // group of row ya = (ya / 4) / 32
             wrapp_remote = trank != c.rank;
             wrapp_addr = wrapp_remote ? tile_mapa(wrap_box, (uint32_t)trank) : wrap_box;
         }
-        const int i_yb = far.yb - r0;                                  // tile row pushed by the wrap producer
-        const int xb_tc = far.xb >= 0 ? far.xb / kTK : -1, xb_j = far.xb >= 0 ? far.xb % kTK : 0;
+        const int i_yb = far.yb & 3;                                   // tile row pushed by the wrap producer
+        const int xb_tc = far.xb >= 0 ? far.xb >> 2 : -1, xb_j = far.xb >= 0 ? far.xb & 3 : 0;
 
         auto issue = [&](int u) {
             const int tc = tc_of(u);
             if (rowok && (unsigned)tc < (unsigned)ntile) {
                 const uint32_t slot = ring + (uint32_t)((u & (D - 1)) * NI) * 512u;
-                const size_t base = (size_t)r0 * dxp + (size_t)tc * kTK;
+                const int blk = blk_of(u);
+                const float4 *cv = gval + cimg(blk, 0, lane), *ce = gext + vimg(blk, 0, lane);
 #pragma unroll
-                for (int i = 0; i < kTM; i++) {
-                    const size_t q = base + (size_t)i * dxp;
+                for (int k = 0; k < 16; k++) cp_async16_cg(slot + (uint32_t)k * 512u, cv + k * 32);
+                if (MODE == 0) {
+                    const float4 *cr = pl.arv + cimg(blk, 0, lane);
 #pragma unroll
-                    for (int j = 0; j < kTK; j++) {
-                        cp_async16_cg(slot + (uint32_t)(i * kTK + j) * 512u, gval + q + j);
-                        if (MODE == 0) cp_async16_cg(slot + (uint32_t)(16 + i * kTK + j) * 512u, pl.arv + q + j);
-                    }
-                    cp_async16_cg(slot + (uint32_t)((MODE == 0 ? 32 : 16) + i) * 512u, gext + q);
-                    if (MODE == 2) cp_async16_cg(slot + (uint32_t)(20 + i) * 512u, zs + q);
+                    for (int k = 0; k < 16; k++) cp_async16_cg(slot + (uint32_t)(16 + k) * 512u, cr + k * 32);
+                }
+#pragma unroll
+                for (int i = 0; i < kTM; i++) cp_async16_cg(slot + (uint32_t)((MODE == 0 ? 32 : 16) + i) * 512u, ce + i * 32);
+                if (MODE == 2) {
+                    const float4 *cz = zs + vimg(blk, 0, lane);
+#pragma unroll
+                    for (int i = 0; i < kTM; i++) cp_async16_cg(slot + (uint32_t)(20 + i) * 512u, cz + i * 32);
                 }
             }
             cp_async_commit();
@@ -246,7 +272,7 @@ __device__ __noinline__ void tile_sweep(const TileCtx c, const TilePlanes pl, co
             }
             if (act) {
                 const uint32_t slot = ring + (uint32_t)((u & (D - 1)) * NI) * 512u;
-                const size_t base = (size_t)r0 * dxp + (size_t)tc * kTK;
+                const int blk = blk_of(u);
                 float res[kTM][kTK];
 #pragma unroll
                 for (int ii = 0; ii < kTM; ii++) {
@@ -264,13 +290,13 @@ __device__ __noinline__ void tile_sweep(const TileCtx c, const TilePlanes pl, co
                         const float prev = jj == 0 ? side[i] : res[i][kUp ? j + 1 : j - 1];
                         res[i][j] = tile_cell<MODE>(v, rv, ev[j], sv[j], nb, prev, fc[j], keep[i], lo[j]);
                     }
-                    const size_t q = base + (size_t)i * dxp;
+                    const float4 r4 = make_float4(res[i][0], res[i][1], res[i][2], res[i][3]);
                     if (MODE == 0) {
 #pragma unroll
-                        for (int j = 0; j < kTK; j++) pl.lval[q + j] = lo[j];
-                        *reinterpret_cast<float4 *>(pl.udiag + q) = make_float4(res[i][0], res[i][1], res[i][2], res[i][3]);
+                        for (int j = 0; j < kTK; j++) pl.lval[cimg(blk, i * kTK + j, lane)] = lo[j];
+                        pl.udiag[vimg(blk, i, lane)] = r4;
                     } else {
-                        *reinterpret_cast<float4 *>(zs + q) = make_float4(res[i][0], res[i][1], res[i][2], res[i][3]);
+                        zs[vimg(blk, i, lane)] = r4;
                     }
                     side[i] = res[i][kUp ? 0 : kTK - 1];
                 }
@@ -313,6 +339,8 @@ __device__ __noinline__ void tile_sweep(const TileCtx c, const TilePlanes pl, co
         }                                                                            \
     } while (0)
 
+__device__ __forceinline__ float f4c(const float4 &a, int j) { return j == 0 ? a.x : (j == 1 ? a.y : (j == 2 ? a.z : a.w)); }
+
 __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_tile_kernel(const TileParams tp) {
     long long tick = clock64();
     cg::cluster_group cluster = cg::this_cluster();
@@ -325,8 +353,13 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_tile_kernel(const Ti
     const int sys = blockIdx.x / C;
     const int sample = sys >> 1, comp = sys & 1;
     const BicgTab &T = prm.tab[comp];
-    const int dx = T.dx, dy = T.n / T.dx, dxp = tp.dxp[comp], dyp = tp.dyp[comp];
+    TileGeo geo;
+    geo.dx = T.dx; geo.dy = T.n / T.dx; geo.ntile = tp.dxp[comp] >> 2; geo.ntr = tp.dyp[comp] >> 2;
+    geo.G = (geo.ntr + 31) >> 5; geo.S = geo.ntile + 31;
+    const int dx = geo.dx, dy = geo.dy, dxp = tp.dxp[comp], dyp = tp.dyp[comp], ntile = geo.ntile, ntr = geo.ntr, S = geo.S;
+    const int NB = geo.G * S;                                     // blocks of this component's images
     const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, NW = NT >> 5;
+    const int wg = rank * NW + warp, nwg = C * NW;                // warp of the cluster: blocks wg, wg + nwg, ... are its own
     const int face_off = comp ? prm.tab[0].n : 0;
     const float *values_c = prm.values + (size_t)sample * prm.nnz_total + (comp ? prm.nnz[0] : 0);
     const int nnz_c = prm.nnz[comp];
@@ -334,27 +367,26 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_tile_kernel(const Ti
     const float *x0_g = prm.x0 + (size_t)sample * prm.n_face + face_off;
     float *x_g = prm.x + (size_t)sample * prm.n_face + face_off;
 
-    const size_t np = tp.np_max;
-    float *ws = prm.workspace + (size_t)sys * prm.ws_floats;
+    const size_t cI = tp.blocks_max * 512, vI = tp.blocks_max * 128;       // float4 per coefficient / vector image
+    float4 *cur = (float4 *)(prm.workspace + (size_t)sys * prm.ws_floats);
     TilePlanes pl;
-    float *cur = ws;
-    pl.alow = (float4 *)cur;  cur += 4 * np;
-    pl.uval = (float4 *)cur;  cur += 4 * np;
-    pl.lval = (float4 *)cur;  cur += 4 * np;
-    pl.adiag = cur;           cur += np;
-    pl.udiag = cur;           cur += np;
-    float *__restrict__ b = cur;
-    float *__restrict__ x = b + np;
-    float *__restrict__ r = x + np;
-    float *__restrict__ rh = r + np;                              // rh, p, v, tt: contiguous, double as the ILU-only arv plane
-    float *__restrict__ p = rh + np;
-    float *__restrict__ v = p + np;
-    float *__restrict__ tt = v + np;
-    pl.arv = (float4 *)rh;
-    float *const zs = tt + np;                                     // the solve vector
+    pl.alow = cur;  cur += cI;
+    pl.uval = cur;  cur += cI;
+    pl.lval = cur;  cur += cI;
+    pl.adiag = cur; cur += vI;
+    pl.udiag = cur; cur += vI;
+    float4 *__restrict__ b = cur;
+    float4 *__restrict__ x = b + vI;
+    float4 *__restrict__ r = x + vI;
+    float4 *__restrict__ rh = r + vI;                             // rh, p, v, tt: contiguous, double as the ILU-only arv image
+    float4 *__restrict__ p = rh + vI;
+    float4 *__restrict__ v = p + vI;
+    float4 *__restrict__ tt = v + vI;
+    pl.arv = rh;
+    float4 *const zs = tt + vI;                                    // the solve vector
 
     TileCtx c;
-    c.dx = dx; c.dy = dy; c.dxp = dxp; c.Wc = Wc; c.rank = rank; c.dxp_max = tp.dxp_max;
+    c.g = geo; c.Wc = Wc; c.rank = rank; c.dxp_max = tp.dxp_max;
     {   // inboxes: tag 0 = no sweep
         unsigned long long *const boxes = (unsigned long long *)(smem_raw + (size_t)Wc * kTileRingBytes);
         for (int k = tid; k < (Wc + 2) * tp.dxp_max; k += NT) boxes[k] = 0ull;
@@ -376,38 +408,47 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_tile_kernel(const Ti
         a = sa; bsum = sb;
         rb ^= 1;
     };
-    // this CTA's block of (padded) grid rows in the SpMV / vector phases
+    // element-wise phases: fn(idx) for every 16-byte item (4 cells of a tile row) of this warp's blocks
+    auto for_items = [&](auto fn) {
+        for (int blk = wg; blk < NB; blk += nwg) {
+            const int g = blk / S, tc = blk - g * S - lane;
+            if ((unsigned)tc < (unsigned)ntile && g * 32 + lane < ntr) {
+#pragma unroll
+                for (int i = 0; i < kTM; i++) fn(vimg(blk, i, lane));
+            }
+        }
+    };
+    // this CTA's share of the padded grid rows in the row-major passes (setup, pivots, result)
     const int rows_cta = (dyp + C - 1) / C;
     const int row_lo = min(dyp, rank * rows_cta), row_hi = min(dyp, row_lo + rows_cta);
-    const int q_lo = row_lo * dxp, q_hi = row_hi * dxp;           // multiples of 4
 
-    // ---- setup: canonical slots, padded row-major planes, NaN guard (":245-256") ---------------------------------
+    // ---- setup: canonical slots scattered into the images, NaN guard (":245-256") ---------------------------------
     double nv = 0.0, nb = 0.0;
 #pragma unroll 8
     for (int i = rank * NT + tid; i < nnz_c; i += C * NT) { const double a = values_c[i]; nv += a * a; }
     const float sg = prm.sign;
     for (int t = row_lo + warp; t < row_hi; t += NW) {
         for (int xx = lane; xx < dxp; xx += 32) {
-            const int q = t * dxp + xx;
+            const size_t qc = ccell(geo, t, xx), qv = vcell(geo, t, xx);
             if (t < dy && xx < dx) {
                 const int i = t * dx + xx;
                 const float bi = rhs_g[i];
-                b[q] = bi; nb += (double)bi * bi;
-                x[q] = x0_g[i];                                       // cublasScopy(x_old -> x) (":261")
+                ((float *)b)[qv] = bi; nb += (double)bi * bi;
+                ((float *)x)[qv] = x0_g[i];                           // cublasScopy(x_old -> x) (":261")
                 auto val4 = [&](const int4 s4) {
                     return make_float4(s4.x >= 0 ? sg * values_c[s4.x] : 0.0f, s4.y >= 0 ? sg * values_c[s4.y] : 0.0f,
                                        s4.z >= 0 ? sg * values_c[s4.z] : 0.0f, s4.w >= 0 ? sg * values_c[s4.w] : 0.0f);
                 };
-                pl.alow[q] = val4(T.c_lsrc[i]);
-                pl.arv[q] = val4(T.c_lrev[i]);
-                pl.uval[q] = val4(T.c_usrc[i]);
+                pl.alow[qc] = val4(T.c_lsrc[i]);
+                pl.arv[qc] = val4(T.c_lrev[i]);
+                pl.uval[qc] = val4(T.c_usrc[i]);
                 const int ds = T.c_dsrc[i];
-                pl.adiag[q] = ds >= 0 ? sg * values_c[ds] : 1.0f;
+                ((float *)pl.adiag)[qv] = ds >= 0 ? sg * values_c[ds] : 1.0f;
             } else {                                                  // padding: unit diagonal, nothing else
                 const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                b[q] = 0.0f; x[q] = 0.0f;
-                pl.alow[q] = z4; pl.arv[q] = z4; pl.uval[q] = z4;
-                pl.adiag[q] = 1.0f;
+                ((float *)b)[qv] = 0.0f; ((float *)x)[qv] = 0.0f;
+                pl.alow[qc] = z4; pl.arv[qc] = z4; pl.uval[qc] = z4;
+                ((float *)pl.adiag)[qv] = 1.0f;
             }
         }
     }
@@ -425,86 +466,127 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_tile_kernel(const Ti
         const float *d_in = prm.pivots_in + (size_t)sample * prm.n_face + face_off;      // caller's row order
         for (int t = row_lo + warp; t < row_hi; t += NW) {
             for (int xx = lane; xx < dxp; xx += 32) {
-                const int q = t * dxp + xx;
+                const size_t qc = ccell(geo, t, xx), qv = vcell(geo, t, xx);
                 if (t < dy && xx < dx) {
                     const int i = t * dx + xx;
-                    const float4 a = pl.alow[q];
+                    const float4 a = pl.alow[qc];
                     const float p0 = t == far_l.ya ? d_in[far_l.yb * dx + xx] : 1.0f, p2 = xx == far_l.xa ? d_in[t * dx + far_l.xb] : 1.0f;
                     const float p1 = t > 0 ? d_in[i - dx] : 1.0f, p3 = xx > 0 ? d_in[i - 1] : 1.0f;
-                    pl.lval[q] = make_float4(__fdiv_rn(a.x, p0), __fdiv_rn(a.y, p1), __fdiv_rn(a.z, p2), __fdiv_rn(a.w, p3));
-                    pl.udiag[q] = d_in[i];
+                    pl.lval[qc] = make_float4(ilu_div(a.x, p0), ilu_div(a.y, p1), ilu_div(a.z, p2), ilu_div(a.w, p3));
+                    ((float *)pl.udiag)[qv] = d_in[i];
                 } else {
-                    pl.lval[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    pl.udiag[q] = 1.0f;
+                    pl.lval[qc] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    ((float *)pl.udiag)[qv] = 1.0f;
                 }
             }
         }
         cluster.sync();
     } else {
+        cluster.sync();                                              // the images are complete
         tile_sweep<0>(c, pl, far_l, nullptr, zs, ++sid);
         cluster.sync();
         if (prm.pivots_out) {
             float *d_out = prm.pivots_out + (size_t)sample * prm.n_face + face_off;
             for (int t = row_lo + warp; t < min(row_hi, dy); t += NW)
-                for (int xx = lane; xx < dx; xx += 32) d_out[t * dx + xx] = pl.udiag[t * dxp + xx];
+                for (int xx = lane; xx < dx; xx += 32) d_out[t * dx + xx] = ((const float *)pl.udiag)[vcell(geo, t, xx)];
         }
     }
     DPISO_TILE_TICK(1);
 
-    auto precondition = [&](const float *src) {                      // zs = U^-1 L^-1 src   (csrsv2 x2, ":321-327")
+    auto precondition = [&](const float4 *src) {                     // zs = U^-1 L^-1 src   (csrsv2 x2, ":321-327")
         cluster.sync();                                              // src complete in global memory
         tile_sweep<1>(c, pl, far_l, src, zs, ++sid);
         cluster.sync();
         tile_sweep<2>(c, pl, far_u, nullptr, zs, ++sid);
         cluster.sync();
     };
-    // y = A vec over this CTA's rows (CsrmvEx: lower slots, diagonal, upper slots = ascending column order); fn(q, y) consumes
-    auto spmv_rows = [&](const float *vec, auto fn) {
-        for (int t = row_lo + warp; t < row_hi; t += NW) {
-            const bool cl = t == far_l.ya, cu = t == far_u.ya;
-            const float *vrow = vec + (size_t)t * dxp;
-            const float *vcl = vec + (size_t)(cl ? far_l.yb : 0) * dxp, *vcu = vec + (size_t)(cu ? far_u.yb : 0) * dxp;
-#pragma unroll 2
-            for (int xx = lane; xx < dxp; xx += 32) {
-                const int q = t * dxp + xx;
-                const float4 lo = pl.alow[q], up = pl.uval[q];
-                const float dg = pl.adiag[q];
-                const float l0 = cl ? vcl[xx] : 0.0f, l1 = t > 0 ? vrow[xx - dxp] : 0.0f;
-                const float l2 = xx == far_l.xa ? vrow[far_l.xb] : 0.0f, l3 = xx > 0 ? vrow[xx - 1] : 0.0f;
-                const float u0 = xx < dxp - 1 ? vrow[xx + 1] : 0.0f, u1 = xx == far_u.xa ? vrow[far_u.xb] : 0.0f;
-                const float u2 = t < dyp - 1 ? vrow[xx + dxp] : 0.0f, u3 = cu ? vcu[xx] : 0.0f;
-                float acc = fmaf(lo.x, l0, 0.0f);
-                acc = fmaf(lo.y, l1, acc);
-                acc = fmaf(lo.z, l2, acc);
-                acc = fmaf(lo.w, l3, acc);
-                acc = fmaf(dg, vrow[xx], acc);
-                acc = fmaf(up.x, u0, acc);
-                acc = fmaf(up.y, u1, acc);
-                acc = fmaf(up.z, u2, acc);
-                acc = fmaf(up.w, u3, acc);
-                fn(q, acc);
+    // y = A vec tile by tile (CsrmvEx per row: lower slots, diagonal, upper slots = ascending column order).  The
+    // x-neighbours of a tile are the same lane's tiles in blocks sigma -+ 1, the y-neighbours lane -+ 1 of those blocks
+    // (lane 31 / 0 of the neighbouring warp group at the edges).  fn(idx, y4) consumes one tile row.
+    auto spmv_tiles = [&](const float4 *vec, auto fn) {
+        for (int blk = wg; blk < NB; blk += nwg) {
+            const int g = blk / S, sgm = blk - g * S, tc = sgm - lane, tr = g * 32 + lane;
+            if (!((unsigned)tc < (unsigned)ntile && tr < ntr)) continue;
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 o[kTM];
+            float lw[kTM], rx[kTM], wrl[kTM], wru[kTM];
+#pragma unroll
+            for (int i = 0; i < kTM; i++) {
+                o[i] = vec[vimg(blk, i, lane)];
+                lw[i] = tc > 0 ? vec[vimg(blk - 1, i, lane)].w : 0.0f;
+                rx[i] = tc < ntile - 1 ? vec[vimg(blk + 1, i, lane)].x : 0.0f;
+                wrl[i] = 0.0f; wru[i] = 0.0f;
+            }
+            const float4 tp4 = tr > 0 ? (lane > 0 ? vec[vimg(blk - 1, 3, lane - 1)] : vec[vimg((g - 1) * S + tc + 31, 3, 31)]) : z4;
+            const float4 bt4 = tr < ntr - 1 ? (lane < 31 ? vec[vimg(blk + 1, 0, lane + 1)] : vec[vimg((g + 1) * S + tc, 0, 0)]) : z4;
+            if (far_l.xa >= 0 && tc == (far_l.xa >> 2)) {
+#pragma unroll
+                for (int i = 0; i < kTM; i++) wrl[i] = f4c(vec[vimg(g * S + (far_l.xb >> 2) + lane, i, lane)], far_l.xb & 3);
+            }
+            if (far_u.xa >= 0 && tc == (far_u.xa >> 2)) {
+#pragma unroll
+                for (int i = 0; i < kTM; i++) wru[i] = f4c(vec[vimg(g * S + (far_u.xb >> 2) + lane, i, lane)], far_u.xb & 3);
+            }
+            float4 cwl = z4, cwu = z4;                               // in-column wrap operands (one tile row of the system each)
+            if (far_l.ya >= 0 && tr == (far_l.ya >> 2)) {
+                const int ytr = far_l.yb >> 2;
+                cwl = vec[vimg((ytr >> 5) * S + tc + (ytr & 31), far_l.yb & 3, ytr & 31)];
+            }
+            if (far_u.ya >= 0 && tr == (far_u.ya >> 2)) {
+                const int ytr = far_u.yb >> 2;
+                cwu = vec[vimg((ytr >> 5) * S + tc + (ytr & 31), far_u.yb & 3, ytr & 31)];
+            }
+#pragma unroll
+            for (int i = 0; i < kTM; i++) {
+                const int t = tr * kTM + i;
+                const float4 dg4 = pl.adiag[vimg(blk, i, lane)];
+                const float4 up_row = i > 0 ? o[i - 1] : tp4, dn_row = i < kTM - 1 ? o[i + 1] : bt4;
+                float y[kTK];
+#pragma unroll
+                for (int j = 0; j < kTK; j++) {
+                    const int xx = tc * kTK + j;
+                    const float4 lo = pl.alow[cimg(blk, i * kTK + j, lane)], up = pl.uval[cimg(blk, i * kTK + j, lane)];
+                    const float l0 = t == far_l.ya ? f4c(cwl, j) : 0.0f, l1 = f4c(up_row, j);
+                    const float l2 = xx == far_l.xa ? wrl[i] : 0.0f, l3 = j > 0 ? f4c(o[i], j - 1) : lw[i];
+                    const float u0 = j < kTK - 1 ? f4c(o[i], j + 1) : rx[i], u1 = xx == far_u.xa ? wru[i] : 0.0f;
+                    const float u2 = f4c(dn_row, j), u3 = t == far_u.ya ? f4c(cwu, j) : 0.0f;
+                    float acc = fmaf(lo.x, l0, 0.0f);
+                    acc = fmaf(lo.y, l1, acc);
+                    acc = fmaf(lo.z, l2, acc);
+                    acc = fmaf(lo.w, l3, acc);
+                    acc = fmaf(f4c(dg4, j), f4c(o[i], j), acc);
+                    acc = fmaf(up.x, u0, acc);
+                    acc = fmaf(up.y, u1, acc);
+                    acc = fmaf(up.z, u2, acc);
+                    acc = fmaf(up.w, u3, acc);
+                    y[j] = acc;
+                }
+                fn(vimg(blk, i, lane), make_float4(y[0], y[1], y[2], y[3]));
             }
         }
+    };
+    auto dot4 = [](const float4 a, const float4 c4) {
+        double s = (double)a.x * c4.x; s += (double)a.y * c4.y; s += (double)a.z * c4.z; s += (double)a.w * c4.w;
+        return s;
     };
 
     float alpha = 1.f, rho = 1.f, rhop = 1.f, omega = 1.f, beta, nrm_r = 0.f;
     int it_count = 0, restarts = 0, exit_kind = 3;
     const float tol = prm.tol;
-    auto ld4 = [](const float *a) { return *reinterpret_cast<const float4 *>(a); };
-    auto st4 = [](float *a, const float4 val) { *reinterpret_cast<float4 *>(a) = val; };
 
     for (int restart = 0; restart < 2; restart++) {
         restarts = restart;
         cluster.sync();                                              // x complete (setup / restart reset)
         double s0 = 0.0, s1 = 0.0;
-        spmv_rows(x, [&](int q, float ax) {                          // r = b - A x  (":275-282")
-            const float rq = __fsub_rn(b[q], ax);
-            r[q] = rq; s0 += (double)rq * rq;
+        spmv_tiles(x, [&](size_t q, const float4 ax) {               // r = b - A x  (":275-282")
+            const float4 bb = b[q];
+            const float4 rq = make_float4(__fsub_rn(bb.x, ax.x), __fsub_rn(bb.y, ax.y), __fsub_rn(bb.z, ax.z), __fsub_rn(bb.w, ax.w));
+            r[q] = rq; s0 += dot4(rq, rq);
         });
         cluster_sum2(s0, s1);
         nrm_r = (float)sqrt(s0);
         if (nrm_r < tol) { exit_kind = 0; break; }                   // lucky guess (":287-289")
-        for (int q = q_lo + tid; q < q_hi; q += NT) { rh[q] = r[q]; p[q] = 0.0f; v[q] = 0.0f; }
+        for_items([&](size_t q) { rh[q] = r[q]; p[q] = make_float4(0.f, 0.f, 0.f, 0.f); v[q] = make_float4(0.f, 0.f, 0.f, 0.f); });
         exit_kind = 3;
         float rho_next = (float)s0;                                  // r.rh with rh = r
         for (int it = 0; it < prm.max_it; it++) {
@@ -512,33 +594,31 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_tile_kernel(const Ti
             rhop = rho;
             rho = rho_next;
             beta = __fmul_rn(__fdiv_rn(rho, rhop), __fdiv_rn(alpha, omega));
-#pragma unroll 2
-            for (int q = q_lo + tid * 4; q < q_hi; q += NT * 4) {    // p = r + beta (p - omega v)  (":315-317")
-                const float4 vv = ld4(v + q), rr = ld4(r + q);
-                float4 pp = ld4(p + q);
+            for_items([&](size_t q) {                                // p = r + beta (p - omega v)  (":315-317")
+                const float4 vv = v[q], rr = r[q];
+                float4 pp = p[q];
                 pp.x = __fadd_rn(__fmul_rn(beta, fmaf(-omega, vv.x, pp.x)), rr.x);
                 pp.y = __fadd_rn(__fmul_rn(beta, fmaf(-omega, vv.y, pp.y)), rr.y);
                 pp.z = __fadd_rn(__fmul_rn(beta, fmaf(-omega, vv.z, pp.z)), rr.z);
                 pp.w = __fadd_rn(__fmul_rn(beta, fmaf(-omega, vv.w, pp.w)), rr.w);
-                st4(p + q, pp);
-            }
+                p[q] = pp;
+            });
             DPISO_TILE_TICK(4);
             precondition(p);                                         // zs = p_hat
             DPISO_TILE_TICK(2);
             s0 = 0.0; s1 = 0.0;
-            spmv_rows(zs, [&](int q, float vq) { v[q] = vq; s0 += (double)rh[q] * vq; });
+            spmv_tiles(zs, [&](size_t q, const float4 vq) { v[q] = vq; s0 += dot4(rh[q], vq); });
             cluster_sum2(s0, s1);
             alpha = __fdiv_rn(rho, (float)s0);
             s0 = 0.0; s1 = 0.0;
-#pragma unroll 2
-            for (int q = q_lo + tid * 4; q < q_hi; q += NT * 4) {    // x += alpha p_hat ; r -= alpha v ; |r|
-                const float4 zz = ld4(zs + q), vv = ld4(v + q);
-                float4 xx = ld4(x + q), rr = ld4(r + q);
+            for_items([&](size_t q) {                                // x += alpha p_hat ; r -= alpha v ; |r|
+                const float4 zz = zs[q], vv = v[q];
+                float4 xx = x[q], rr = r[q];
                 xx.x = fmaf(alpha, zz.x, xx.x); xx.y = fmaf(alpha, zz.y, xx.y); xx.z = fmaf(alpha, zz.z, xx.z); xx.w = fmaf(alpha, zz.w, xx.w);
                 rr.x = fmaf(-alpha, vv.x, rr.x); rr.y = fmaf(-alpha, vv.y, rr.y); rr.z = fmaf(-alpha, vv.z, rr.z); rr.w = fmaf(-alpha, vv.w, rr.w);
-                st4(x + q, xx); st4(r + q, rr);
-                s0 += (double)rr.x * rr.x; s0 += (double)rr.y * rr.y; s0 += (double)rr.z * rr.z; s0 += (double)rr.w * rr.w;
-            }
+                x[q] = xx; r[q] = rr;
+                s0 += dot4(rr, rr);
+            });
             cluster_sum2(s0, s1);
             nrm_r = (float)sqrt(s0);
             if (nrm_r < tol) { exit_kind = 1; break; }
@@ -546,34 +626,32 @@ __global__ void __launch_bounds__(kBicgThreads, 1) bicgstab_tile_kernel(const Ti
             precondition(r);                                         // zs = s_hat
             DPISO_TILE_TICK(2);
             s0 = 0.0; s1 = 0.0;
-            spmv_rows(zs, [&](int q, float tq) { tt[q] = tq; s0 += (double)tq * r[q]; s1 += (double)tq * tq; });
+            spmv_tiles(zs, [&](size_t q, const float4 tq) { tt[q] = tq; s0 += dot4(tq, r[q]); s1 += dot4(tq, tq); });
             cluster_sum2(s0, s1);
             omega = __fdiv_rn((float)s0, (float)s1);
             s0 = 0.0; s1 = 0.0;
-#pragma unroll 2
-            for (int q = q_lo + tid * 4; q < q_hi; q += NT * 4) {    // x += omega s_hat ; r -= omega t ; |r| ; r.rh
-                const float4 zz = ld4(zs + q), t4 = ld4(tt + q), hh = ld4(rh + q);
-                float4 xx = ld4(x + q), rr = ld4(r + q);
+            for_items([&](size_t q) {                                // x += omega s_hat ; r -= omega t ; |r| ; r.rh
+                const float4 zz = zs[q], t4 = tt[q], hh = rh[q];
+                float4 xx = x[q], rr = r[q];
                 xx.x = fmaf(omega, zz.x, xx.x); xx.y = fmaf(omega, zz.y, xx.y); xx.z = fmaf(omega, zz.z, xx.z); xx.w = fmaf(omega, zz.w, xx.w);
                 rr.x = fmaf(-omega, t4.x, rr.x); rr.y = fmaf(-omega, t4.y, rr.y); rr.z = fmaf(-omega, t4.z, rr.z); rr.w = fmaf(-omega, t4.w, rr.w);
-                st4(x + q, xx); st4(r + q, rr);
-                s0 += (double)rr.x * rr.x; s0 += (double)rr.y * rr.y; s0 += (double)rr.z * rr.z; s0 += (double)rr.w * rr.w;
-                s1 += (double)rr.x * hh.x; s1 += (double)rr.y * hh.y; s1 += (double)rr.z * hh.z; s1 += (double)rr.w * hh.w;
-            }
+                x[q] = xx; r[q] = rr;
+                s0 += dot4(rr, rr); s1 += dot4(rr, hh);
+            });
             cluster_sum2(s0, s1);
             nrm_r = (float)sqrt(s0);
             rho_next = (float)s1;
             if (nrm_r < tol) { exit_kind = 2; break; }
         }
         if (nrm_r > __fmul_rn(tol, 100.0f) || isnan(nrm_r)) {        // ":392-404"
-            for (int q = q_lo + tid; q < q_hi; q += NT) x[q] = 0.0f;
+            for_items([&](size_t q) { x[q] = make_float4(0.f, 0.f, 0.f, 0.f); });
             if (restart == 1) restarts = 2;
         } else break;
     }
-    cluster.sync();                                                  // no CTA leaves while packets may be in flight
+    cluster.sync();                                                  // x complete; no CTA leaves while packets may be in flight
     DPISO_TILE_TICK(4);
-    for (int t = row_lo + warp; t < min(row_hi, dy); t += NW)        // this CTA's rows of the result (its own writes)
-        for (int xx = lane; xx < dx; xx += 32) x_g[t * dx + xx] = x[t * dxp + xx];
+    for (int t = row_lo + warp; t < min(row_hi, dy); t += NW)        // back to the caller's row order
+        for (int xx = lane; xx < dx; xx += 32) x_g[t * dx + xx] = ((const float *)x)[vcell(geo, t, xx)];
     if (rank == 0 && tid == 0) {
         int *st = prm.stats + (size_t)sys * 4;
         st[0] = it_count; st[1] = restarts; st[2] = warn; st[3] = exit_kind;
@@ -587,13 +665,15 @@ static void tile_padded(const dpiso_bicg_tables *h, int *dxp, int *dyp) {
     *dxp = (h->dx + kTK - 1) / kTK * kTK;
     *dyp = (h->n / h->dx + kTM - 1) / kTM * kTM;
 }
+static size_t tile_blocks(const dpiso_bicg_tables *h) {
+    int dxp, dyp;
+    tile_padded(h, &dxp, &dyp);
+    return (size_t)((dyp / kTM + 31) / 32) * (size_t)(dxp / kTK + 31);
+}
 
 size_t tile_workspace_floats(const dpiso_bicg_tables *h_tab_u, const dpiso_bicg_tables *h_tab_v) {
-    int ax, ay, bx, by;
-    tile_padded(h_tab_u, &ax, &ay);
-    tile_padded(h_tab_v, &bx, &by);
-    const size_t np = (size_t)ax * ay > (size_t)bx * by ? (size_t)ax * ay : (size_t)bx * by;
-    return 22 * np;
+    const size_t bu = tile_blocks(h_tab_u), bv = tile_blocks(h_tab_v);
+    return (size_t)kTileBlockFloats * (bu > bv ? bu : bv);
 }
 
 int launch_bicgstab_tile(BicgParams &prm, const dpiso_bicg_tables *h_tab_u, const dpiso_bicg_tables *h_tab_v, int batch,
@@ -613,8 +693,8 @@ int launch_bicgstab_tile(BicgParams &prm, const dpiso_bicg_tables *h_tab_u, cons
     tile_padded(h_tab_u, &tp.dxp[0], &tp.dyp[0]);
     tile_padded(h_tab_v, &tp.dxp[1], &tp.dyp[1]);
     tp.dxp_max = tp.dxp[0] > tp.dxp[1] ? tp.dxp[0] : tp.dxp[1];
-    tp.np_max = tile_workspace_floats(h_tab_u, h_tab_v) / 22;
-    if (22 * tp.np_max > prm.ws_floats) return DPISO_EUNSUPPORTED;
+    tp.blocks_max = tile_workspace_floats(h_tab_u, h_tab_v) / kTileBlockFloats;
+    if ((size_t)kTileBlockFloats * tp.blocks_max > prm.ws_floats) return DPISO_EUNSUPPORTED;
     const int dymax = tp.dyp[0] > tp.dyp[1] ? tp.dyp[0] : tp.dyp[1];
     const int warps = (dymax / kTM + 31) / 32;                    // sweep warps per system
     const size_t kBudget = 224 * 1024;

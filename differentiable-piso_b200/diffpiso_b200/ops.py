@@ -260,6 +260,11 @@ def predictor_rhs_adj(g, grhs, dirichlet_u8, dy, dx, beta, want_force, want_dval
     return gvel, gforce, gdvals, gfree
 
 
+# test hook: fill solver workspaces with NaN bit patterns before every call (the kernels must never read workspace they
+# have not written in the same call)
+POISON_SCRATCH = False
+
+
 @_on_device_of(0)
 def bicgstab_ilu(g, values, rhs, x0, tol, max_it, transpose=False, negate=False, pivots_out=None, pivots_in=None):
     """-> x [B, nf], stats int32 [B, 2, 4] (iterations, restarts, warn, exit kind), warn float32 [1].
@@ -270,6 +275,8 @@ def bicgstab_ilu(g, values, rhs, x0, tol, max_it, transpose=False, negate=False,
     tu, tv = g.tables(transpose)
     ws_floats = N.lib.dpiso_bicgstab_workspace_floats(C.byref(tu), C.byref(tv))
     ws = g.scratch("bicgstab", b * 2 * ws_floats * 4)
+    if POISON_SCRATCH:
+        ws.fill_(255)                                     # every float a NaN: a read of unwritten workspace shows up in x
     x = torch.empty_like(rhs)
     stats = torch.empty((b, 2, 4), dtype=torch.int32, device=rhs.device)
     warn = torch.empty(1, dtype=torch.float32, device=rhs.device)

@@ -295,9 +295,11 @@ def test_bicgstab_cluster_kernel_matches_oracle(name, cluster, transpose):
     rhs = (vels * _beta(s)).astype(np.float32)
     N.lib.dpiso_bicgstab_set_debug(64)
     N.lib.dpiso_bicgstab_set_band_cluster(cluster)
+    ops.POISON_SCRATCH = True
     try:
         x, stats, warn = ops.bicgstab_ilu(g, neg, _t(rhs), _t(vels), s["bicg_tol"], s["bicg_max_it"], transpose)
     finally:
+        ops.POISON_SCRATCH = False
         N.lib.dpiso_bicgstab_set_debug(-1)
         N.lib.dpiso_bicgstab_set_band_cluster(0)
     x, stats = x.cpu().numpy(), stats.cpu().numpy()
@@ -348,8 +350,9 @@ def test_bicgstab_cluster_kernel_factor_reuse_and_pivots():
                                           ("periodic128", 4), ("ldc_like64", 2), ("periodic264x256", 0), ("periodic264x256", 5)])
 @pytest.mark.parametrize("transpose", [False, True])
 def test_bicgstab_tile_kernel_matches_oracle_and_row_kernel(name, cluster, transpose):
-    """The default predictor kernel (bicgstab_tile.cu: 4 x 4 register tiles per sweep step, packets between warps and
-    CTAs) with the heuristic and with forced cluster sizes: iteration counts within +-1 of the oracle, restarts / warn
+    """The register-tiled predictor kernel (bicgstab_tile.cu: 4 x 4 tiles per sweep step, sweep-image storage, packets
+    between warps and CTAs; default beyond ~1100 rows per component, forced here with debug flag 256) with the heuristic
+    and with forced cluster sizes: iteration counts within +-1 of the oracle, restarts / warn
     identical, solution within 1e-5 relative L2, for A and A^T; and the ILU(0) pivots equal those of the row-per-thread
     kernel bit for bit (same fma / division chain per row)."""
     from diffpiso_b200 import _native as N, ops
@@ -361,11 +364,15 @@ def test_bicgstab_tile_kernel_matches_oracle_and_row_kernel(name, cluster, trans
     rhs = (vels * _beta(s)).astype(np.float32)
     piv = torch.zeros(2, g.nf, device=DEV)
     N.lib.dpiso_bicgstab_set_tile_cluster(cluster)
+    N.lib.dpiso_bicgstab_set_debug(256)
+    ops.POISON_SCRATCH = True
     try:
         x, stats, warn = ops.bicgstab_ilu(g, values, _t(rhs), _t(vels), s["bicg_tol"], s["bicg_max_it"], transpose, negate=True,
                                           pivots_out=piv)
     finally:
+        ops.POISON_SCRATCH = False
         N.lib.dpiso_bicgstab_set_tile_cluster(0)
+        N.lib.dpiso_bicgstab_set_debug(-1)
     if name != "periodic264x256":                                  # the row-per-thread kernel covers at most 512 rows
         piv_rows = torch.zeros(2, g.nf, device=DEV)
         N.lib.dpiso_bicgstab_set_debug(128)
@@ -387,3 +394,37 @@ def test_bicgstab_tile_kernel_matches_oracle_and_row_kernel(name, cluster, trans
             assert abs(int(got[0]) - st["iterations"]) <= 1, (name, i, comp, got, st)
             assert int(got[1]) == st["restarts"] and int(got[2]) == st["warn"], (name, i, comp, got, st)
             assert rel_l2(x[i, r0:r1], ox) < 1e-5, (name, i, comp, rel_l2(x[i, r0:r1], ox), got, st)
+
+
+@pytest.mark.parametrize("dbg,cluster", [(0, 0), (64, 1), (64, 2), (256, 0), (256, 2), (8, 0)])
+def test_bicgstab_kernels_are_deterministic_and_never_read_unwritten_workspace(dbg, cluster):
+    """Every predictor kernel (0 default rows kernel, 64 cluster kernel, 256 tile kernel, 8 level-major) returns the same bits
+    on every run, whether the workspace holds the previous run's data or NaN patterns.  A 65 x 64 cavity (n_u = 4225: odd, so
+    the scalar tails of the float4 loops are exercised; this is the case that exposed a missing barrier between the vector
+    initialisation and the first p update of the cluster kernel)."""
+    from diffpiso_b200 import _native as N, ops
+    s = ALL_SETUPS["ldc_like64"]()
+    g, m = _geom(s), _masks(s)
+    vels = np.stack([random_fields(s, 50 + i)[0] for i in range(2)])
+    values, _ = ops.assemble(g, _t(vels), m["dirichlet"], m["active"], m["noslip"], _t(np.atleast_1d(s["visc"])), s["dy"],
+                             s["dx"], _beta(s))
+    rhs = _t((vels * _beta(s)).astype(np.float32))
+    N.lib.dpiso_bicgstab_set_debug(dbg)
+    N.lib.dpiso_bicgstab_set_band_cluster(cluster)
+    N.lib.dpiso_bicgstab_set_tile_cluster(cluster)
+    try:
+        for transpose in (False, True):
+            ref = None
+            for k in range(8):
+                ops.POISON_SCRATCH = k % 2 == 0
+                x, st, _ = ops.bicgstab_ilu(g, values, rhs, _t(vels), s["bicg_tol"], s["bicg_max_it"], transpose, negate=True)
+                assert torch.isfinite(x).all()
+                if ref is None:
+                    ref = (x.clone(), st.clone())
+                else:
+                    assert torch.equal(x, ref[0]) and torch.equal(st, ref[1]), (dbg, cluster, transpose, k)
+    finally:
+        ops.POISON_SCRATCH = False
+        N.lib.dpiso_bicgstab_set_debug(-1)
+        N.lib.dpiso_bicgstab_set_band_cluster(0)
+        N.lib.dpiso_bicgstab_set_tile_cluster(0)
