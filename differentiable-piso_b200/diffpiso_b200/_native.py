@@ -78,6 +78,7 @@ _SIGS = {
     "dpiso_pressure_cg_last_config": ([_P], _I),
     "dpiso_pressure_cg_set_tuning": ([_I, _I], _I),
     "dpiso_pressure_cg_set_reduction_order": ([_I], _I),
+    "dpiso_pressure_cg_set_static_nx": ([_I], _I),
 }
 for _name, (_args, _res) in _SIGS.items():
     _fn = getattr(lib, _name)

@@ -260,6 +260,8 @@ int dpiso_pressure_cg_set_tuning(int cluster, int variant);
  * alpha -> update x, r -> {r.z} -> beta: two cluster-wide reductions per iteration) instead of the default merged
  * single reduction (r_new.z = r.z - alpha z.z, DESIGN.md deviation D2).  Cluster-resident kernel only. */
 int dpiso_pressure_cg_set_reduction_order(int two_reductions);
+/* A/B switch: 0 = never use the instantiations with a compile-time row length (nx = 128), 1 (default) = use them */
+int dpiso_pressure_cg_set_static_nx(int enable);
 
 #ifdef __cplusplus
 }

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--fp32", action="store_true")
     ap.add_argument("--max-it", type=int, default=10000)
     ap.add_argument("--check", type=int, default=0, help="compare the first N samples with the CPU oracle")
+    ap.add_argument("--static-nx", type=int, default=1, help="0: never use the compile-time-nx kernel instantiations")
     args = ap.parse_args()
     from diffpiso_b200 import ops, setups as SU
     from diffpiso_b200 import _native as N
@@ -46,6 +47,7 @@ def main():
     div = div - div.mean(dim=1, keepdim=True)
     lap = ops.laplace(g, ones, ones, a_diag, 1, beta, float(np.float32(s["dx"] / s["dy"])), fp64=not args.fp32)
     N.lib.dpiso_pressure_cg_set_tuning(args.cluster, args.variant)
+    N.lib.dpiso_pressure_cg_set_static_nx(args.static_nx)
     tol = 1e-8 if not args.fp32 else 1e-5
     x, its = ops.pressure_cg(g, lap, div, tol, args.max_it, 1000, True)
     torch.cuda.synchronize()
