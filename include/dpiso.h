@@ -204,8 +204,9 @@ int dpiso_bicgstab_ilu(int batch, const dpiso_bicg_tables *h_tab_u, const dpiso_
                        int max_it, float *x, int *stats, float *warn, float *pivots_out, const float *pivots_in,
                        float *workspace, void *stream);
 int dpiso_bicgstab_supports_factor_reuse(const dpiso_bicg_tables *h_tab_u, const dpiso_bicg_tables *h_tab_v);
-/* profiling / test switch: dbg >= 0 overrides the DPISO_BICG_DBG environment variable (8 forces the level-major
- * kernel), -1 restores it */
+/* profiling / test switch: dbg >= 0 overrides the DPISO_BICG_DBG environment variable, -1 restores it.  Bits: 8 force the
+ * level-major fallback kernel, 64 the cluster-per-system kernel, 128 the row-per-thread kernel, 256 the tile kernel,
+ * 1024 tile kernel with TMA bulk copies instead of per-lane cp.async, 16 / 32 / 512 A/B variants of the sweeps */
 int dpiso_bicgstab_set_debug(int dbg);
 /* 0 (default): reuse pivots only for structurally symmetric components; 1: for every component */
 int dpiso_bicgstab_set_reuse_policy(int always);

@@ -349,7 +349,8 @@ def test_bicgstab_cluster_kernel_factor_reuse_and_pivots():
                                           ("periodic64", 2), ("tml64x128", 3), ("sml32x128", 0), ("periodic128", 0),
                                           ("periodic128", 4), ("ldc_like64", 2), ("periodic264x256", 0), ("periodic264x256", 5)])
 @pytest.mark.parametrize("transpose", [False, True])
-def test_bicgstab_tile_kernel_matches_oracle_and_row_kernel(name, cluster, transpose):
+@pytest.mark.parametrize("tma", [0, 1024])
+def test_bicgstab_tile_kernel_matches_oracle_and_row_kernel(name, cluster, transpose, tma):
     """The register-tiled predictor kernel (bicgstab_tile.cu: 4 x 4 tiles per sweep step, sweep-image storage, packets
     between warps and CTAs; default beyond ~1100 rows per component, forced here with debug flag 256) with the heuristic
     and with forced cluster sizes: iteration counts within +-1 of the oracle, restarts / warn
@@ -364,7 +365,7 @@ def test_bicgstab_tile_kernel_matches_oracle_and_row_kernel(name, cluster, trans
     rhs = (vels * _beta(s)).astype(np.float32)
     piv = torch.zeros(2, g.nf, device=DEV)
     N.lib.dpiso_bicgstab_set_tile_cluster(cluster)
-    N.lib.dpiso_bicgstab_set_debug(256)
+    N.lib.dpiso_bicgstab_set_debug(256 | tma)                      # 1024: ring refilled by TMA bulk copies (cp.async.bulk + mbarrier)
     ops.POISON_SCRATCH = True
     try:
         x, stats, warn = ops.bicgstab_ilu(g, values, _t(rhs), _t(vels), s["bicg_tol"], s["bicg_max_it"], transpose, negate=True,
@@ -396,7 +397,7 @@ def test_bicgstab_tile_kernel_matches_oracle_and_row_kernel(name, cluster, trans
             assert rel_l2(x[i, r0:r1], ox) < 1e-5, (name, i, comp, rel_l2(x[i, r0:r1], ox), got, st)
 
 
-@pytest.mark.parametrize("dbg,cluster", [(0, 0), (64, 1), (64, 2), (256, 0), (256, 2), (8, 0)])
+@pytest.mark.parametrize("dbg,cluster", [(0, 0), (64, 1), (64, 2), (256, 0), (256, 2), (1280, 2), (8, 0)])
 def test_bicgstab_kernels_are_deterministic_and_never_read_unwritten_workspace(dbg, cluster):
     """Every predictor kernel (0 default rows kernel, 64 cluster kernel, 256 tile kernel, 8 level-major) returns the same bits
     on every run, whether the workspace holds the previous run's data or NaN patterns.  A 65 x 64 cavity (n_u = 4225: odd, so
