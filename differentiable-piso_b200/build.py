@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "diffpiso_b200", "libdpiso.so")
-SOURCES = ["piso_ops.cu", "pressure_cg.cu", "bicgstab.cu", "bicgstab_band.cu", "bicgstab_tile.cu", "piso_adjoint.cu", "tables.cu"]
+SOURCES = ["piso_ops.cu", "pressure_cg.cu", "bicgstab.cu", "bicgstab_band.cu", "bicgstab_tile.cu", "bicgstab_f64.cu", "piso_adjoint.cu", "tables.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--threads", "4"]
 

@@ -68,6 +68,8 @@ _SIGS = {
     "dpiso_bicgstab_set_band_cluster": ([_I], _I),
     "dpiso_bicgstab_set_tile_cluster": ([_I], _I),
     "dpiso_bicgstab_supports_factor_reuse": ([_P, _P], _I),
+    "dpiso_bicgstab_f64_workspace_bytes": ([_P, _P], _SZ),
+    "dpiso_bicgstab_ilu_f64": ([_I, _P, _P, _I, _I, _P, _I, _P, _P, _F, _I, _P, _P, _P, _P, _P], _I),
     "dpiso_bicgstab_ilu": ([_I, _P, _P, _I, _I, _P, _I, _P, _P, _F, _I, _P, _P, _P, _P, _P, _P, _P], _I),
     "dpiso_laplace_f64": ([_I, _I, _I, _P, _P, _P, _I, _F, _F, _P, _P], _I),
     "dpiso_laplace_f32": ([_I, _I, _I, _P, _P, _P, _I, _F, _F, _P, _P], _I),

@@ -42,10 +42,10 @@ class _BicgSolveFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, rhs, values, x0, solver, geom, transpose):
         pivots = None
-        if ctx.needs_input_grad[0] and solver.reuse_factors and ops.factor_reuse_supported(geom):
+        if ctx.needs_input_grad[0] and solver.reuse_factors and not solver.cast_to_double and ops.factor_reuse_supported(geom):
             pivots = torch.empty_like(rhs)
         x, stats, warn = ops.bicgstab_ilu(geom, values, rhs, x0, solver.accuracy, solver.max_iterations, transpose,
-                                          pivots_out=pivots)
+                                          pivots_out=pivots, fp64=solver.cast_to_double)
         solver.last_stats = stats
         ctx.solver, ctx.geom, ctx.transpose, ctx.has_pivots = solver, geom, transpose, pivots is not None
         ctx.save_for_backward(*([values, x0] + ([pivots] if pivots is not None else [])))
@@ -60,7 +60,8 @@ class _BicgSolveFn(torch.autograd.Function):
         # linear_solver.py:169-173: same op on ds with `not transpose`, same initial-guess tensor, times (1 - warn);
         # the ILU(0) pivots of the forward solve are reused where that is exact (structurally symmetric components)
         df, stats, warn = ops.bicgstab_ilu(ctx.geom, values, gx.contiguous(), x0, solver.accuracy, solver.max_iterations,
-                                           not ctx.transpose, pivots_in=saved[2] if ctx.has_pivots else None)
+                                           not ctx.transpose, pivots_in=saved[2] if ctx.has_pivots else None,
+                                           fp64=solver.cast_to_double)
         solver.last_adjoint_stats = stats
         # per-sample NaN guard (stats[:, :, 2]); the batch-wide OR is only the returned `warn` value
         keep = 1.0 - stats[:, :, 2].amax(dim=1, keepdim=True).to(torch.float32)
@@ -75,10 +76,10 @@ class LinearSolverCudaMultiBicgstabILU(LinearSolver):
     def __init__(self, accuracy=1e-5, max_iterations=2000, cast_to_double=False, reuse_factors=True):
         LinearSolver.__init__(self, 'CUDA dual iLU-preconditioned BiCGStab solve', supported_devices=('GPU',),
                               supports_guess=True, supports_batch=True, solver_type='iterative', input_format='csr')
-        if cast_to_double:
-            raise NotImplementedError("cast_to_double=True (fp64 BiCGStab) is not built; the reference default is fp32")
         self.max_iterations = int(max_iterations)
-        self.cast_to_double = False
+        # True: the fp64 variant (linear_solver.py:130-133): values / rhs are cast to fp64, the solution back to fp32;
+        # here the casts are fused into the kernel (dpiso_bicgstab_ilu_f64)
+        self.cast_to_double = bool(cast_to_double)
         self.accuracy = float(accuracy)
         # adjoint solves take the forward ILU(0) pivots instead of factorising A^T again, per component and only where
         # that is the reference's preconditioner up to rounding (structurally symmetric pattern); components
@@ -92,7 +93,8 @@ class LinearSolverCudaMultiBicgstabILU(LinearSolver):
         """The solve without autograd bookkeeping, for callers that own forward and backward themselves (piso_step):
         -> (x, warn float32 [1], stats int32 [B, 2, 4])."""
         x, stats, warn = ops.bicgstab_ilu(geom, values, rhs, x0, self.accuracy, self.max_iterations, transpose,
-                                          negate=negate, pivots_out=pivots_out, pivots_in=pivots_in)
+                                          negate=negate, pivots_out=None if self.cast_to_double else pivots_out,
+                                          pivots_in=None if self.cast_to_double else pivots_in, fp64=self.cast_to_double)
         if adjoint:
             self.last_adjoint_stats = stats
         else:

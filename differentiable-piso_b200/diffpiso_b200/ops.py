@@ -266,13 +266,26 @@ POISON_SCRATCH = False
 
 
 @_on_device_of(0)
-def bicgstab_ilu(g, values, rhs, x0, tol, max_it, transpose=False, negate=False, pivots_out=None, pivots_in=None):
+def bicgstab_ilu(g, values, rhs, x0, tol, max_it, transpose=False, negate=False, pivots_out=None, pivots_in=None,
+                 fp64=False):
     """-> x [B, nf], stats int32 [B, 2, 4] (iterations, restarts, warn, exit kind), warn float32 [1].
     Solves (values or, with negate, -values) x = rhs.  pivots_out / pivots_in [B, nf] float32: ILU(0) pivots written by /
-    taken from the solve of the other orientation (factor reuse; honoured where `factor_reuse_supported`)."""
+    taken from the solve of the other orientation (factor reuse; honoured where `factor_reuse_supported`).
+    fp64: the cast_to_double=True path of the reference's solver class (fp32 in, fp64 solve, fp32 out; no factor reuse)."""
     values, rhs, x0 = _f32(values), _f32(rhs), _f32(x0)
     b = rhs.shape[0]
     tu, tv = g.tables(transpose)
+    if fp64:
+        ws = g.scratch("bicgstab_f64", b * 2 * N.lib.dpiso_bicgstab_f64_workspace_bytes(C.byref(tu), C.byref(tv)))
+        if POISON_SCRATCH:
+            ws.fill_(255)
+        x = torch.empty_like(rhs)
+        stats = torch.empty((b, 2, 4), dtype=torch.int32, device=rhs.device)
+        warn = torch.empty(1, dtype=torch.float32, device=rhs.device)
+        N.check(N.lib.dpiso_bicgstab_ilu_f64(b, C.byref(tu), C.byref(tv), g.nnz_u, g.nnz_v, N.ptr(values), int(bool(negate)),
+                                             N.ptr(rhs), N.ptr(x0), float(tol), int(max_it), N.ptr(x), N.ptr(stats),
+                                             N.ptr(warn), N.ptr(ws), N.stream()), "dpiso_bicgstab_ilu_f64")
+        return x, stats, warn
     ws_floats = N.lib.dpiso_bicgstab_workspace_floats(C.byref(tu), C.byref(tv))
     ws = g.scratch("bicgstab", b * 2 * ws_floats * 4)
     if POISON_SCRATCH:

@@ -203,6 +203,15 @@ int dpiso_bicgstab_ilu(int batch, const dpiso_bicg_tables *h_tab_u, const dpiso_
                        int nnz_v, const float *values, int negate, const float *rhs, const float *x0, float tol,
                        int max_it, float *x, int *stats, float *warn, float *pivots_out, const float *pivots_in,
                        float *workspace, void *stream);
+/* The fp64 variant, LinearSolverCudaMultiBicgstabILU(cast_to_double=True) (diffpiso/linear_solver.py:130-133, launcher
+ * multi_bicgstab_ilu_linear_solve_op.cu.cc:540-988): fp32 values / rhs / x0 in, fp64 solve, fp32 solution out (the casts of
+ * linear_solver.py:131-133,171 are fused).  Same tables, stats and warn as above; workspace: caller-owned,
+ * batch * 2 * dpiso_bicgstab_f64_workspace_bytes() bytes.  No shipped script of the reference uses this path: one CTA per
+ * system, one barrier per wavefront level. */
+size_t dpiso_bicgstab_f64_workspace_bytes(const dpiso_bicg_tables *h_tab_u, const dpiso_bicg_tables *h_tab_v);
+int dpiso_bicgstab_ilu_f64(int batch, const dpiso_bicg_tables *h_tab_u, const dpiso_bicg_tables *h_tab_v, int nnz_u, int nnz_v,
+                           const float *values, int negate, const float *rhs, const float *x0, float tol, int max_it,
+                           float *x, int *stats, float *warn, void *workspace, void *stream);
 int dpiso_bicgstab_supports_factor_reuse(const dpiso_bicg_tables *h_tab_u, const dpiso_bicg_tables *h_tab_v);
 /* profiling / test switch: dbg >= 0 overrides the DPISO_BICG_DBG environment variable, -1 restores it.  Bits: 8 force the
  * level-major fallback kernel, 64 the cluster-per-system kernel, 128 the row-per-thread kernel, 256 the tile kernel,

@@ -149,14 +149,15 @@ def lu_solve(rp, ci, lu, b):
     return x
 
 
-def bicgstab_ilu(rp, ci, val, rhs, x0, tol, max_it, transpose=False):
-    """Returns x, dict(iterations, restarts, warn, exit_kind, residual)."""
+def bicgstab_ilu(rp, ci, val, rhs, x0, tol, max_it, transpose=False, fp64=False):
+    """Returns x, dict(iterations, restarts, warn, exit_kind, residual).  fp64: the cast_to_double=True variant (fp32 in,
+    fp64 solve, fp32 out)."""
     rp, ci, val, rhs, x0 = _i32(rp), _i32(ci), _f32(val), _f32(rhs), _f32(x0)
     n = rp.size - 1
     x = np.zeros(n, np.float32)
     stats = np.zeros(4, np.int32)
     res = C.c_float(0)
-    f = lib().orc_bicgstab_ilu_f32
+    f = lib().orc_bicgstab_ilu_f64 if fp64 else lib().orc_bicgstab_ilu_f32
     f.argtypes = [C.c_int] + [C.c_void_p] * 5 + [C.c_float, C.c_int, C.c_int] + [C.c_void_p] * 2 + [C.POINTER(C.c_float)]
     f(n, rp.ctypes.data, ci.ctypes.data, val.ctypes.data, rhs.ctypes.data, x0.ctypes.data, tol, max_it,
       int(transpose), x.ctypes.data, stats.ctypes.data, C.byref(res))

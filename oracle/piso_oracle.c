@@ -450,6 +450,129 @@ int orc_bicgstab_ilu_f32(int n, const int *rp_in, const int *ci_in, const float 
 }
 
 /* ------------------------------------------------------------------------------------------
+ * The fp64 variant of the predictor solve -- CUDAsrc/multi_bicgstab_ilu_linear_solve_op.cu.cc:540-988, selected by
+ * LinearSolverCudaMultiBicgstabILU(cast_to_double=True) (diffpiso/linear_solver.py:130-133, which casts the fp32
+ * matrix values and right-hand side to fp64 and the solution back to fp32, ":171").  Same sequence as the fp32
+ * launcher with cusparseD / cublasD calls; the tolerance stays a float.  Inputs and output are fp32 here as well.
+ * ---------------------------------------------------------------------------------------- */
+static double dotdd(int n, const double *a, const double *b) {
+    double s = 0.0;
+    for (int i = 0; i < n; i++) s += a[i] * b[i];
+    return s;
+}
+static void spmv_f64(int n, const int *rp, const int *ci, const double *val, const double *x, double *y) {
+    for (int i = 0; i < n; i++) {
+        double acc = 0.0;
+        for (int k = rp[i]; k < rp[i + 1]; k++) acc = fma(val[k], x[ci[k]], acc);
+        y[i] = acc;
+    }
+}
+static void ilu0_f64(int n, const int *rp, const int *ci, const double *val, double *lu) {
+    memcpy(lu, val, sizeof(double) * (size_t)rp[n]);
+    int *dpos = (int *)malloc(sizeof(int) * (size_t)n);
+    for (int i = 0; i < n; i++) {
+        dpos[i] = -1;
+        for (int k = rp[i]; k < rp[i + 1]; k++) if (ci[k] == i) dpos[i] = k;
+    }
+    for (int i = 0; i < n; i++)
+        for (int kk = rp[i]; kk < rp[i + 1] && ci[kk] < i; kk++) {
+            int k = ci[kk];
+            double lik = lu[kk] / lu[dpos[k]];
+            lu[kk] = lik;
+            for (int jj = kk + 1; jj < rp[i + 1]; jj++) {
+                int j = ci[jj];
+                for (int mm = dpos[k] + 1; mm < rp[k + 1]; mm++)
+                    if (ci[mm] == j) { lu[jj] = fma(-lik, lu[mm], lu[jj]); break; }
+            }
+        }
+    free(dpos);
+}
+static void lu_solve_f64(int n, const int *rp, const int *ci, const double *lu, const double *b, double *y, double *x) {
+    for (int i = 0; i < n; i++) {
+        double acc = b[i];
+        for (int k = rp[i]; k < rp[i + 1] && ci[k] < i; k++) acc = fma(-lu[k], y[ci[k]], acc);
+        y[i] = acc;
+    }
+    for (int i = n - 1; i >= 0; i--) {
+        double acc = y[i], d = 1.0;
+        for (int k = rp[i]; k < rp[i + 1]; k++) {
+            if (ci[k] == i) d = lu[k];
+            else if (ci[k] > i) acc = fma(-lu[k], x[ci[k]], acc);
+        }
+        x[i] = acc / d;
+    }
+}
+int orc_bicgstab_ilu_f64(int n, const int *rp_in, const int *ci_in, const float *val_in,
+                         const float *rhs_in, const float *x0, float tol_f, int max_it, int transpose,
+                         float *x_out, int *stats, float *final_res) {
+    int nnz = rp_in[n];
+    const int *rp = rp_in, *ci = ci_in;
+    int *trp = NULL, *tci = NULL; float *tvalf = NULL;
+    const float *valf = val_in;
+    if (transpose) {
+        trp = (int *)malloc(sizeof(int) * (size_t)(n + 1));
+        tci = (int *)malloc(sizeof(int) * (size_t)nnz);
+        tvalf = (float *)malloc(sizeof(float) * (size_t)nnz);
+        orc_csr_transpose_f32(n, rp_in, ci_in, val_in, trp, tci, tvalf);
+        rp = trp; ci = tci; valf = tvalf;
+    }
+    double *val = (double *)malloc(sizeof(double) * (size_t)nnz), *lu = (double *)malloc(sizeof(double) * (size_t)nnz);
+    for (int k = 0; k < nnz; k++) val[k] = (double)valf[k];                /* tf.cast(matrix_values, tf.float64) */
+    double *w = (double *)calloc((size_t)n * 10, sizeof(double));
+    double *r = w, *rh = w + n, *p = w + 2 * n, *v = w + 3 * n, *t = w + 4 * n, *z = w + 5 * n,
+           *ph = w + 6 * n, *sh = w + 7 * n, *x = w + 8 * n, *rhs = w + 9 * n;
+    for (int i = 0; i < n; i++) { rhs[i] = (double)rhs_in[i]; x[i] = (double)x0[i]; }
+    ilu0_f64(n, rp, ci, val, lu);
+    const double tol = (double)tol_f;
+    double alpha = 1., rho = 1., rhop = 1., omega = 1., beta, nrm_r = 0.;
+    int it_count = 0, restarts = 0, exit_kind = 3;
+    int warn = isnan(sqrt(dotdd(nnz, val, val))) || isnan(sqrt(dotdd(n, rhs, rhs)));
+    for (int restart = 0; restart < 2; restart++) {
+        restarts = restart;
+        spmv_f64(n, rp, ci, val, x, r);
+        for (int i = 0; i < n; i++) r[i] = rhs[i] - r[i];
+        nrm_r = sqrt(dotdd(n, r, r));
+        if (nrm_r < tol) { exit_kind = 0; break; }
+        memcpy(rh, r, sizeof(double) * (size_t)n);
+        memset(p, 0, sizeof(double) * (size_t)n);
+        memset(v, 0, sizeof(double) * (size_t)n);
+        exit_kind = 3;
+        for (int it = 0; it < max_it; it++) {
+            it_count++;
+            rhop = rho;
+            rho = dotdd(n, r, rh);
+            beta = (rho / rhop) * (alpha / omega);
+            for (int i = 0; i < n; i++) {
+                double pi = fma(-omega, v[i], p[i]);
+                pi = beta * pi;
+                p[i] = pi + r[i];
+            }
+            lu_solve_f64(n, rp, ci, lu, p, z, ph);
+            spmv_f64(n, rp, ci, val, ph, v);
+            alpha = rho / dotdd(n, rh, v);
+            for (int i = 0; i < n; i++) { x[i] = fma(alpha, ph[i], x[i]); r[i] = fma(-alpha, v[i], r[i]); }
+            nrm_r = sqrt(dotdd(n, r, r));
+            if (nrm_r < tol) { exit_kind = 1; break; }
+            lu_solve_f64(n, rp, ci, lu, r, z, sh);
+            spmv_f64(n, rp, ci, val, sh, t);
+            omega = dotdd(n, t, r) / dotdd(n, t, t);
+            for (int i = 0; i < n; i++) { x[i] = fma(omega, sh[i], x[i]); r[i] = fma(-omega, t[i], r[i]); }
+            nrm_r = sqrt(dotdd(n, r, r));
+            if (nrm_r < tol) { exit_kind = 2; break; }
+        }
+        if (nrm_r > tol * 100 || isnan(nrm_r)) {
+            memset(x, 0, sizeof(double) * (size_t)n);
+            if (restart == 1) restarts = 2;
+        } else break;
+    }
+    for (int i = 0; i < n; i++) x_out[i] = (float)x[i];                    /* tf.cast(sol[3], tf.float32) */
+    stats[0] = it_count; stats[1] = restarts; stats[2] = warn; stats[3] = exit_kind;
+    if (final_res) *final_res = (float)nrm_r;
+    free(val); free(lu); free(w); free(trp); free(tci); free(tvalf);
+    return ORC_OK;
+}
+
+/* ------------------------------------------------------------------------------------------
  * PISO pressure matrix -- CUDAsrc/laplace_op.cu.cc:79-179 (calcPISOLaplaceMatrix)
  * k_faces is flattened [v, u] (piso_cuda_pressure_solver.py:70); output 5 per cell
  * [y-, x-, diag, x+, y+].

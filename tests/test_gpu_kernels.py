@@ -429,3 +429,65 @@ def test_bicgstab_kernels_are_deterministic_and_never_read_unwritten_workspace(d
         N.lib.dpiso_bicgstab_set_debug(-1)
         N.lib.dpiso_bicgstab_set_band_cluster(0)
         N.lib.dpiso_bicgstab_set_tile_cluster(0)
+
+
+@pytest.mark.parametrize("name", ["ldc8", "periodic16", "periodic24x20", "tml16x24", "sml16x48", "obstacle16x24", "periodic64", "ldc_like64"])
+@pytest.mark.parametrize("transpose", [False, True])
+def test_bicgstab_fp64_matches_oracle(name, transpose):
+    """The cast_to_double=True path of LinearSolverCudaMultiBicgstabILU (dpiso_bicgstab_ilu_f64: fp32 in, fp64 solve, fp32
+    out; reference launcher multi_bicgstab_ilu_linear_solve_op.cu.cc:540-988) against the oracle's fp64 restatement:
+    iteration counts within +-1, restarts / warn identical, solution within 1e-6 relative L2 (both sides round the fp64
+    solution to fp32), for A and A^T; workspace poisoned with NaN patterns."""
+    from diffpiso_b200 import ops
+    s = ALL_SETUPS[name]()
+    g, m = _geom(s), _masks(s)
+    vels = np.stack([random_fields(s, 20 + i)[0] for i in range(2)])
+    values, _ = ops.assemble(g, _t(vels), m["dirichlet"], m["active"], m["noslip"], _t(np.atleast_1d(s["visc"])), s["dy"],
+                             s["dx"], _beta(s))
+    rhs = (vels * _beta(s)).astype(np.float32)
+    ops.POISON_SCRATCH = True
+    try:
+        x, stats, warn = ops.bicgstab_ilu(g, values, _t(rhs), _t(vels), s["bicg_tol"], s["bicg_max_it"], transpose, negate=True,
+                                          fp64=True)
+    finally:
+        ops.POISON_SCRATCH = False
+    x, stats = x.cpu().numpy(), stats.cpu().numpy()
+    assert int(warn.item()) == 0 and np.isfinite(x).all()
+    orp, oci = O.csr_structure(s["ny"], s["nx"], s["per_x"], s["per_y"])
+    negh = -values.cpu().numpy()
+    for i in range(2):
+        for comp, (r0, r1, z0, z1, rp) in enumerate(((0, g.n_u, 0, g.nnz_u, orp[:g.n_u + 1]),
+                                                     (g.n_u, g.nf, g.nnz_u, g.nnz, orp[g.n_u + 1:]))):
+            ox, st = O.bicgstab_ilu(rp, oci[z0:z1], negh[i, z0:z1], rhs[i, r0:r1], vels[i, r0:r1], s["bicg_tol"],
+                                    s["bicg_max_it"], transpose, fp64=True)
+            got = stats[i, comp]
+            assert abs(int(got[0]) - st["iterations"]) <= 1, (name, i, comp, got, st)
+            assert int(got[1]) == st["restarts"] and int(got[2]) == st["warn"], (name, i, comp, got, st)
+            assert rel_l2(x[i, r0:r1], ox) < 1e-6, (name, i, comp, rel_l2(x[i, r0:r1], ox), got, st)
+
+
+def test_linear_solver_class_cast_to_double_forward_and_gradient():
+    """LinearSolverCudaMultiBicgstabILU(cast_to_double=True).solve: forward close to the fp32 solver's, and the gradient
+    (transposed fp64 solve of the cotangent, linear_solver.py:164-173) equal to the oracle's transposed fp64 solve."""
+    import diffpiso_b200 as dp
+    from diffpiso_b200 import ops
+    s = ALL_SETUPS["periodic24x20"]()
+    g, m = _geom(s), _masks(s)
+    vel = random_fields(s, 3)[0][None]
+    values, _ = ops.assemble(g, _t(vel), m["dirichlet"], m["active"], m["noslip"], _t(np.atleast_1d(s["visc"])), s["dy"],
+                             s["dx"], _beta(s))
+    neg = torch.neg(values)
+    rhs = (_t(vel) * _beta(s)).requires_grad_(True)
+    shape = (1, s["ny"] + 1, s["nx"] + 1, 2)
+    ls64 = dp.LinearSolverCudaMultiBicgstabILU(accuracy=s["bicg_tol"], max_iterations=s["bicg_max_it"], cast_to_double=True)
+    ls32 = dp.LinearSolverCudaMultiBicgstabILU(accuracy=s["bicg_tol"], max_iterations=s["bicg_max_it"])
+    x64, w = ls64.solve(neg, None, None, rhs, shape, initial_guess=_t(vel), structure=g)
+    x32, _ = ls32.solve(neg, None, None, rhs.detach(), shape, initial_guess=_t(vel), structure=g)
+    assert float(w.item()) == 0.0 and rel_l2(x64.detach().cpu().numpy(), x32.cpu().numpy()) < 1e-5
+    cot = torch.as_tensor(np.random.RandomState(5).randn(1, g.nf).astype(np.float32)).to(DEV)
+    (x64 * cot).sum().backward()
+    orp, oci = O.csr_structure(s["ny"], s["nx"], s["per_x"], s["per_y"])
+    negh, coth, velh = neg.cpu().numpy()[0], cot.cpu().numpy()[0], vel[0]
+    for r0, r1, z0, z1, rp in ((0, g.n_u, 0, g.nnz_u, orp[:g.n_u + 1]), (g.n_u, g.nf, g.nnz_u, g.nnz, orp[g.n_u + 1:])):
+        og, _ = O.bicgstab_ilu(rp, oci[z0:z1], negh[z0:z1], coth[r0:r1], velh[r0:r1], s["bicg_tol"], s["bicg_max_it"], True, fp64=True)
+        assert rel_l2(rhs.grad.cpu().numpy()[0, r0:r1], og) < 1e-6
