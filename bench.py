@@ -568,6 +568,8 @@ def main():
                     help="skip the extra BASELINE configs[4] measurement (periodic 1024^2, batch 8)")
     ap.add_argument("--config5-only", action="store_true", help="run only the configs[4] measurement (used under ncu)")
     ap.add_argument("--config5-maxit", type=int, default=20000, help="CG iteration cap of the configs[4] run (profiling)")
+    ap.add_argument("--config5-n", type=int, default=1024, help="grid of the --config5-only run (1024 or 2048)")
+    ap.add_argument("--config5-batch", type=int, default=8, help="batch of the --config5-only run")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
@@ -576,7 +578,8 @@ def main():
     elif args.config5_only:
         import torch
         torch.cuda.set_device(0)
-        print(json.dumps(run_config5(torch.device("cuda", 0), 6460.9, steps=1, cg_max_it=args.config5_maxit)))
+        print(json.dumps(run_config5(torch.device("cuda", 0), 6460.9, n=args.config5_n, batch=args.config5_batch, steps=1,
+                                     cg_max_it=args.config5_maxit)))
     else:
         if int(os.environ.get("WORLD_SIZE", "1")) > 1:
             args.cpu_baseline = args.cpu_baseline and int(os.environ.get("RANK", "0")) == 0
