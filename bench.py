@@ -442,6 +442,18 @@ def run_ours(args):
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     per_rank = [[float(v) for v in t_.cpu()] for t_ in per_rank]
     ms, ms_fwd, ms_e2e = [float(x) for x in times.cpu()]
+    # BASELINE configs[2]: one training iteration around the path (16-step unroll with the closure network, backward through
+    # every step, NCCL all-reduce of the closure gradients -- the only collective of the workload -- and Adam) at N GPUs
+    training = None
+    if args.training:
+        import types
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        import training_bench
+        try:
+            training = training_bench.measure(types.SimpleNamespace(config="tml", batch=8, unroll=16, iters=2, warmup=1),
+                                              dev, rank, world)
+        except Exception as e:                                   # never lose the headline line to the extra key
+            training = {"error": repr(e)[:200]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -542,6 +554,8 @@ def run_ours(args):
                      "cg_ms_per_step": [r_[3] for r_ in per_rank], "bicgstab_ms_per_step": [r_[4] for r_ in per_rank]},
         "clocks": clocks, "finite": finite,
     }
+    if training is not None:
+        line["training_c3"] = training
     if args.config5 and world == 1:
         line["config5"] = run_config5(dev, peak)
     if args.cpu_baseline:
@@ -566,6 +580,8 @@ def main():
     ap.add_argument("--same-seeds", action="store_true", help="every rank solves the same samples (scaling diagnostics)")
     ap.add_argument("--no-config5", dest="config5", action="store_false",
                     help="skip the extra BASELINE configs[4] measurement (periodic 1024^2, batch 8)")
+    ap.add_argument("--no-training", dest="training", action="store_false",
+                    help="skip the extra BASELINE configs[2] training-iteration measurement (closure network + all-reduce)")
     ap.add_argument("--config5-only", action="store_true", help="run only the configs[4] measurement (used under ncu)")
     ap.add_argument("--config5-maxit", type=int, default=20000, help="CG iteration cap of the configs[4] run (profiling)")
     ap.add_argument("--config5-n", type=int, default=1024, help="grid of the --config5-only run (1024 or 2048)")

@@ -33,6 +33,17 @@ def main():
     dev = "cuda:%d" % local
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
+    out = measure(args, dev, rank, world)
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def measure(args, dev, rank, world):
+    """One measurement on an initialised process group (every rank calls; rank 0 gets the dict, the others None).
+    `args`: config, batch, unroll, iters, warmup."""
+    dev = str(dev)
     import diffpiso_b200 as dp
     from diffpiso_b200 import losses as L, masks as M, networks as N, setups as SU, training as T
     from common import random_fields
@@ -101,6 +112,22 @@ def main():
     ms = torch.tensor([e0.elapsed_time(e1) / args.iters], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    # the collective alone: the flat closure-gradient bucket this workload all-reduces once per iteration
+    ar_us = None
+    if world > 1:
+        bucket = torch.zeros(sum(w.numel() for w in weights), device=dev)
+        for _ in range(3):
+            dist.all_reduce(bucket)
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(20):
+            dist.all_reduce(bucket)
+        a1.record()
+        torch.cuda.synchronize()
+        t_ar = torch.tensor([a0.elapsed_time(a1) / 20 * 1e3], dtype=torch.float64, device=dev)
+        dist.all_reduce(t_ar, op=dist.ReduceOp.MAX)
+        ar_us = float(t_ar)
     wsum = torch.stack([w.detach().double().sum() for w in weights]).sum()
     if world > 1:                                               # replicas must stay identical
         lo, hi = wsum.clone(), wsum.clone()
@@ -109,16 +136,18 @@ def main():
         in_sync = bool(lo == hi)
     else:
         in_sync = True
-    if rank == 0:
-        cells = B * ny * nx * unroll * world
-        print(json.dumps({"workload": "%s_%dx%d_unroll%d_batch%d_per_gpu_training_iteration" % (args.config, nx, ny, unroll, B),
-                          "n_gpus": world, "ms_per_iteration": float(ms), "cell_updates_per_s": cells / (float(ms) * 1e-3),
-                          "scaling": "weak", "loss": float(loss), "finite": bool(torch.isfinite(loss)),
-                          "replicas_in_sync": in_sync, "closure_parameters": int(sum(w.numel() for w in weights)),
-                          "last_cg_iterations": float(ps.last_iterations.float().mean()),
-                          "conv_precision": "tf32" if torch.backends.cudnn.allow_tf32 else "fp32"}))
-    if world > 1:
-        dist.destroy_process_group()
+    if rank != 0:
+        return None
+    cells = B * ny * nx * unroll * world
+    nparam = int(sum(w.numel() for w in weights))
+    return {"workload": "%s_%dx%d_unroll%d_batch%d_per_gpu_training_iteration" % (args.config, nx, ny, unroll, B),
+            "n_gpus": world, "ms_per_iteration": float(ms), "cell_updates_per_s": cells / (float(ms) * 1e-3),
+            "scaling": "weak", "loss": float(loss), "finite": bool(torch.isfinite(loss)),
+            "replicas_in_sync": in_sync, "closure_parameters": nparam,
+            "collective": {"what": "NCCL all-reduce of the flat closure-gradient bucket, once per iteration",
+                           "bytes": 4 * nparam, "us_per_allreduce_alone": ar_us},
+            "last_cg_iterations": float(ps.last_iterations.float().mean()),
+            "conv_precision": "tf32" if torch.backends.cudnn.allow_tf32 else "fp32"}
 
 
 if __name__ == "__main__":
