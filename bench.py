@@ -288,8 +288,12 @@ def run_ours(args):
                                   s["accessible_mask"], bool_periodic=(True, True), no_slip_mask=s["no_slip_mask"],
                                   viscosity=float(s["visc"]), linear_solver=ls, pressure_solver=ps)
     # --same-seeds: every rank solves the same samples, which separates host launch jitter from iteration imbalance
+    from diffpiso_b200 import sharding
+    # weak scaling: the job has BATCH * world samples, rank r owns the contiguous block shard_bounds() gives it
+    first_sample, n_local = sharding.shard_bounds(BATCH * world, world, rank)
+    assert n_local == BATCH
     seed_rank = 0 if args.same_seeds else rank
-    vel_h, pres_h = initial_state(s, BATCH, 1234 + seed_rank * BATCH)
+    vel_h, pres_h = initial_state(s, BATCH, 1234 + (0 if args.same_seeds else first_sample))
     dxy = (s["dy"], s["dx"])
     dvals = torch.zeros(1, nf, device=dev)
     rng = np.random.RandomState(99 + seed_rank)
@@ -439,9 +443,8 @@ def run_ours(args):
     per_rank = [mine.clone() for _ in range(world)]
     if world > 1:
         dist.all_gather(per_rank, mine)
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
     per_rank = [[float(v) for v in t_.cpu()] for t_ in per_rank]
-    ms, ms_fwd, ms_e2e = [float(x) for x in times.cpu()]
+    ms, ms_fwd, ms_e2e = sharding.max_over_ranks([float(x) for x in times.cpu()], device=dev)   # the slowest rank's time
     # BASELINE configs[2]: one training iteration around the path (16-step unroll with the closure network, backward through
     # every step, NCCL all-reduce of the closure gradients -- the only collective of the workload -- and Adam) at N GPUs
     training = None

@@ -242,7 +242,8 @@ int dpiso_assemble(int batch, int ny, int nx, int per_x, int per_y, float dy, fl
     if (int rc = check_grid(batch, ny, nx)) return rc;
     DPISO_REQUIRE(vel && dirichlet && active && noslip && visc && values && a_diag, "null pointer");
     DPISO_REQUIRE(visc_mode >= 0 && visc_mode <= 2, "visc_mode must be 0, 1 or 2");
-    const Grid g = make_grid(ny, nx, per_x, per_y);
+    Grid g = make_grid(ny, nx, per_x & 1, per_y & 1);
+    g.per_x = per_x & 3; g.per_y = per_y & 3;                     // bit 1 travels to assemble_row (replicated velocity padding)
     assemble_kernel<<<blocks_for((long long)batch * g.nf()), kThreads, 0, (cudaStream_t)stream>>>(
         batch, g, dy, dx, area_x, area_y, beta, vel, dirichlet, active, noslip, visc, visc_mode, values, a_diag);
     DPISO_CHECK_LAUNCH();

@@ -52,6 +52,13 @@ DPISO_HD void assemble_row(int comp, int row, int ny, int nx, int per_x, int per
                            float area_y, float beta, const float *vel, const uint8_t *dirichlet_c, const float *active,
                            const uint8_t *noslip, const float *visc_c, int visc_is_field, float *values_c,
                            float *a_diag_c) {
+    // per_x / per_y: bit 0 = the axis is periodic (matrix structure, wrap entries); bit 1 = the VELOCITY is nevertheless
+    // padded by replication on that axis.  That combination is what the reference computes from the second unrolled step
+    // on: run_piso_steps re-wraps the state as StaggeredGrid(array, box, extrapolation), whose third positional parameter is
+    // `name`, so the grid falls back to the default 'boundary' extrapolation and custom_padded replicates instead of
+    // wrapping (combined_training_integrated.py:431-432,473-474; SURVEY quirk list, Q21).
+    const int pad_per_x = (per_x & 1) && !(per_x & 2), pad_per_y = (per_y & 1) && !(per_y & 2);
+    per_x &= 1; per_y &= 1;
     const CompDims cd = comp_dims(ny, nx, comp);
     const int lx = row % cd.Dx, ly = row / cd.Dx;
     const RowLayout L = row_layout(lx, ly, cd, per_x, per_y);
@@ -67,21 +74,21 @@ DPISO_HD void assemble_row(int comp, int row, int ny, int nx, int per_x, int per
     const float spacing[2] = {dx, dy};                       // piso_tf.py:96
     float F[4];
     if (comp == 0) {       // calcCellFluxesX (":35-69"); padded location (ly+1, lx+1)
-        const float c = u_padded(u, ny, nx, per_x, per_y, ly + 1, lx + 1);
-        F[0] = flux(c, u_padded(u, ny, nx, per_x, per_y, ly + 1, lx), cell_area[0]);
-        F[1] = flux(u_padded(u, ny, nx, per_x, per_y, ly + 1, lx + 2), c, cell_area[0]);
-        F[2] = flux(v_padded(v, ny, nx, per_x, per_y, ly + 1, lx + 1), v_padded(v, ny, nx, per_x, per_y, ly + 1, lx),
+        const float c = u_padded(u, ny, nx, pad_per_x, pad_per_y, ly + 1, lx + 1);
+        F[0] = flux(c, u_padded(u, ny, nx, pad_per_x, pad_per_y, ly + 1, lx), cell_area[0]);
+        F[1] = flux(u_padded(u, ny, nx, pad_per_x, pad_per_y, ly + 1, lx + 2), c, cell_area[0]);
+        F[2] = flux(v_padded(v, ny, nx, pad_per_x, pad_per_y, ly + 1, lx + 1), v_padded(v, ny, nx, pad_per_x, pad_per_y, ly + 1, lx),
                     cell_area[1]);
-        F[3] = flux(v_padded(v, ny, nx, per_x, per_y, ly + 2, lx + 1), v_padded(v, ny, nx, per_x, per_y, ly + 2, lx),
+        F[3] = flux(v_padded(v, ny, nx, pad_per_x, pad_per_y, ly + 2, lx + 1), v_padded(v, ny, nx, pad_per_x, pad_per_y, ly + 2, lx),
                     cell_area[1]);
     } else {               // calcCellFluxesY (":73-101")
-        F[0] = flux(u_padded(u, ny, nx, per_x, per_y, ly + 1, lx + 1), u_padded(u, ny, nx, per_x, per_y, ly, lx + 1),
+        F[0] = flux(u_padded(u, ny, nx, pad_per_x, pad_per_y, ly + 1, lx + 1), u_padded(u, ny, nx, pad_per_x, pad_per_y, ly, lx + 1),
                     cell_area[0]);
-        F[1] = flux(u_padded(u, ny, nx, per_x, per_y, ly + 1, lx + 2), u_padded(u, ny, nx, per_x, per_y, ly, lx + 2),
+        F[1] = flux(u_padded(u, ny, nx, pad_per_x, pad_per_y, ly + 1, lx + 2), u_padded(u, ny, nx, pad_per_x, pad_per_y, ly, lx + 2),
                     cell_area[0]);
-        const float c = v_padded(v, ny, nx, per_x, per_y, ly + 1, lx + 1);
-        F[2] = flux(c, v_padded(v, ny, nx, per_x, per_y, ly, lx + 1), cell_area[1]);
-        F[3] = flux(v_padded(v, ny, nx, per_x, per_y, ly + 2, lx + 1), c, cell_area[1]);
+        const float c = v_padded(v, ny, nx, pad_per_x, pad_per_y, ly + 1, lx + 1);
+        F[2] = flux(c, v_padded(v, ny, nx, pad_per_x, pad_per_y, ly, lx + 1), cell_area[1]);
+        F[3] = flux(v_padded(v, ny, nx, pad_per_x, pad_per_y, ly + 2, lx + 1), c, cell_area[1]);
     }
     // padded-centred mask cell consulted per direction (gridIDXpaddedCenteredMasks, ":132-146")
     const int wm = nx + 2;

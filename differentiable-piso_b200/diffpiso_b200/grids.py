@@ -197,7 +197,11 @@ class StaggeredGrid(_Grid):
     """Staggered velocity holder.  Built either from a staggered tensor [B, ny+1, nx+1, 2] or (internally) from the
     flat [B, n_u+n_v] vector; the other representation is produced on demand."""
 
-    def __init__(self, data=None, box=None, extrapolation="boundary", dx=None, name=None, flat=None, resolution=None):
+    def __init__(self, data=None, box=None, extrapolation="boundary", dx=None, name=None, flat=None, resolution=None,
+                 pad_periodic=None):
+        # pad_periodic: None = custom_padded pads the velocity as the simulation's periodic flags say; (y, x) booleans
+        # override that (False = replicate on a periodic axis: the state of the reference's unrolled steps, Q21)
+        self.pad_periodic = pad_periodic
         if data is None and flat is None:
             raise ValueError("need a staggered tensor or a flat vector")
         self._staggered = None if data is None else as_tensor(data)
@@ -235,7 +239,7 @@ class StaggeredGrid(_Grid):
 
     def copied_with(self, data=None, flat=None):
         return StaggeredGrid(data, box=self.box, dx=self.dx, extrapolation=self.extrapolation, flat=flat,
-                             resolution=self._resolution)
+                             resolution=self._resolution, pad_periodic=self.pad_periodic)
 
     @property
     def data(self):

@@ -122,8 +122,13 @@ def cell_areas(dy64, dx64):
 
 
 @_on_device_of(0)
-def assemble(g, vel, dirichlet_u8, active, noslip_u8, visc, dy, dx, beta, areas=None):
-    """-> values [B, nnz], a_diag [B, nf]   (advection_matrix_cuda, diffpiso/piso_tf.py:85-137)"""
+def assemble(g, vel, dirichlet_u8, active, noslip_u8, visc, dy, dx, beta, areas=None, vel_periodic=None):
+    """-> values [B, nnz], a_diag [B, nf]   (advection_matrix_cuda, diffpiso/piso_tf.py:85-137)
+    vel_periodic = (y, x): whether the velocity GRID says periodic on that axis (custom_padded pads by it); defaults to the
+    geometry's flags.  False on a periodic axis reproduces the replicated padding of the reference's unrolled steps."""
+    vpy, vpx = (g.per_y, g.per_x) if vel_periodic is None else vel_periodic
+    fx = int(g.per_x) | (2 if (g.per_x and not vpx) else 0)
+    fy = int(g.per_y) | (2 if (g.per_y and not vpy) else 0)
     area_x, area_y = cell_areas(dy, dx) if areas is None else areas
     vel = _f32(vel)
     b = vel.shape[0]
@@ -140,7 +145,7 @@ def assemble(g, vel, dirichlet_u8, active, noslip_u8, visc, dy, dx, beta, areas=
         raise ValueError("viscosity must be a scalar or a flat [u, v] face field")
     values = torch.empty((b, g.nnz), dtype=torch.float32, device=vel.device)
     a_diag = torch.empty((b, g.nf), dtype=torch.float32, device=vel.device)
-    N.check(N.lib.dpiso_assemble(b, g.ny, g.nx, int(g.per_x), int(g.per_y), dy, dx, area_x, area_y, beta, N.ptr(vel), N.ptr(dirichlet_u8),
+    N.check(N.lib.dpiso_assemble(b, g.ny, g.nx, fx, fy, dy, dx, area_x, area_y, beta, N.ptr(vel), N.ptr(dirichlet_u8),
                                  N.ptr(active), N.ptr(noslip_u8), N.ptr(visc), mode, N.ptr(values), N.ptr(a_diag),
                                  N.stream()), "dpiso_assemble")
     return values, a_diag
@@ -218,12 +223,14 @@ def fv_gradient_adj(g, gs, access, dy, dx, pbc, a_diag=None, beta=0.0, divisor=1
 
 
 @_on_device_of(0)
-def fv_divergence_adj(g, gc, dy, dx, base=None, a_diag=None, beta=0.0, base_sub=None):
-    """([base [- base_sub]] + D^T gc) [/ (beta - a_diag)]"""
+def fv_divergence_adj(g, gc, dy, dx, base=None, a_diag=None, beta=0.0, base_sub=None, vel_periodic=None):
+    """([base [- base_sub]] + D^T gc) [/ (beta - a_diag)]; vel_periodic = (y, x): which registered gradient of
+    finite_volume_divergence applies (it follows the velocity grid's extrapolation, piso_helpers.py:291-305)."""
     gc = _f32(gc)
     b = gc.shape[0]
     out = torch.empty((b, g.nf), dtype=torch.float32, device=gc.device)
-    N.check(N.lib.dpiso_fv_divergence_adj(b, g.ny, g.nx, int(g.per_x), int(g.per_y), dy, dx, N.ptr(gc),
+    vpy, vpx = (g.per_y, g.per_x) if vel_periodic is None else vel_periodic
+    N.check(N.lib.dpiso_fv_divergence_adj(b, g.ny, g.nx, int(g.per_x and vpx), int(g.per_y and vpy), dy, dx, N.ptr(gc),
                                           N.ptr(None if base is None else _f32(base)),
                                           N.ptr(None if base_sub is None else _f32(base_sub)), N.ptr(a_diag), beta,
                                           N.ptr(out), N.stream()), "dpiso_fv_divergence_adj")

@@ -46,7 +46,8 @@ def pressure_extrapolation(boundaries):
 
 class _Ctx(object):
     """Host-side constants of one step."""
-    __slots__ = ("g", "m", "dy", "dx", "areas", "beta", "prod", "dx_factor", "pbc", "pbc_inc", "sim", "unrolling_step")
+    __slots__ = ("g", "m", "dy", "dx", "areas", "beta", "prod", "dx_factor", "pbc", "pbc_inc", "sim", "unrolling_step",
+                 "vel_periodic")
 
 
 def _linear_solve(c, values, rhs, x0, transpose, unrolling_step, pivots_out=None, pivots_in=None):
@@ -91,7 +92,8 @@ class _PisoStepFn(torch.autograd.Function):
         native_ps = getattr(c.sim.pressure_solver, "_dpiso_native", False)
         needs_bwd = any(ctx.needs_input_grad[:4])
         # advection matrices (piso_tf.py:29-33)
-        values, a_diag = ops.assemble(g, vel, m["dirichlet"], m["active"], m["noslip"], visc, c.dy, c.dx, c.beta, c.areas)
+        values, a_diag = ops.assemble(g, vel, m["dirichlet"], m["active"], m["noslip"], visc, c.dy, c.dx, c.beta, c.areas,
+                                      vel_periodic=c.vel_periodic)
         # predictor (piso_tf.py:36-47); the forward ILU(0) pivots are kept for the adjoint solve (factor reuse)
         rhs = ops.predictor_rhs(g, vel, pres, m["access"], m["dirichlet"], dvals, forcing, c.dy, c.dx, c.beta, c.pbc)
         pivots = None
@@ -145,7 +147,7 @@ class _PisoStepFn(torch.autograd.Function):
                                      divisor=c.prod, negate=True, base=g_pres)
         d2_bar, _, _ = _pressure_solve(c, a_diag, p2_bar, 1100 + c.unrolling_step, scaling)
         # h_bar = (g_vel + D^T d2_bar) / (beta - A)
-        h_bar = ops.fv_divergence_adj(g, d2_bar, c.dy, c.dx, base=g_vel, a_diag=a_diag, beta=c.beta)
+        h_bar = ops.fv_divergence_adj(g, d2_bar, c.dy, c.dx, base=g_vel, a_diag=a_diag, beta=c.beta, vel_periodic=c.vel_periodic)
         # delta_bar = H^T h_bar ; u**_bar = g_vel + delta_bar (same pass)
         delta_bar, us2_bar = ops.h_apply_adj(g, values, a_diag, h_bar, c.beta, base=g_vel)
         # u** = u* - G(p1)/(beta-A)/prod
@@ -153,7 +155,7 @@ class _PisoStepFn(torch.autograd.Function):
                                      divisor=c.prod, negate=True, base=g_pres)
         d1_bar, _, _ = _pressure_solve(c, a_diag, p1_bar, 100 + c.unrolling_step, scaling)
         # u*_bar = (us2_bar - delta_bar) + D^T d1_bar
-        ustar_bar = ops.fv_divergence_adj(g, d1_bar, c.dy, c.dx, base=us2_bar, base_sub=delta_bar)
+        ustar_bar = ops.fv_divergence_adj(g, d1_bar, c.dy, c.dx, base=us2_bar, base_sub=delta_bar, vel_periodic=c.vel_periodic)
         # predictor: transposed solve, same initial-guess tensor as forward, times (1 - warn) (linear_solver.py:169-173)
         rhs_bar, warn_b, stats_b = _linear_solve(c, values, ustar_bar, vel, True, 100 + c.unrolling_step, pivots_in=pivots)
         if stats_b is None:                     # foreign plug-in: batch-wide warning scalar, as the reference applies it
@@ -205,6 +207,9 @@ def make_step_context(velocity, pressure, pressure_inc, dt, simulation_physics, 
     c.pbc_inc = extrapolation_codes(pressure_inc.extrapolation)
     c.sim = sim
     c.unrolling_step = unrolling_step
+    # how custom_padded pads the velocity and which registered gradient finite_volume_divergence uses: the velocity
+    # grid's own extrapolation in the reference; here the simulation's flags unless the grid overrides them (Q21)
+    c.vel_periodic = getattr(velocity, "pad_periodic", None)
     return c
 
 

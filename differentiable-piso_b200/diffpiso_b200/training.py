@@ -73,7 +73,8 @@ def run_piso_steps(velocity, pressure, domain, physical_parameters, simulation_p
     for i in range(step_count):
         if i > 0:
             if i % training_dict["loss_influence_range"] == 0:            # :436-438
-                velnew = StaggeredGrid(velnew.staggered_tensor().detach(), dx=velnew.dx, extrapolation=velnew.extrapolation)
+                velnew = StaggeredGrid(velnew.staggered_tensor().detach(), dx=velnew.dx, extrapolation=velnew.extrapolation,
+                                       pad_periodic=velnew.pad_periodic)
                 pnew = CenteredGrid(zero_gradient_op(pnew.data), dx=pnew.dx, extrapolation=pnew.extrapolation)
             if dirichlet_placeholder_update is not None:                  # :440-441
                 bc = torch.as_tensor(np.asarray(bcx), dtype=bc_placeholders[i].dtype, device=device) + bc_placeholders[i]
@@ -96,7 +97,12 @@ def run_piso_steps(velocity, pressure, domain, physical_parameters, simulation_p
         pressure_all_steps.append(p_piso)
         velocity_all_arrays.append(vel_piso.staggered_tensor())
         pressure_all_arrays.append(p_piso.data)
-        velnew = StaggeredGrid(velocity_all_arrays[i], dx=vel_piso.dx, extrapolation=vel_piso.extrapolation)
+        # Q21: the reference writes StaggeredGrid(array, vel_piso.box, vel_piso.extrapolation) (:431-432, :473-474), but the
+        # third positional parameter of PhiFlow's StaggeredGrid is `name`: the re-wrapped state has the DEFAULT
+        # extrapolation 'boundary'.  From the second unrolled step on custom_padded therefore replicates the velocity on
+        # periodic axes (the matrix keeps its periodic structure) and finite_volume_divergence registers its non-circular
+        # gradient.  Reproduced, because it changes the states (1e-4 per step on a 256-wide grid) and the gradients.
+        velnew = StaggeredGrid(velocity_all_arrays[i], dx=vel_piso.dx, extrapolation="boundary", pad_periodic=(False, False))
         pnew = CenteredGrid(pressure_all_arrays[i], dx=p_piso.dx, extrapolation=p_piso.extrapolation)
     return (velocity_all_steps, pressure_all_steps, nn_all_steps, velnew, pnew, nn_out, warn, velocity_all_arrays,
             pressure_all_arrays)

@@ -61,6 +61,9 @@ int dpiso_csr_structure(int ny, int nx, int per_x, int per_y, int *row_ptr, int 
  * i.e. the area of a face normal to x (~dy) and normal to y (~dx).
  * dirichlet uint8 [nf]; active float [(ny+2)(nx+2)]; noslip uint8 [(ny+2)(nx+2)];
  * visc: visc_mode 0 = scalar (1 float), 1 = face field [nf] shared, 2 = face field [batch][nf].
+ * per_x / per_y: bit 0 = periodic axis; bit 1 (only with bit 0) = pad the velocity of that axis by replication
+ * although the matrix is periodic -- what the reference computes from the second step of run_piso_steps on, where the
+ * re-wrapped state loses its extrapolation (combined_training_integrated.py:431-432,473-474).
  * outputs: values [batch][nnz] (centre = diag - beta), a_diag [batch][nf]. */
 int dpiso_assemble(int batch, int ny, int nx, int per_x, int per_y, float dy, float dx, float area_x, float area_y,
                    float beta, const float *vel, const uint8_t *dirichlet, const float *active, const uint8_t *noslip,

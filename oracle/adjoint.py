@@ -104,13 +104,16 @@ def piso_step_adjoint(setup, vel, pres, g_vel, g_pres, forcing=None):
     t = -((g_vel / kt) / prod)
     p2_bar = g_pres + fv_gradient_adj(ny, nx, s["dy"], s["dx"], s["pbc_inc"], s["access"], t)
     d2_bar, it_a = _cg(s, lap, p2_bar)
-    h_bar = (g_vel + fv_divergence_adj(ny, nx, s["per_x"], s["per_y"], s["dy"], s["dx"], d2_bar)) / kt
+    # the registered gradient of finite_volume_divergence follows the velocity grid's extrapolation (piso_helpers.py:291-305)
+    vpy, vpx = s.get("vel_pad_periodic", (True, True))
+    dpx, dpy = bool(s["per_x"] and vpx), bool(s["per_y"] and vpy)
+    h_bar = (g_vel + fv_divergence_adj(ny, nx, dpx, dpy, s["dy"], s["dx"], d2_bar)) / kt
     delta_bar = h_apply_adj(s, values, a_diag, beta, h_bar)
     us2_bar = g_vel + delta_bar
     t = -((us2_bar / kt) / prod)
     p1_bar = g_pres + fv_gradient_adj(ny, nx, s["dy"], s["dx"], s["pbc_inc"], s["access"], t)
     d1_bar, it_b = _cg(s, lap, p1_bar)
-    ustar_bar = (us2_bar - delta_bar) + fv_divergence_adj(ny, nx, s["per_x"], s["per_y"], s["dy"], s["dx"], d1_bar)
+    ustar_bar = (us2_bar - delta_bar) + fv_divergence_adj(ny, nx, dpx, dpy, s["dy"], s["dx"], d1_bar)
     rp, ci = O.csr_structure(ny, nx, s["per_x"], s["per_y"])
     neg = -values
     xu, su = O.bicgstab_ilu(rp[:n_u + 1], ci[:z_u], neg[:z_u], ustar_bar[:n_u], vel[:n_u], s["bicg_tol"], s["bicg_max_it"], True)

@@ -216,7 +216,8 @@ def piso_step(setup, vel, pres, forcing=None, dirichlet_values=None, full_output
 
     setup: dict with ny, nx, per_y, per_x, dy, dx, dt, pbc, pbc_inc, dirichlet (flat [u,v] uint8),
     dirichlet_values (flat [u,v]), active, access, noslip ((ny+2)(nx+2)), visc (scalar or flat field),
-    bicg_tol, bicg_max_it, cg_tol, cg_max_it, cg_reset, rank_deficient, cg_fp64.
+    bicg_tol, bicg_max_it, cg_tol, cg_max_it, cg_reset, rank_deficient, cg_fp64; optional vel_pad_periodic = (y, x):
+    False pads the velocity by replication on a periodic axis (steps >= 2 of the reference's run_piso_steps).
     vel flat [u,v] float32, pres (ny*nx).  Returns vel_next, pres_next, stats[, extras].
     """
     s = setup
@@ -226,7 +227,7 @@ def piso_step(setup, vel, pres, forcing=None, dirichlet_values=None, full_output
     visc = _f32(np.atleast_1d(s["visc"])).ravel()
     ip = np.array([ny, nx, int(s["per_y"]), int(s["per_x"])] + list(s["pbc"]) + list(s["pbc_inc"]) +
                   [int(visc.size > 1), s["bicg_max_it"], s["cg_max_it"], s["cg_reset"], int(s["rank_deficient"]),
-                   int(s.get("cg_fp64", True))], np.int32)
+                   int(s.get("cg_fp64", True))] + [int(k) for k in s.get("vel_pad_periodic", (True, True))], np.int32)
     c = step_constants(s["dy"], s["dx"], s["dt"])
     ax, ay = cell_areas(s["dy"], s["dx"])
     fp = np.array([s["dy"], s["dx"], s["dt"], s["bicg_tol"], s["cg_tol"], c["beta"], c["prod"], c["dx_factor"], ax, ay],

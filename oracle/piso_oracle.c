@@ -698,6 +698,7 @@ void orc_h_apply(int n, const int *rp, const int *ci, const float *val, const fl
  * iparams: [0]=ny [1]=nx [2]=per_y [3]=per_x [4..7]=pbc of pressure (y_lo,y_hi,x_lo,x_hi)
  *          [8..11]=pbc of the pressure increments [12]=visc_is_field [13]=bicg max_it
  *          [14]=cg max_it [15]=cg residual_reset [16]=rank_deficient [17]=cg fp64 (1) / fp32 (0)
+ *          [18],[19]=velocity padding periodic in y, x (1 = as the domain; 0 = replicate although the domain is periodic)
  * fparams: [0]=dy [1]=dx [2]=dt [3]=bicg tol [4]=cg accuracy [5]=beta [6]=unused [7]=dx_factor [8]=cell_area x [9]=cell_area y
  *          ([5..7] are the fp32 graph constants the Python side forms in fp64, piso_tf.py:26,53; 0 = derive here)
  * out_stats (int[12]): [0..3] u solve stats, [4..7] v solve stats, [8] cg1 its, [9] cg2 its
@@ -738,7 +739,10 @@ int orc_piso_step(const int *ip, const float *fp, const float *vel, const float 
 
     /* advection matrices (piso_tf.py:29-33) */
     orc_csr_structure(ny, nx, per_x, per_y, row_ptr, col_ind);
-    orc_pad_velocity(ny, nx, per_x, per_y, vel, vel + n[0], up, vp);
+    /* ip[18], ip[19]: the velocity GRID's periodic flags (y, x) as custom_padded sees them; they differ from the domain's from the
+     * second step of run_piso_steps on, where the re-wrapped state has the default 'boundary' extrapolation
+     * (combined_training_integrated.py:431-432,473-474: the extrapolation is passed in the position of `name`) */
+    orc_pad_velocity(ny, nx, per_x && ip[19], per_y && ip[18], vel, vel + n[0], up, vp);
     orc_assemble(ny, nx, per_x, per_y, dy, dx, fp[8] != 0.0f ? fp[8] : dy, fp[8] != 0.0f ? fp[9] : dx, beta, up, vp,
                  dirichlet, active, noslip, visc, ip[12],
                  row_ptr, values, a_diag);

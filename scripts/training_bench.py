@@ -69,7 +69,9 @@ def measure(args, dev, rank, world):
                                   no_slip_mask=s["no_slip_mask"], viscosity=float(np.atleast_1d(s["visc"])[0]),
                                   linear_solver=ls, pressure_solver=ps)
     visc_field = torch.as_tensor(np.asarray(s["visc"], np.float32)).to(dev) if np.atleast_1d(s["visc"]).size > 1 else None
-    states = [random_fields(s, 500 + rank * B + i) for i in range(B)]
+    from diffpiso_b200 import sharding
+    first_sample, _ = sharding.shard_bounds(B * world, world, rank)             # weak scaling: B samples per rank
+    states = [random_fields(s, 500 + first_sample + i) for i in range(B)]
     vel0 = torch.as_tensor(SU.stagger_flat(np.stack([v for v, _ in states]), ny, nx)).to(dev)
     pres0 = torch.as_tensor(np.stack([p for _, p in states]).reshape(B, ny, nx, 1)).to(dev)
     dxy = (s["dy"], s["dx"])
@@ -109,9 +111,7 @@ def measure(args, dev, rank, world):
         loss = T.training_iteration(opt, weights, loss_fn)
     e1.record()
     barrier()
-    ms = torch.tensor([e0.elapsed_time(e1) / args.iters], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = sharding.max_over_ranks([e0.elapsed_time(e1) / args.iters], device=dev)[0]
     # the collective alone: the flat closure-gradient bucket this workload all-reduces once per iteration
     ar_us = None
     if world > 1:

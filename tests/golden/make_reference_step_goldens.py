@@ -188,7 +188,7 @@ def network_goldens(ns):
                         **{"w%d" % i: k for i, k in enumerate(w)})
 
 
-def unroll_goldens(ns, log, name="sml16x48", steps=3):
+def unroll_goldens(ns, log, name="sml16x48", steps=3, influence=2):
     """run_piso_steps (combined_training_integrated.py:396-478) with the closure network, the per-step inflow
     perturbation and a stop-gradient window of 2 steps; loss = sum_s <w_s, velocity_s>; gradients w.r.t. the closure
     weights and the initial state."""
@@ -201,22 +201,25 @@ def unroll_goldens(ns, log, name="sml16x48", steps=3):
     vel, pres = random_fields(s, 60)
     w = closure_weights()
     tw = [RR.tf_tensor(k, True) for k in w]
-    bcx = s["inlet_profile"].reshape(1, ny + 2, 1, 1).astype(np.float32)
-    bc_pert = (rng.randn(steps, 1, ny + 2, 1, 1) * 0.01).astype(np.float32)
-    sim.dirichlet_values = ns["update_dirichlet_values"](s["dirichlet_values_staggered"], ((False, False), (True, False)),
-                                                       (([], []), (bcx + bc_pert[0], [])))
+    inflow = "inlet_profile" in s                      # spatial mixing layer: per-step inflow perturbation; periodic setups: none
+    bcx = s["inlet_profile"].reshape(1, ny + 2, 1, 1).astype(np.float32) if inflow else np.zeros((1, ny + 2, 1, 1), np.float32)
+    bc_pert = (rng.randn(steps, 1, ny + 2, 1, 1) * (0.01 if inflow else 0.0)).astype(np.float32)
+    if inflow:
+        sim.dirichlet_values = ns["update_dirichlet_values"](s["dirichlet_values_staggered"], ((False, False), (True, False)),
+                                                           (([], []), (bcx + bc_pert[0], [])))
     vel_t = RR.tf_tensor(SU.stagger_flat(vel[None], ny, nx), True)
     pres_t = RR.tf_tensor(pres.reshape(1, ny, nx, 1).copy(), True)
     velocity = ns["StaggeredGrid"].sample(vel_t, domain=domain)
     pressure = ns["CenteredGrid"](pres_t, box=domain.box, extrapolation=ns["pressure_extrapolation"](domain.boundaries))
     simulation_parameters = dict(dx_ratio=1, dt=s["dt"], dt_ratio=1, HRres=[ny, nx], sponge_ratio=0.875)
-    training_dict = dict(step_count=steps, HR_buffer_width=[[0, 0], [0, 0]], pressure_included=True, loss_influence_range=2)
+    training_dict = dict(step_count=steps, HR_buffer_width=[[0, 0], [0, 0]], pressure_included=True, loss_influence_range=influence)
     network = lambda x: ns["fullyconv_network"](x, tw, [[0, 0], [0, 0]], "SAME", False)
-    visc_field = RR.tf_tensor(np.asarray(s["visc"], np.float32))
-    update = lambda dv, pl: ns["update_dirichlet_values"](dv, ((False, False), (True, False)), pl)
+    visc_field = RR.tf_tensor(np.asarray(s["visc"], np.float32)) if np.atleast_1d(s["visc"]).size > 1 else None
+    update = (lambda dv, pl: ns["update_dirichlet_values"](dv, ((False, False), (True, False)), pl)) if inflow else None
+    wrapper = ns["neural_network_wrapper"] if inflow else (lambda net, x, *a: net(x))
     log.calls.clear()
     out = ns["run_piso_steps"](velocity, pressure, domain, {}, simulation_parameters, training_dict, network,
-                               ns["neural_network_wrapper"], sim, visc_field, bcx, RR.tf_tensor(bc_pert), update, None)
+                               wrapper, sim, visc_field, bcx, RR.tf_tensor(bc_pert), update, None)
     w_loss = rng.randn(steps, 1, ny + 1, nx + 1, 2).astype(np.float32)
     loss = sum((out[7][k] * RR.tf_tensor(w_loss[k])).sum() for k in range(steps))
     loss.backward()
@@ -231,6 +234,49 @@ def unroll_goldens(ns, log, name="sml16x48", steps=3):
         res["g_w%d" % i] = tw[i].grad.numpy()
     np.savez_compressed(os.path.join(OUT, "unroll_%s.npz" % name), **res)
     print("unroll", name, "loss", float(loss), "ops", len(log.calls), "|g_w0|", float(np.abs(res["g_w0"]).sum()))
+
+
+def unroll_c3_goldens(ns, log, steps=16):
+    """BASELINE configs[2] at full size: temporally evolving mixing layer 256 x 128, 16-step unrolled run_piso_steps with
+    the closure network and gradients through all 16 steps (loss_influence_range = 16), executed by the reference's own
+    Python.  To keep the fixture small only steps 0, 7 and 15 are stored in full, plus fp64 checksums (sum, L2 norm) of
+    every step's velocity and pressure, the loss, and the gradients w.r.t. the closure weights and the initial velocity."""
+    from common import random_fields
+    from diffpiso_b200 import setups as SU
+    s = SU.temporal_mixing_layer(ny=128, nx=256, visc=2e-3, dt=0.05)
+    ny, nx = s["ny"], s["nx"]
+    domain, sim = reference_objects(ns, s)
+    rng = np.random.RandomState(23)
+    vel, pres = random_fields(s, 61)
+    w = closure_weights()
+    tw = [RR.tf_tensor(k, True) for k in w]
+    bcx = np.zeros((1, ny + 2, 1, 1), np.float32)
+    bc_pert = np.zeros((steps, 1, ny + 2, 1, 1), np.float32)
+    vel_t = RR.tf_tensor(SU.stagger_flat(vel[None], ny, nx), True)
+    pres_t = RR.tf_tensor(pres.reshape(1, ny, nx, 1).copy(), True)
+    velocity = ns["StaggeredGrid"].sample(vel_t, domain=domain)
+    pressure = ns["CenteredGrid"](pres_t, box=domain.box, extrapolation=ns["pressure_extrapolation"](domain.boundaries))
+    simulation_parameters = dict(dx_ratio=1, dt=s["dt"], dt_ratio=1, HRres=[ny, nx], sponge_ratio=0.875)
+    training_dict = dict(step_count=steps, HR_buffer_width=[[0, 0], [0, 0]], pressure_included=True, loss_influence_range=steps)
+    network = lambda x: ns["fullyconv_network"](x, tw, [[0, 0], [0, 0]], "SAME", False)
+    wrapper = lambda net, x, *a: net(x)
+    log.calls.clear()
+    out = ns["run_piso_steps"](velocity, pressure, domain, {}, simulation_parameters, training_dict, network,
+                               wrapper, sim, None, bcx, RR.tf_tensor(bc_pert), None, None)
+    w_loss = rng.randn(1, ny + 1, nx + 1, 2).astype(np.float32)          # the same cotangent for every step
+    loss = sum((out[7][k] * RR.tf_tensor(w_loss)).sum() for k in range(steps))
+    loss.backward()
+    vs = [t.detach().numpy() for t in out[7]]
+    ps = [t.detach().numpy() for t in out[8]]
+    res = dict(vel=vel, pres=pres, w_loss=w_loss, loss=np.float64(loss.detach().numpy()), keep=np.array([0, 7, 15]),
+               velocities=np.stack([vs[k] for k in (0, 7, 15)]), pressures=np.stack([ps[k] for k in (0, 7, 15)]),
+               vel_sum=np.array([v.astype(np.float64).sum() for v in vs]), vel_l2=np.array([np.linalg.norm(v.astype(np.float64)) for v in vs]),
+               pres_l2=np.array([np.linalg.norm((p - p.mean()).astype(np.float64)) for p in ps]),
+               g_vel=vel_t.grad.numpy(), ops=np.array([n + (":T" if kw.get("transpose") else "") for n, kw in log.calls]))
+    for i, k in enumerate(w):
+        res["g_w%d" % i] = tw[i].grad.numpy()
+    np.savez_compressed(os.path.join(OUT, "unroll_c3_tml256x128.npz"), **res)
+    print("unroll c3", "loss", float(loss), "ops", len(log.calls), "|g_w0|", float(np.abs(res["g_w0"]).sum()))
 
 
 def loss_goldens(ns):
@@ -263,6 +309,12 @@ def main():
     from common import SMALL_SETUPS
     os.makedirs(OUT, exist_ok=True)
     ns, log = RR.load_reference(O)
+    if "--c3" in sys.argv:                                   # only the full-size configs[2] unroll (minutes of CPU)
+        unroll_c3_goldens(ns, log)
+        return
+    if "--unroll-periodic" in sys.argv:                      # run_piso_steps on a periodic axis: 5 steps, gradients through all
+        unroll_goldens(ns, log, name="tml16x24", steps=5, influence=5)
+        return
     mask_goldens(ns)
     network_goldens(ns)
     loss_goldens(ns)

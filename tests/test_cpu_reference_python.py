@@ -213,3 +213,37 @@ def test_oracle_bicgstab_matches_reference_cpu_solver(name):
         #  larger relative error)
         assert rel_l2(xt, g["bicg_adj_spsolve"][lo:hi]) < 2e-5
     assert rel_l2(g["u_star"], g["u_star_spsolve"]) < 1e-6
+
+
+def test_oracle_unroll_on_a_periodic_axis_reproduces_the_rewrapped_state_quirk():
+    """run_piso_steps (combined_training_integrated.py:396-478) on the temporal mixing layer (periodic in x), 5 unrolled
+    steps executed by the reference's own Python.  From the second step on the reference re-wraps the state with
+    StaggeredGrid(array, box, extrapolation) -- the extrapolation lands in the `name` parameter -- so custom_padded
+    replicates the velocity on the periodic axis while the matrix stays periodic (quirk Q21), and the increments have the
+    default 'boundary' extrapolation.  The oracle with `vel_pad_periodic=(False, False)` from step 2 on reproduces every
+    state; without the quirk the second state is already off by ~1e-3."""
+    import torch
+    from diffpiso_b200 import networks as N, setups as SU, training as T
+    from diffpiso_b200.grids import CenteredGrid, StaggeredGrid
+    from test_gpu_piso_step import extrap
+    g = np.load(os.path.join(GOLD, "unroll_tml16x24.npz"))
+    s = SMALL_SETUPS["tml16x24"]()
+    ny, nx = s["ny"], s["nx"]
+    steps = g["velocities"].shape[0]
+    quirk = dict(s, pbc_inc=[SU.REPLICATE] * 4, vel_pad_periodic=(False, False))
+    first = dict(s, pbc_inc=[SU.REPLICATE] * 4)
+    w = _weights(g)
+    flat = lambda t: SU.flatten_staggered(t)[0].astype(np.float32)
+    for use_quirk in (True, False):
+        vel, pres = g["vel"].copy(), g["pres"].copy()
+        worst = 0.0
+        for k in range(steps):
+            velocity = StaggeredGrid(torch.from_numpy(SU.stagger_flat(vel[None], ny, nx)), dx=(s["dy"], s["dx"]))
+            forcing = flat(T.closure_forcing(torch.from_numpy(g["nn_out"][k]), velocity).numpy())
+            setup = first if (k == 0 or not use_quirk) else quirk
+            vel, pres, _ = O.piso_step(setup, vel, pres, forcing=forcing)
+            worst = max(worst, rel_l2(vel, flat(g["velocities"][k])))
+        if use_quirk:
+            assert worst < 2e-6, worst
+        else:
+            assert worst > 1e-4, worst                                   # the quirk is visible: it has to be reproduced
