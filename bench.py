@@ -392,7 +392,8 @@ def run_ours(args):
     # ---- end-to-end: host buffers in, host buffers out, every step ------------------------------------------------
     # Every step takes its state from pinned host memory and leaves the new state and the gradients in pinned host
     # memory.  The new state is copied out on a side stream as soon as the forward pass has produced it (it overlaps
-    # the adjoint); the step's output buffers become the next step's input buffers (pointer swap, no host memcpy).
+    # the adjoint); the step's output buffers become the next step's input buffers (pointer swap, no host memcpy), and
+    # their upload for the next step follows the download on the same side stream, i.e. it also overlaps the adjoint.
     hv = torch.as_tensor(vel.cpu().numpy()).pin_memory()
     hp = torch.as_tensor(pres.cpu().numpy()).pin_memory()
     out_v, out_p = torch.empty_like(hv).pin_memory(), torch.empty_like(hp).pin_memory()
@@ -400,9 +401,20 @@ def run_ours(args):
     copy_stream = torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.current_stream(dev)
 
-    def e2e_step(hv, hp, out_v, out_p):
-        dv = hv.to(dev, non_blocking=True).requires_grad_(True)
-        dpres = hp.to(dev, non_blocking=True).requires_grad_(True)
+    prefetched = {}
+
+    def e2e_step(hv, hp, out_v, out_p, prefetch_next):
+        """One forward + adjoint step with host buffers on both sides.  The step's inputs come from pinned host memory (hv,
+        hp): either uploaded here, or -- software pipelining, as a rollout driver would do it -- already uploaded on the
+        copy stream while the PREVIOUS step's adjoint was running (its new state had reached the host by then; the upload
+        reads exactly these host buffers).  Every copy of every step stays inside the timed region."""
+        if prefetched:
+            main_stream.wait_event(prefetched.pop("event"))
+            dv, dpres = prefetched.pop("v"), prefetched.pop("p")
+        else:
+            dv, dpres = hv.to(dev, non_blocking=True), hp.to(dev, non_blocking=True)
+        dv.requires_grad_(True)
+        dpres.requires_grad_(True)
         velocity = dp.StaggeredGrid(flat=dv, resolution=(NY, NX), dx=dxy, extrapolation="periodic")
         pressure = dp.CenteredGrid(dpres.reshape(BATCH, NY, NX, 1), dx=dxy, extrapolation="periodic")
         v_new, p_new, warn = dp.piso_step(velocity, pressure, pressure, pressure, s["dt"], sim, dvals)
@@ -413,21 +425,28 @@ def run_ours(args):
             copy_stream.wait_event(fwd_done)
             out_v.copy_(nv, non_blocking=True)
             out_p.copy_(npr, non_blocking=True)
+            if prefetch_next:                        # the next step reads (out_v, out_p): upload them behind the download
+                nxt_v, nxt_p = out_v.to(dev, non_blocking=True), out_p.to(dev, non_blocking=True)
+                nxt_v.record_stream(main_stream)
+                nxt_p.record_stream(main_stream)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+                prefetched.update(v=nxt_v, p=nxt_p, event=ev)
         loss = (v_new.flat * w_u).sum() + (p_new.data.reshape(BATCH, nc) * w_p).sum()
         gv2, gp2 = torch.autograd.grad(loss, (dv, dpres))
         out_gv.copy_(gv2, non_blocking=True)
         out_gp.copy_(gp2, non_blocking=True)
         copy_stream.synchronize()
-        main_stream.synchronize()
+        main_stream.synchronize()                    # the host owns the step's results (state + gradients) from here on
         return nv, npr
 
     for _ in range(2):                                   # untimed: stream / allocator warm-up of this loop
-        e2e_step(hv, hp, out_v, out_p)
+        e2e_step(hv, hp, out_v, out_p, False)
     barrier()
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     g0.record()
-    for _ in range(args.steps):
-        e2e_step(hv, hp, out_v, out_p)
+    for k in range(args.steps):
+        e2e_step(hv, hp, out_v, out_p, k + 1 < args.steps)
         hv, out_v = out_v, hv
         hp, out_p = out_p, hp
     g1.record()

@@ -1,0 +1,3 @@
+timeout 900 python -m pytest tests/test_gpu_kernels.py -m gpu -q --timeout 300 -p no:cacheprovider -k "bicgstab" 2>&1 | tail -4
+timeout 120 python scripts/bicg_micro.py 64 128
+timeout 120 python scripts/bicg_micro.py 64 128
