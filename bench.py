@@ -286,7 +286,8 @@ def run_ours(args):
                                          residual_reset=s["cg_reset"])
     sim = dp.SimulationParameters(s["dirichlet_mask"], s["dirichlet_values_staggered"], s["active_mask"],
                                   s["accessible_mask"], bool_periodic=(True, True), no_slip_mask=s["no_slip_mask"],
-                                  viscosity=float(s["visc"]), linear_solver=ls, pressure_solver=ps)
+                                  viscosity=float(s["visc"]), linear_solver=ls, pressure_solver=ps,
+                                  stream_groups=args.stream_groups)
     # --same-seeds: every rank solves the same samples, which separates host launch jitter from iteration imbalance
     from diffpiso_b200 import sharding
     # weak scaling: the job has BATCH * world samples, rank r owns the contiguous block shard_bounds() gives it
@@ -301,18 +302,23 @@ def run_ours(args):
     w_p = rng.randn(BATCH, nc).astype(np.float32)
     w_p = torch.as_tensor(w_p - w_p.mean(axis=1, keepdims=True)).to(dev)
 
-    def step(vel, pres):
-        """forward + adjoint of one PISO step; returns the new state and the input gradients"""
+    def group_step(vel, pres, w_u, w_p):
+        """forward + adjoint of one PISO step for a block of samples -> new state and input gradients (what the sample
+        groups run; the loss weights are per sample, so the block's gradients are those of the whole-batch loss)"""
+        nb = vel.shape[0]
         vel = vel.detach().requires_grad_(True)
         pres = pres.detach().requires_grad_(True)
         velocity = dp.StaggeredGrid(flat=vel, resolution=(NY, NX), dx=dxy, extrapolation="periodic")
-        pressure = dp.CenteredGrid(pres.reshape(BATCH, NY, NX, 1), dx=dxy, extrapolation="periodic")
+        pressure = dp.CenteredGrid(pres.reshape(nb, NY, NX, 1), dx=dxy, extrapolation="periodic")
         v_new, p_new, warn = dp.piso_step(velocity, pressure, pressure, pressure, s["dt"], sim, dvals)
-        loss = (v_new.flat * w_u).sum() + (p_new.data.reshape(BATCH, nc) * w_p).sum()
+        loss = (v_new.flat * w_u).sum() + (p_new.data.reshape(nb, nc) * w_p).sum()
         gv, gp = torch.autograd.grad(loss, (vel, pres))
-        return v_new.flat.detach(), p_new.data.reshape(BATCH, nc).detach(), gv, gp
+        return v_new.flat.detach(), p_new.data.reshape(nb, nc).detach(), gv, gp
 
-    # launch counting / per-kernel event timing hooks
+    def step(vel, pres):
+        return group_step(vel, pres, w_u, w_p)
+
+    # launch counting / per-kernel event timing hooks (eager passes only: a graph replay does not come through Python)
     launches = {"n": 0}
     cg_events = []
     orig_check = ops.N.check
@@ -330,7 +336,6 @@ def run_ours(args):
         e1.record()
         cg_events.append((e0, e1, out[1]))
         return out
-    ops.pressure_cg = timed_cg
     bicg_events = []
     orig_bicg = ops.bicgstab_ilu
 
@@ -341,40 +346,64 @@ def run_ours(args):
         e1.record()
         bicg_events.append((e0, e1, out[1]))
         return out
-    ops.bicgstab_ilu = timed_bicg
-
-    vel, pres = torch.as_tensor(vel_h).to(dev), torch.as_tensor(pres_h).to(dev)
-    for _ in range(args.warmup):
-        vel, pres, gv, gp = step(vel, pres)
-    torch.cuda.synchronize()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing --------------------------------------------------------------------------------
-    cg_events.clear()
-    bicg_events.clear()
-    launches["n"] = 0
+    vel, pres = torch.as_tensor(vel_h).to(dev), torch.as_tensor(pres_h).to(dev)
+    # ---- headline: the batch as `groups` independent sample pipelines (diffpiso_b200.SampleGroups), each captured once
+    # as a CUDA graph; a step = one launch of every group, the new state fed back as the next step's input -------------
+    groups = max(1, min(args.groups, BATCH))
+    runner = dp.SampleGroups(group_step, (vel, pres, w_u, w_p), groups=groups, graph=args.graph)
+    feedback = {0: 0, 1: 1}
+    for _ in range(args.warmup):
+        runner.step(feedback)
+    runner.join()
     sampler = ClockSampler(local) if rank == 0 else None
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    for st_ in runner.streams:
+        st_.wait_event(e0)
     for _ in range(args.steps):
-        vel, pres, gv, gp = step(vel, pres)
+        runner.step(feedback)
+    runner.join()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    n_launch = launches["n"]
     clocks = sampler.stop() if sampler else None
+    vel, pres, gv = runner.gather(0), runner.gather(1), runner.gather(2)
+    finite = bool(torch.isfinite(vel).all() and torch.isfinite(gv).all())
+
+    # ---- per-kernel pass: the same steps, eagerly, with the whole batch on ONE stream, so that every solver launch runs
+    # alone and its CUDA-event duration is the kernel's own (in the headline region the launches of the sample groups
+    # overlap each other on purpose); the rooflines below are computed from these durations and say so.  The native
+    # launches of one eager step are counted here: every group's graph holds the same kernel sequence.
+    ops.pressure_cg, ops.bicgstab_ilu = timed_cg, timed_bicg
+    vs_, ps_ = vel.clone(), pres.clone()
+    for _ in range(2):
+        vs_, ps_, _, _ = step(vs_, ps_)
+    cg_events.clear()
+    bicg_events.clear()
+    launches["n"] = 0
+    barrier()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for _ in range(args.steps):
+        vs_, ps_, _, _ = step(vs_, ps_)
+    k1.record()
+    barrier()
+    ms_serial = k0.elapsed_time(k1)
+    n_launch = launches["n"] * groups                              # launches inside the headline region (all groups)
+    ops.pressure_cg, ops.bicgstab_ilu = orig_cg, orig_bicg
     cg_ms = [a.elapsed_time(b) for a, b, _ in cg_events]
     cg_its = np.concatenate([it.cpu().numpy() for _, _, it in cg_events]).astype(np.float64)
     bicg_ms = [a.elapsed_time(b) for a, b, _ in bicg_events]
     bicg_its = np.concatenate([st.cpu().numpy()[:, :, 0].ravel() for _, _, st in bicg_events]).astype(np.float64)
-    finite = bool(torch.isfinite(vel).all() and torch.isfinite(gv).all())
 
-    # ---- forward-only rollout (reported beside the headline) -------------------------------------------------------
+    # ---- forward-only rollout (reported beside the headline; eager, one stream) ---------------------------------------
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     vf, pf = vel.clone(), pres.clone()
@@ -389,71 +418,43 @@ def run_ours(args):
     barrier()
     ms_fwd = f0.elapsed_time(f1)
 
-    # ---- end-to-end: host buffers in, host buffers out, every step ------------------------------------------------
-    # Every step takes its state from pinned host memory and leaves the new state and the gradients in pinned host
-    # memory.  The new state is copied out on a side stream as soon as the forward pass has produced it (it overlaps
-    # the adjoint); the step's output buffers become the next step's input buffers (pointer swap, no host memcpy), and
-    # their upload for the next step follows the download on the same side stream, i.e. it also overlaps the adjoint.
-    hv = torch.as_tensor(vel.cpu().numpy()).pin_memory()
-    hp = torch.as_tensor(pres.cpu().numpy()).pin_memory()
-    out_v, out_p = torch.empty_like(hv).pin_memory(), torch.empty_like(hp).pin_memory()
-    out_gv, out_gp = torch.empty_like(hv).pin_memory(), torch.empty_like(hp).pin_memory()
-    copy_stream = torch.cuda.Stream(device=dev)
-    main_stream = torch.cuda.current_stream(dev)
+    # ---- end-to-end: host buffers in, host buffers out, every step of every group ---------------------------------------
+    # The same runner, driven with HOST buffers: every step a group uploads its state from pinned host memory, runs forward
+    # + adjoint, and downloads the new state and the gradients into pinned host memory; the host waits for the group's
+    # download before it hands the step's output buffers back as the next step's input buffers (pointer swap, no host
+    # memcpy).  Groups are independent, so one group's copies overlap the others' kernels.  Every copy of every step is
+    # inside the timed region.
+    h_in = [[torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in runner.inputs(i)[:2]] for i in range(groups)]
+    h_out = [[torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in runner.outputs(i)] for i in range(groups)]
+    for i in range(groups):
+        for h, d in zip(h_in[i], runner.outputs(i)[:2]):
+            h.copy_(d)
+    torch.cuda.synchronize()
 
-    prefetched = {}
-
-    def e2e_step(hv, hp, out_v, out_p, prefetch_next):
-        """One forward + adjoint step with host buffers on both sides.  The step's inputs come from pinned host memory (hv,
-        hp): either uploaded here, or -- software pipelining, as a rollout driver would do it -- already uploaded on the
-        copy stream while the PREVIOUS step's adjoint was running (its new state had reached the host by then; the upload
-        reads exactly these host buffers).  Every copy of every step stays inside the timed region."""
-        if prefetched:
-            main_stream.wait_event(prefetched.pop("event"))
-            dv, dpres = prefetched.pop("v"), prefetched.pop("p")
-        else:
-            dv, dpres = hv.to(dev, non_blocking=True), hp.to(dev, non_blocking=True)
-        dv.requires_grad_(True)
-        dpres.requires_grad_(True)
-        velocity = dp.StaggeredGrid(flat=dv, resolution=(NY, NX), dx=dxy, extrapolation="periodic")
-        pressure = dp.CenteredGrid(dpres.reshape(BATCH, NY, NX, 1), dx=dxy, extrapolation="periodic")
-        v_new, p_new, warn = dp.piso_step(velocity, pressure, pressure, pressure, s["dt"], sim, dvals)
-        nv, npr = v_new.flat.detach(), p_new.data.reshape(BATCH, nc).detach()
-        fwd_done = torch.cuda.Event()
-        fwd_done.record(main_stream)
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(fwd_done)
-            out_v.copy_(nv, non_blocking=True)
-            out_p.copy_(npr, non_blocking=True)
-            if prefetch_next:                        # the next step reads (out_v, out_p): upload them behind the download
-                nxt_v, nxt_p = out_v.to(dev, non_blocking=True), out_p.to(dev, non_blocking=True)
-                nxt_v.record_stream(main_stream)
-                nxt_p.record_stream(main_stream)
-                ev = torch.cuda.Event()
-                ev.record(copy_stream)
-                prefetched.update(v=nxt_v, p=nxt_p, event=ev)
-        loss = (v_new.flat * w_u).sum() + (p_new.data.reshape(BATCH, nc) * w_p).sum()
-        gv2, gp2 = torch.autograd.grad(loss, (dv, dpres))
-        out_gv.copy_(gv2, non_blocking=True)
-        out_gp.copy_(gp2, non_blocking=True)
-        copy_stream.synchronize()
-        main_stream.synchronize()                    # the host owns the step's results (state + gradients) from here on
-        return nv, npr
-
-    for _ in range(2):                                   # untimed: stream / allocator warm-up of this loop
-        e2e_step(hv, hp, out_v, out_p, False)
+    def e2e_steps(n):
+        for _ in range(n):
+            for i in range(groups):
+                runner.sync(i)                       # the host owns group i's previous results (state + gradients)
+                runner.load(i, h_in[i][0], h_in[i][1], None, None)
+                runner.launch(i)
+                runner.fetch(i, *h_out[i])
+                h_in[i][0], h_out[i][0] = h_out[i][0], h_in[i][0]       # next step reads what this step writes
+                h_in[i][1], h_out[i][1] = h_out[i][1], h_in[i][1]
+        for i in range(groups):
+            runner.sync(i)
+    e2e_steps(2)                                         # untimed: warm-up of this loop
     barrier()
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     g0.record()
-    for k in range(args.steps):
-        e2e_step(hv, hp, out_v, out_p, k + 1 < args.steps)
-        hv, out_v = out_v, hv
-        hp, out_p = out_p, hp
+    for st_ in runner.streams:
+        st_.wait_event(g0)
+    e2e_steps(args.steps)
+    runner.join()
     g1.record()
     barrier()
     ms_e2e = g0.elapsed_time(g1)
-
-    times = torch.tensor([ms, ms_fwd, ms_e2e], dtype=torch.float64, device=dev)
+    ops.N.check = orig_check
+    times = torch.tensor([ms, ms_fwd, ms_e2e, ms_serial], dtype=torch.float64, device=dev)
     # per-rank diagnostics of the device-resident loop: step time, sum of CG iterations, mean of the per-launch maxima
     # (a launch lasts as long as its slowest sample), time inside the CG / BiCGStab launches
     launch_max = [float(it.max()) for _, _, it in cg_events[:len(cg_ms)]]
@@ -463,7 +464,7 @@ def run_ours(args):
     if world > 1:
         dist.all_gather(per_rank, mine)
     per_rank = [[float(v) for v in t_.cpu()] for t_ in per_rank]
-    ms, ms_fwd, ms_e2e = sharding.max_over_ranks([float(x) for x in times.cpu()], device=dev)   # the slowest rank's time
+    ms, ms_fwd, ms_e2e, ms_serial_all = sharding.max_over_ranks([float(x) for x in times.cpu()], device=dev)   # slowest rank
     # BASELINE configs[2]: one training iteration around the path (16-step unroll with the closure network, backward through
     # every step, NCCL all-reduce of the closure gradients -- the only collective of the workload -- and Adam) at N GPUs
     training = None
@@ -523,7 +524,10 @@ def run_ours(args):
         "flops_per_cell_iteration": CG_FLOPS_PER_CELL_ITER, "mean_cg_iterations": mean_it,
         "cg_iterations_min_max": [float(cg_its.min()), float(cg_its.max())],
         "mean_of_per_launch_max_iterations": float(np.mean(launch_max)),
-        "avg_launch_ms": cg_avg_ms, "cg_share_of_step": float(sum(cg_ms) / ms),
+        "avg_launch_ms": cg_avg_ms, "cg_share_of_step": float(sum(cg_ms) / ms_serial),
+        "timed": "per-kernel pass of this run: %d steps with the whole batch on one stream (%.3f ms per step), each launch "
+                 "bracketed by CUDA events; in the headline region the launches of %d sample groups overlap"
+                 % (args.steps, ms_serial / args.steps, groups),
         "traffic": traffic,
         "hbm_actual": {"achieved": (traffic / (cg_avg_ms * 1e-3) / 1e9) if traffic else None, "peak": peak, "unit": "GB/s",
                        "frac": (traffic / (cg_avg_ms * 1e-3) / 1e9 / peak) if traffic else None,
@@ -554,7 +558,11 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "grid": [NY, NX], "batch_per_gpu": BATCH, "visc": 1e-3, "cfl": 0.5,
                    "bicgstab": "fp32 tol 1e-8", "pressure_cg": "fp64 tol 1e-8 reset 1000",
                    "l2": "per-step working set (~0.4 GB of solver workspace + state) exceeds the 126 MB L2; rollout "
-                         "state changes every step", "cg_launch": cfg, "same_seeds": bool(args.same_seeds)},
+                         "state changes every step", "cg_launch": cfg, "same_seeds": bool(args.same_seeds),
+                   "sample_groups": groups, "cuda_graph_per_group": bool(args.graph)},
+        "single_stream": {"ms_per_step": ms_serial_all / args.steps, "value": cells * args.steps / (ms_serial_all * 1e-3),
+                          "note": "the same steps run eagerly with the whole batch on one stream (the per-kernel pass the "
+                                  "rooflines are taken from)"},
         "forward_only": {"value": cells * args.steps / (ms_fwd * 1e-3), "unit": "cell-updates/s",
                          "ms_per_step": ms_fwd / args.steps},
         "e2e": {"value": cells * args.steps / (ms_e2e * 1e-3), "unit": "cell-updates/s",
@@ -564,7 +572,7 @@ def run_ours(args):
         "roofline_bicgstab": {"bound": "hbm", "kernel": "bicgstab_rows_kernel (one 512-thread CTA per system, 2 launches per step)",
                               "achieved": bicg_gbs, "peak": peak, "unit": "GB/s", "frac": bicg_gbs / peak,
                               "traffic": bicg_prof.get("bytes_per_launch"), "mean_iterations": bicg_it,
-                              "avg_launch_ms": bicg_avg_ms, "share_of_step": float(sum(bicg_ms) / ms),
+                              "avg_launch_ms": bicg_avg_ms, "share_of_step": float(sum(bicg_ms) / ms_serial),
                               "note": "algorithmic bytes (SURVEY 8(d)) / launch time; latency-bound: 13 triangular sweeps x "
                                       "~260 dependent wavefront levels per solve, one CTA per system"},
         "roofline_step": {"bound": "hbm", "achieved": step_achieved, "peak": peak, "unit": "GB/s",
@@ -600,6 +608,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--cpu-steps", type=int, default=60)
     ap.add_argument("--same-seeds", action="store_true", help="every rank solves the same samples (scaling diagnostics)")
+    ap.add_argument("--groups", type=int, default=8,
+                    help="independent sample pipelines the batch is run as (diffpiso_b200.SampleGroups; 1 = one stream)")
+    ap.add_argument("--no-graph", dest="graph", action="store_false", help="run the sample groups eagerly (no CUDA graphs)")
+    ap.add_argument("--stream-groups", type=int, default=None,
+                    help="sample groups forked INSIDE every piso_step call (SimulationParameters.stream_groups)")
     ap.add_argument("--no-config5", dest="config5", action="store_false",
                     help="skip the extra BASELINE configs[4] measurement (periodic 1024^2, batch 8)")
     ap.add_argument("--no-training", dest="training", action="store_false",

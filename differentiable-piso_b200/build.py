@@ -23,17 +23,22 @@ def _deps():
     return files
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, timing=False):
+    """timing=True: diagnostics build libdpiso_timing.so (-DDPISO_CG_TIMING: %clock stamps of the pressure-CG phases,
+    scripts/cg_timing.py); never loaded by the package unless DPISO_LIBRARY points at it."""
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    if not force and os.path.exists(OUT):
-        t = os.path.getmtime(OUT)
+    out = OUT[:-3] + "_timing.so" if timing else OUT
+    extra = ["-DDPISO_CG_TIMING"] if timing else []
+    suffix = ".timing.o" if timing else ".o"
+    if not force and os.path.exists(out):
+        t = os.path.getmtime(out)
         if all(os.path.getmtime(f) <= t for f in _deps()):
-            return OUT
+            return out
     objs = []
     procs = []
     for s in srcs:
-        o = os.path.join(CSRC, os.path.basename(s)[:-3] + ".o")
-        cmd = ["nvcc"] + NVCC_FLAGS + ["-c", s, "-o", o]
+        o = os.path.join(CSRC, os.path.basename(s)[:-3] + suffix)
+        cmd = ["nvcc"] + NVCC_FLAGS + extra + ["-c", s, "-o", o]
         if verbose:
             print(" ".join(cmd))
         procs.append((subprocess.Popen(cmd), cmd))
@@ -41,14 +46,14 @@ def build(force=False, verbose=False):
     for p, cmd in procs:
         if p.wait() != 0:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    cmd = ["nvcc", "-shared", "--cudart", "shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT] + objs
+    cmd = ["nvcc", "-shared", "--cudart", "shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + objs
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)
     for o in objs:
         os.remove(o)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, timing="--timing" in sys.argv))

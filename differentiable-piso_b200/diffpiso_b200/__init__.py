@@ -14,6 +14,7 @@ from .networks import fullyconv_network, initialise_fullyconv_network
 from .losses import L2_field_loss, multistep_averaging_loss, spectral_energy_loss, strain_rate_loss
 from .training import boundary_perturbation_fun, inference_rollout, run_piso_steps, zero_gradient_op
 from .datamanagement import create_base_dir, data_path_assembler, load_function
+from .sharding import SampleGroups
 
 __all__ = ["CenteredGrid", "StaggeredGrid", "flatten_staggered_data", "stagger_flattened_data",
            "stack_staggered_components", "unstack_staggered_tensor", "LinearSolver", "LinearSolverCudaBicgstabILU",
@@ -24,4 +25,4 @@ __all__ = ["CenteredGrid", "StaggeredGrid", "flatten_staggered_data", "stagger_f
            "initialise_fullyconv_network", "L2_field_loss", "spectral_energy_loss", "strain_rate_loss",
            "multistep_averaging_loss", "run_piso_steps", "zero_gradient_op", "inference_rollout",
            "boundary_perturbation_fun", "create_base_dir", "data_path_assembler",
-           "load_function"]
+           "load_function", "SampleGroups"]

@@ -10,7 +10,9 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libdpiso.so")
+# DPISO_LIBRARY: load another build of the same C ABI (the diagnostics build of build.py --timing); no effect on the
+# no-fallback rule: whatever is loaded must export every entry point below
+_LIB_PATH = os.environ.get("DPISO_LIBRARY") or os.path.join(_HERE, "libdpiso.so")
 
 
 class DpisoError(RuntimeError):

@@ -347,6 +347,11 @@ def pressure_cg(g, lap, div, accuracy, max_it, residual_reset, rank_deficient):
     return x32, its
 
 
+def pressure_cg_on_chip(g, batch):
+    """True when the pressure CG of this grid keeps its solver state on chip (cluster-resident kernel, no workspace)."""
+    return N.lib.dpiso_pressure_cg_workspace_bytes(int(batch), g.ny, g.nx, 8, 0) == 0
+
+
 def pressure_cg_config():
     out = (C.c_int * 5)()
     N.lib.dpiso_pressure_cg_last_config(out)

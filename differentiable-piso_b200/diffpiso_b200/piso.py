@@ -25,7 +25,10 @@ class SimulationParameters(object):
     centred grid; bool_periodic = (periodic_y, periodic_x)."""
 
     def __init__(self, dirichlet_mask, dirichlet_values, active_mask, accessible_mask, bool_periodic=None,
-                 no_slip_mask=None, viscosity=0., linear_solver=None, pressure_solver=None):
+                 no_slip_mask=None, viscosity=0., linear_solver=None, pressure_solver=None, stream_groups=None):
+        # stream_groups (not in the reference): how many sample groups of a batch `piso_step` runs on concurrent CUDA
+        # streams; None / 1 = the whole batch on the caller's stream, "auto" = the rule of `_stream_groups`
+        self.stream_groups = stream_groups
         self.pressure_solver = pressure_solver
         self.linear_solver = linear_solver
         self.dirichlet_mask = dirichlet_mask
@@ -170,6 +173,82 @@ class _PisoStepFn(torch.autograd.Function):
         return gvel_in, gpres_in, gdvals, gforce, None, None
 
 
+# ---- sample groups on concurrent streams -------------------------------------------------------------------------
+# The samples of a batch never exchange data inside a step (the batch is the partition), and on the small
+# grids both solvers are latency-bound persistent kernels whose launches end in a tail of a few slow samples (the
+# pressure CG runs one cluster per sample until ITS residual test passes; the predictor runs one CTA per system).
+# Running sample groups on separate streams lets the solver launches of one group fill the SMs the tail of another
+# group's launch leaves idle.  Results are bit-identical to the single-stream step (same kernels, same per-sample
+# arithmetic).  Measured on B200, periodic 128^2 x 64, forward + adjoint, groups forked and joined inside every call:
+# 10.09 ms (1 group), 9.64 (2), 9.56 (4); as independent pipelines (sharding.SampleGroups): 9.07 (2), 8.47 (4),
+# profiles/r02_stream_groups.md.
+_GROUP_STREAMS = {}
+
+
+def _group_streams(device, n):
+    key = (device.index if device.index is not None else torch.cuda.current_device(), n)
+    st = _GROUP_STREAMS.get(key)
+    if st is None:
+        st = _GROUP_STREAMS[key] = [torch.cuda.Stream(device=device) for _ in range(n)]
+    return st
+
+
+def _stream_groups(sim, c, b):
+    """Number of sample groups `piso_step` itself forks for a batch of b samples: `SimulationParameters.stream_groups`
+    (or DPISO_STREAM_GROUPS), default 1.  Opt-in because inside ONE call all groups pass through the same phase together
+    (measured gain 4-5 %: 10.09 -> 9.56 ms with 4 groups); the larger gain needs pipelines that are independent across
+    forward, adjoint and steps -- `sharding.SampleGroups`, 16-20 %.  "auto" = 4 groups from 32 samples, 2 from 16, where both solver plug-ins
+    are native and the pressure CG keeps its state on chip (larger grids already fill the GPU with one cooperative
+    launch), never while a CUDA graph is being captured."""
+    import os
+    want = getattr(sim, "stream_groups", None)
+    if want is None:
+        want = os.environ.get("DPISO_STREAM_GROUPS") or 1
+    if want != "auto":
+        return max(1, min(int(want), b))
+    if not (getattr(sim.linear_solver, "_dpiso_native", False) and getattr(sim.pressure_solver, "_dpiso_native", False)):
+        return 1
+    if torch.cuda.is_current_stream_capturing():
+        return 1
+    if not ops.pressure_cg_on_chip(c.g, b):
+        return 1
+    return 4 if b >= 32 else (2 if b >= 16 else 1)
+
+
+def _apply_grouped(vel, pres, dvals, forcing, visc, c, groups):
+    """`_PisoStepFn` on `groups` contiguous sample blocks, each on its own stream; -> list of per-group output tuples.
+    The caller's stream waits for every group before it touches the results; gradients flow back through the same
+    streams (autograd runs a node's backward on the stream of its forward)."""
+    dev = vel.device
+    b = vel.shape[0]
+    main = torch.cuda.current_stream(dev)
+    streams = _group_streams(dev, groups)
+
+    def parts(t):
+        if t is None:
+            return [None] * groups
+        if t.shape[0] == b and b > 1:
+            return list(torch.tensor_split(t, groups))
+        return [t] * groups
+    vs, prs, dvs, fs, vis = parts(vel.contiguous()), parts(pres.contiguous()), parts(dvals), parts(forcing), parts(visc)
+    ready = torch.cuda.Event()
+    ready.record(main)
+    outs = []
+    for i, st in enumerate(streams):
+        st.wait_event(ready)
+        with torch.cuda.stream(st):
+            out = _PisoStepFn.apply(vs[i], prs[i], dvs[i], fs[i], vis[i], c)
+        done = torch.cuda.Event()
+        done.record(st)
+        main.wait_event(done)
+        outs.append(out)
+    # No record_stream on the group outputs: the caller's stream consumes them (concatenation) before it records the next
+    # step's `ready` event, which every group stream waits for before it can reuse a block of its own pool; recording
+    # them would park every freed block behind an event query and drive a run-ahead host into cudaMalloc (measured:
+    # 36 ms instead of 8.5 ms per step).
+    return outs
+
+
 def _flat_faces(x, b, g, name):
     """staggered tensor / StaggeredGrid / flat -> [1|B, nf] float32 on the right device"""
     if isinstance(x, StaggeredGrid):
@@ -237,7 +316,14 @@ def piso_step(velocity, pressure, pressure_inc1, pressure_inc2, dt, simulation_p
         visc = as_tensor(viscosity_field).to(vel.device)
         if visc.dim() == 4:
             visc = flatten_staggered_data(visc, coord_flip=True)
-    out = _PisoStepFn.apply(vel, pres, dvals, forcing, visc, c)
+    groups = _stream_groups(sim, c, b)
+    if groups > 1:
+        outs = _apply_grouped(vel, pres, dvals, forcing, visc, c, groups)
+        n_cat = len(outs[0]) if full_output else 2                           # the intermediates only when asked for
+        out = [torch.cat([o[k] for o in outs]) if k != 4 else None for k in range(n_cat)] + [None] * (len(outs[0]) - n_cat)
+        out[4] = torch.stack([o[4] for o in outs]).amax(0)                   # warn: any sample of any group
+    else:
+        out = _PisoStepFn.apply(vel, pres, dvals, forcing, visc, c)
     vel_next, pres_next, p1, p2, warn_new, values, a_diag, rhs, u_star, u_s2, h, div1, div2, lap1, lap2, its1, its2 = out
     if warn is not None:
         warn_new = torch.maximum(warn_new, as_tensor(warn).to(vel.device).reshape(-1)[:1].to(torch.float32))

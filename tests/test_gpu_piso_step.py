@@ -286,3 +286,74 @@ def test_forward_step_is_cuda_graph_capturable():
         graph.replay()
     torch.cuda.synchronize()
     assert torch.equal(sv, v) and torch.equal(sp, p)
+
+
+def _grouped_case(name, batch, seed0):
+    import diffpiso_b200 as dp
+    s = ALL_SETUPS[name]() if name in ALL_SETUPS else SMALL_SETUPS[name]()
+    ny, nx = s["ny"], s["nx"]
+    nf, nc = ny * (nx + 1) + (ny + 1) * nx, ny * nx
+    fields = [random_fields(s, seed0 + i) for i in range(batch)]
+    vel = np.stack([f[0] for f in fields])
+    pres = np.stack([f[1] for f in fields])
+    rng = np.random.RandomState(5)
+    w_u, w_p = rng.randn(batch, nf).astype(np.float32), rng.randn(batch, nc).astype(np.float32)
+    w_p -= w_p.mean(axis=1, keepdims=True)
+    forcing = (0.1 * rng.randn(batch, nf)).astype(np.float32)
+    return dp, s, vel, pres, forcing, w_u, w_p
+
+
+@pytest.mark.parametrize("name,groups", [("periodic32", 4), ("ldc32", 3), ("tml16x24", 2)])
+def test_stream_groups_are_bit_identical_to_the_single_stream_step(name, groups):
+    """Sample groups of a batch on concurrent CUDA streams (`SimulationParameters.stream_groups`): state, every
+    intermediate of `full_output`, the warning and all input gradients equal the single-stream step bit for bit (uneven
+    group sizes included: 10 samples in 3 or 4 groups)."""
+    dp, s, vel, pres, forcing, w_u, w_p = _grouped_case(name, 10, 40)
+    ny, nx = s["ny"], s["nx"]
+    results = []
+    for g in (1, groups):
+        sim = build_sim(s)
+        sim.stream_groups = g
+        tv = torch.as_tensor(vel).to(DEV).requires_grad_(True)
+        tp = torch.as_tensor(pres).to(DEV).requires_grad_(True)
+        tf = torch.as_tensor(forcing).to(DEV).requires_grad_(True)
+        out = run_step(s, sim, tv, tp, forcing=tf, full_output=True)
+        v_new, p_new = out[0], out[1]
+        loss = (v_new.flat * torch.as_tensor(w_u).to(DEV)).sum() + (p_new.data.reshape(10, -1) * torch.as_tensor(w_p).to(DEV)).sum()
+        gv, gp, gf = torch.autograd.grad(loss, (tv, tp, tf))
+        torch.cuda.synchronize()
+        flat = [v_new.flat, p_new.data, out[2].data, out[3].data, out[4], out[7], out[9], out[10], out[13], out[14],
+                out[15], out[16], gv, gp, gf]
+        results.append([t.detach().cpu() for t in flat])
+    for a, b in zip(*results):
+        assert a.shape == b.shape and torch.equal(a, b)
+
+
+def test_stream_groups_auto_rule_and_rollout():
+    """The "auto" rule picks 2 groups for 16 samples and 4 for 32+ on a grid whose CG state is on chip, one group for
+    small batches (the default is one group); a 3-step no-grad rollout with the automatic groups equals the
+    single-stream rollout."""
+    from diffpiso_b200 import piso as P
+    dp, s, vel, pres, forcing, w_u, w_p = _grouped_case("periodic32", 16, 70)
+    ny, nx = s["ny"], s["nx"]
+    finals = []
+    for g in (1, "auto"):
+        sim = build_sim(s)
+        sim.stream_groups = g
+        v, p = torch.as_tensor(vel).to(DEV), torch.as_tensor(pres).to(DEV)
+        with torch.no_grad():
+            for _ in range(3):
+                vg, pg, _ = run_step(s, sim, v, p)
+                v, p = vg.flat, pg.data.reshape(16, -1)
+        torch.cuda.synchronize()
+        finals.append((v.cpu(), p.cpu()))
+    assert torch.equal(finals[0][0], finals[1][0]) and torch.equal(finals[0][1], finals[1][1])
+    sim = build_sim(s)
+    velocity = dp.StaggeredGrid(flat=torch.as_tensor(vel).to(DEV), resolution=(ny, nx), dx=(s["dy"], s["dx"]))
+    pressure = dp.CenteredGrid(torch.zeros(16, ny, nx, 1, device=DEV), dx=(s["dy"], s["dx"]), extrapolation="periodic")
+    c = P.make_step_context(velocity, pressure, pressure, s["dt"], sim)
+    assert P._stream_groups(sim, c, 64) == 1
+    sim.stream_groups = "auto"
+    assert P._stream_groups(sim, c, 16) == 2 and P._stream_groups(sim, c, 64) == 4 and P._stream_groups(sim, c, 8) == 1
+    sim.stream_groups = 3
+    assert P._stream_groups(sim, c, 2) == 2
