@@ -1,0 +1,9 @@
+L=differentiable-piso_b200/diffpiso_b200
+DPISO_LIBRARY=$L/libdpiso_old.so timeout 600 python scripts/cg_bitcmp.py --out gpurun_out/cg_old.npz 2>&1 | tail -2
+timeout 600 python scripts/cg_bitcmp.py --out gpurun_out/cg_new.npz 2>&1 | tail -2
+python scripts/cg_bitcmp.py --compare gpurun_out/cg_old.npz gpurun_out/cg_new.npz 2>&1 | tail -15
+DPISO_LIBRARY=$L/libdpiso_old.so timeout 120 python scripts/cg_micro.py --batch 64 2>&1 | tail -1 | cut -c1-120
+timeout 120 python scripts/cg_micro.py --batch 64 2>&1 | tail -1 | cut -c1-120
+timeout 120 python scripts/cg_micro.py --batch 33 2>&1 | tail -1 | cut -c1-120
+DPISO_LIBRARY=$L/libdpiso_timing.so timeout 300 python scripts/cg_timing.py 1 33 64 2>&1 | tail -3
+rm -f gpurun_out/cg_old.npz gpurun_out/cg_new.npz
