@@ -112,7 +112,9 @@ class SampleGroups(object):
             torch.cuda.synchronize(self.device)
             for i, st in enumerate(self.streams):
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=st):
+                # thread_local: only the capturing thread is held to the capture rules -- a process that also runs NCCL has a
+                # watchdog thread polling events, which the default "global" mode would turn into a capture error
+                with torch.cuda.graph(g, stream=st, capture_error_mode="thread_local"):
                     out = self.fn(*self._in[i])
                 self._graphs[i] = g
                 self._out[i] = self._as_tuple(out)
