@@ -473,7 +473,7 @@ def run_ours(args):
         sys.path.insert(0, os.path.join(ROOT, "scripts"))
         import training_bench
         try:
-            training = training_bench.measure(types.SimpleNamespace(config="tml", batch=8, unroll=16, iters=2, warmup=1),
+            training = training_bench.measure(types.SimpleNamespace(config="tml", batch=8, unroll=16, iters=1, warmup=1),
                                               dev, rank, world)
         except Exception as e:                                   # never lose the headline line to the extra key
             training = {"error": repr(e)[:200]}

@@ -22,6 +22,17 @@ def main(path):
     lines = open(path, errors="replace").read().splitlines()
     start = next(i for i, l in enumerate(lines) if l.startswith('"ID"'))
     rows = list(csv.DictReader(lines[start:]))
+    table(rows, peak, "all launches of the command (sample-group launches on their own streams included)")
+    # bench.py runs its per-kernel pass (and the forward-only rollout) with the whole batch per launch on the caller's
+    # stream, the sample groups on side streams: the first profiled launch belongs to the caller's stream
+    main = rows[0]["Stream"]
+    sel = [r for r in rows if r["Stream"] == main]
+    if len(sel) != len(rows):
+        print()
+        table(sel, peak, "launches on the caller's stream only (whole batch per launch: the per-kernel pass of bench.py)")
+
+
+def table(rows, peak, title):
     per = OrderedDict()
     for r in rows:
         name = re.sub(r"\(.*", "", r["Kernel Name"]).strip()
@@ -30,6 +41,7 @@ def main(path):
         val = float(r["Metric Value"].replace(",", ""))
         d["m"][r["Metric Name"]] += val * UNIT.get(r["Metric Unit"], 1.0)
     total = sum(d["m"]["gpu__time_duration.sum"] for d in per.values())
+    print("%s\n" % title)
     print("| kernel | launches | mean time (us) | share of GPU time | DRAM read+write per launch (MB) | DRAM GB/s | %% of HBM peak (%.1f GB/s) |" % peak)
     print("|---|---|---|---|---|---|---|")
     for name, d in sorted(per.items(), key=lambda kv: -kv[1]["m"]["gpu__time_duration.sum"]):
