@@ -6,8 +6,10 @@ tolerances (residual_reset 1000).
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one PISO step of the whole batch, forward AND adjoint (loss gradient back to the step's inputs), advancing
-a rollout.  `value` = batch * ny * nx * n_gpus * steps / time with inputs resident in HBM; `e2e` = the same through
-piso_step with HOST buffers (pinned H2D of the state, D2H of the new state and gradient every step).  The batch is
+a rollout.  The batch of a GPU runs as `--groups` independent sample pipelines (diffpiso_b200.SampleGroups: one stream and
+one CUDA graph per group; bit-identical to the one-stream batch).  `value` = batch * ny * nx * n_gpus * steps / time with
+inputs resident in HBM; `e2e` = the same with HOST buffers (pinned H2D of the state, D2H of the new state and gradients,
+every step of every group).  A per-kernel pass (the same steps eagerly on one stream) feeds the rooflines.  The batch is
 sharded over GPUs with no data-path collective (weak scaling: 64 samples per GPU).
 `--impl reference` times the reference's CPU path = the oracle port (the reference has no CPU implementation of the
 step and its CUDA path cannot be built here) on all host cores, bounded sample.
@@ -20,6 +22,10 @@ import subprocess
 import sys
 import tempfile
 import time
+
+# one hardware queue per sample-group stream (the default of 8 is enough for the default 8 groups; more groups alias
+# queues and serialise: 16 groups 8.9 ms per step with 8 queues, 8.0 ms with 32).  Read at CUDA initialisation.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for _p in (ROOT, os.path.join(ROOT, "differentiable-piso_b200")):
