@@ -153,7 +153,50 @@ def run_reference(args):
 # our arm
 # ------------------------------------------------------------------------------------------------------------------
 class ClockSampler(object):
+    """SM clock and throttle reasons sampled DURING a timed region: an NVML thread in this process (a sample every 5 ms,
+    the first one immediately; the regions last ~80 ms), or -- without the NVML bindings -- an `nvidia-smi -lms` child."""
+
+    _REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+
     def __init__(self, index):
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.thread = self.p = None
+        try:
+            import threading
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nv = pynvml
+            self.mx.append(float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)))
+            self.stop_flag = threading.Event()
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self._sample()
+            self.thread.start()
+        except Exception:
+            self.thread = None
+            self._start_smi(index)
+
+    def _sample(self):
+        nv = self.nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        try:
+            mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+        except Exception:
+            mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+        for name, bit in self._REASONS:
+            if mask & bit:
+                self.reasons.add(name)
+
+    def _loop(self):
+        while not self.stop_flag.wait(0.005):
+            try:
+                self._sample()
+            except Exception:
+                break
+
+    def _start_smi(self, index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -165,6 +208,15 @@ class ClockSampler(object):
             self.p = None
 
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag.set()
+            self.thread.join()
+            try:
+                self._sample()
+            except Exception:
+                pass
+            return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": max(self.mx), "reasons": sorted(self.reasons),
+                    "samples": len(self.sm), "source": "nvml"}
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.p.terminate()
@@ -183,7 +235,7 @@ class ClockSampler(object):
                 if len(r) > 5 + k and "Active" in r[5 + k] and "Not" not in r[5 + k]:
                     reasons.add(nme)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def run_config5(dev, hbm_peak, n=1024, batch=8, steps=2, cg_max_it=20000):
@@ -438,16 +490,26 @@ def run_ours(args):
     torch.cuda.synchronize()
 
     def e2e_steps(n):
-        for _ in range(n):
+        """n steps of every group.  A group's next step is issued as soon as the host has its previous results (state +
+        gradients downloaded: the group's `done` event), whichever group that is -- the host polls the events instead of
+        waiting for the groups in a fixed order."""
+        left = [n] * groups
+        done = [None] * groups
+        while any(left) or any(d is not None for d in done):
             for i in range(groups):
-                runner.sync(i)                       # the host owns group i's previous results (state + gradients)
-                runner.load(i, h_in[i][0], h_in[i][1], None, None)
-                runner.launch(i)
-                runner.fetch(i, *h_out[i])
-                h_in[i][0], h_out[i][0] = h_out[i][0], h_in[i][0]       # next step reads what this step writes
-                h_in[i][1], h_out[i][1] = h_out[i][1], h_in[i][1]
-        for i in range(groups):
-            runner.sync(i)
+                if done[i] is not None:
+                    if not done[i].query():
+                        continue
+                    done[i] = None                   # the host owns group i's results from here on
+                if left[i]:
+                    runner.load(i, h_in[i][0], h_in[i][1], None, None)
+                    runner.launch(i)
+                    runner.fetch(i, *h_out[i])
+                    done[i] = torch.cuda.Event()
+                    done[i].record(runner.streams[i])
+                    h_in[i][0], h_out[i][0] = h_out[i][0], h_in[i][0]       # next step reads what this step writes
+                    h_in[i][1], h_out[i][1] = h_out[i][1], h_in[i][1]
+                    left[i] -= 1
     e2e_steps(2)                                         # untimed: warm-up of this loop
     barrier()
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

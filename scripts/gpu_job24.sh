@@ -1,4 +1,4 @@
-timeout 900 python bench.py --steps 10 --warmup 3 --no-config5 --no-training > gpurun_out/bench_g8.json 2> gpurun_out/bench_g8.err; tail -3 gpurun_out/bench_g8.err
+timeout 900 python bench.py --steps 10 --warmup 3 --no-config5 --no-training --no-cpu-baseline > gpurun_out/bench_g8.json 2> gpurun_out/bench_g8.err; tail -3 gpurun_out/bench_g8.err
 python - <<'PY'
 import json
 d=json.loads(open('gpurun_out/bench_g8.json').read().strip().splitlines()[-1])
