@@ -83,10 +83,14 @@ class SampleGroups(object):
         if any(int(t.shape[0]) != b for t in inputs):
             raise ValueError("every input must have the batch as its leading dimension")
         if device is None:
-            device = next((t.device for t in inputs if t.is_cuda), torch.device("cuda", torch.cuda.current_device()))
+            device = next((t.device for t in inputs if t.is_cuda), None)
+            if device is None:
+                if not torch.cuda.is_available():
+                    raise ValueError("SampleGroups runs on a CUDA device: there is no CPU path")
+                device = torch.device("cuda", torch.cuda.current_device())
         self.device = torch.device(device)
         if self.device.type != "cuda":
-            raise ValueError("SampleGroups runs on a CUDA device")
+            raise ValueError("SampleGroups runs on a CUDA device: there is no CPU path")
         self.fn = fn
         self.groups = max(1, min(int(groups), b))
         self.bounds = [shard_bounds(b, self.groups, i) for i in range(self.groups)]

@@ -113,3 +113,21 @@ def test_reference_arm_prints_one_contract_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
     assert line["config"]["workload"].startswith("decaying_turbulence_periodic_128x128")
+
+
+def test_sample_groups_argument_checks_without_a_gpu():
+    """`SampleGroups` (sample groups on concurrent CUDA streams) validates its inputs before it touches CUDA and has no
+    CPU path; the group boundaries are the same contiguous split the ranks use."""
+    import torch
+    from diffpiso_b200 import sharding
+    fn = lambda a: (a,)
+    with pytest.raises(ValueError, match="at least one"):
+        sharding.SampleGroups(fn, (), groups=2)
+    with pytest.raises(ValueError, match="leading dimension"):
+        sharding.SampleGroups(fn, (torch.zeros(4, 3), torch.zeros(3, 3)), groups=2)
+    with pytest.raises(ValueError, match="CUDA"):
+        sharding.SampleGroups(fn, (torch.zeros(4, 3),), groups=2, device="cpu")
+    if not torch.cuda.is_available():
+        with pytest.raises(ValueError, match="CUDA"):
+            sharding.SampleGroups(fn, (torch.zeros(4, 3),), groups=2)
+    assert [sharding.shard_bounds(10, 4, i) for i in range(4)] == [(0, 3), (3, 3), (6, 2), (8, 2)]
