@@ -461,20 +461,40 @@ def run_ours(args):
     bicg_ms = [a.elapsed_time(b) for a, b, _ in bicg_events]
     bicg_its = np.concatenate([st.cpu().numpy()[:, :, 0].ravel() for _, _, st in bicg_events]).astype(np.float64)
 
-    # ---- forward-only rollout (reported beside the headline; eager, one stream) ---------------------------------------
+    # ---- forward-only rollout (reported beside the headline): the same sample groups, forward step only -------------------
+    def group_forward(vel, pres):
+        nb = vel.shape[0]
+        with torch.no_grad():
+            velocity = dp.StaggeredGrid(flat=vel, resolution=(NY, NX), dx=dxy, extrapolation="periodic")
+            pressure = dp.CenteredGrid(pres.reshape(nb, NY, NX, 1), dx=dxy, extrapolation="periodic")
+            v_new, p_new, _ = dp.piso_step(velocity, pressure, pressure, pressure, s["dt"], sim, dvals)
+        return v_new.flat, p_new.data.reshape(nb, nc)
+    fwd_runner = dp.SampleGroups(group_forward, (vel, pres), groups=groups, graph=args.graph)
+    for _ in range(args.warmup):
+        fwd_runner.step(feedback)
+    fwd_runner.join()
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    vf, pf = vel.clone(), pres.clone()
     f0.record()
-    with torch.no_grad():
-        for _ in range(args.steps):
-            velocity = dp.StaggeredGrid(flat=vf, resolution=(NY, NX), dx=dxy, extrapolation="periodic")
-            pressure = dp.CenteredGrid(pf.reshape(BATCH, NY, NX, 1), dx=dxy, extrapolation="periodic")
-            v_new, p_new, _ = dp.piso_step(velocity, pressure, pressure, pressure, s["dt"], sim, dvals)
-            vf, pf = v_new.flat, p_new.data.reshape(BATCH, nc)
+    for st_ in fwd_runner.streams:
+        st_.wait_event(f0)
+    for _ in range(args.steps):
+        fwd_runner.step(feedback)
+    fwd_runner.join()
     f1.record()
     barrier()
     ms_fwd = f0.elapsed_time(f1)
+    finite = finite and bool(torch.isfinite(fwd_runner.gather(0)).all())
+    del fwd_runner
+    # the same forward-only steps eagerly on one stream
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    vf, pf = vel.clone(), pres.clone()
+    f0.record()
+    for _ in range(args.steps):
+        vf, pf = group_forward(vf, pf)
+    f1.record()
+    barrier()
+    ms_fwd_serial = f0.elapsed_time(f1)
 
     # ---- end-to-end: host buffers in, host buffers out, every step of every group ---------------------------------------
     # The same runner, driven with HOST buffers: every step a group uploads its state from pinned host memory, runs forward
@@ -632,7 +652,7 @@ def run_ours(args):
                           "note": "the same steps run eagerly with the whole batch on one stream (the per-kernel pass the "
                                   "rooflines are taken from)"},
         "forward_only": {"value": cells * args.steps / (ms_fwd * 1e-3), "unit": "cell-updates/s",
-                         "ms_per_step": ms_fwd / args.steps},
+                         "ms_per_step": ms_fwd / args.steps, "single_stream_ms_per_step": ms_fwd_serial / args.steps},
         "e2e": {"value": cells * args.steps / (ms_e2e * 1e-3), "unit": "cell-updates/s",
                 "h2d_bytes_per_step": int(BATCH * (nf + nc) * 4), "d2h_bytes_per_step": int(2 * BATCH * (nf + nc) * 4)},
         "gpu_launches": n_launch,
