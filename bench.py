@@ -414,7 +414,17 @@ def run_ours(args):
     # ---- headline: the batch as `groups` independent sample pipelines (diffpiso_b200.SampleGroups), each captured once
     # as a CUDA graph; a step = one launch of every group, the new state fed back as the next step's input -------------
     groups = max(1, min(args.groups, BATCH))
-    runner = dp.SampleGroups(group_step, (vel, pres, w_u, w_p), groups=groups, graph=args.graph)
+    def make_runner(fn, inputs):
+        """Sample groups with one CUDA graph each; if capture fails on this box the same groups run eagerly (recorded)."""
+        if args.graph:
+            try:
+                return dp.SampleGroups(fn, inputs, groups=groups, graph=True)
+            except Exception as e:                               # never lose the bench line to a capture problem
+                sys.stderr.write("CUDA graph capture failed (%r): running the sample groups eagerly\n" % (e,))
+                torch.cuda.synchronize()
+                args.graph = False
+        return dp.SampleGroups(fn, inputs, groups=groups, graph=False)
+    runner = make_runner(group_step, (vel, pres, w_u, w_p))
     feedback = {0: 0, 1: 1}
     for _ in range(args.warmup):
         runner.step(feedback)
@@ -469,7 +479,7 @@ def run_ours(args):
             pressure = dp.CenteredGrid(pres.reshape(nb, NY, NX, 1), dx=dxy, extrapolation="periodic")
             v_new, p_new, _ = dp.piso_step(velocity, pressure, pressure, pressure, s["dt"], sim, dvals)
         return v_new.flat, p_new.data.reshape(nb, nc)
-    fwd_runner = dp.SampleGroups(group_forward, (vel, pres), groups=groups, graph=args.graph)
+    fwd_runner = make_runner(group_forward, (vel, pres))
     for _ in range(args.warmup):
         fwd_runner.step(feedback)
     fwd_runner.join()
