@@ -369,8 +369,9 @@ def run_ours(args):
         velocity = dp.StaggeredGrid(flat=vel, resolution=(NY, NX), dx=dxy, extrapolation="periodic")
         pressure = dp.CenteredGrid(pres.reshape(nb, NY, NX, 1), dx=dxy, extrapolation="periodic")
         v_new, p_new, warn = dp.piso_step(velocity, pressure, pressure, pressure, s["dt"], sim, dvals)
-        loss = (v_new.flat * w_u).sum() + (p_new.data.reshape(nb, nc) * w_p).sum()
-        gv, gp = torch.autograd.grad(loss, (vel, pres))
+        # gradient of the loss sum(w_u * velocity) + sum(w_p * pressure) with respect to the step's inputs, as the
+        # vector-Jacobian product with the loss weights (no elementwise / reduction kernels around the native ones)
+        gv, gp = torch.autograd.grad([v_new.flat, p_new.data.reshape(nb, nc)], [vel, pres], [w_u, w_p])
         return v_new.flat.detach(), p_new.data.reshape(nb, nc).detach(), gv, gp
 
     def step(vel, pres):
