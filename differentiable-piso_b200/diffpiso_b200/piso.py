@@ -197,9 +197,9 @@ def _stream_groups(sim, c, b):
     """Number of sample groups `piso_step` itself forks for a batch of b samples: `SimulationParameters.stream_groups`
     (or DPISO_STREAM_GROUPS), default 1.  Opt-in because inside ONE call all groups pass through the same phase together
     (measured gain 4-5 %: 10.09 -> 9.56 ms with 4 groups); the larger gain needs pipelines that are independent across
-    forward, adjoint and steps -- `sharding.SampleGroups`, 16-20 %.  "auto" = 4 groups from 32 samples, 2 from 16, where both solver plug-ins
-    are native and the pressure CG keeps its state on chip (larger grids already fill the GPU with one cooperative
-    launch), never while a CUDA graph is being captured."""
+    forward, adjoint and steps -- `sharding.SampleGroups`, 20 %.  "auto" = 4 groups from 32 samples, 2 from 16, where both
+    solver plug-ins are native and the pressure CG keeps its state on chip (larger grids already fill the GPU with one
+    cooperative launch), never while a CUDA graph is being captured."""
     import os
     want = getattr(sim, "stream_groups", None)
     if want is None:
