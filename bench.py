@@ -37,6 +37,12 @@ import numpy as np  # noqa: E402
 NY = NX = 128
 BATCH = 64
 WORKLOAD = "decaying_turbulence_periodic_128x128_batch64_fwd+adjoint"
+# the workload both arms (--impl ours / reference) run: identical `config` in their JSON lines; what is specific to the GPU
+# implementation (launch geometry, sample groups) goes into the `execution` key of our line
+WORKLOAD_CONFIG = {"workload": WORKLOAD, "grid": [NY, NX], "batch_per_gpu": BATCH, "visc": 1e-3, "cfl": 0.5,
+                   "bicgstab": "fp32 tol 1e-8", "pressure_cg": "fp64 tol 1e-8 reset 1000",
+                   "l2": "inputs larger than L2: per-step working set (~0.4 GB of solver workspace + state) against 126 MB; "
+                         "the rollout state changes every step"}
 # algorithmic bytes per cell per CG iteration (fp64, 5 stored coefficients) and per reset
 CG_BYTES_PER_CELL_ITER = 168
 CG_BYTES_PER_CELL_RESET = 88
@@ -141,7 +147,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "piso_cell_updates_per_s_fwd_adjoint", "value": value, "unit": "cell-updates/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "grid": [NY, NX], "batch_per_gpu": BATCH},
+            "config": dict(WORKLOAD_CONFIG),
             "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": cores, "kind": "port",
                              "sample": "%d samples (one per core) x %d fwd+adjoint steps of the 128x128 case per timed step, %d timed steps"
                                        % (cores, REF_CHUNK, args.steps)},
@@ -466,6 +472,7 @@ def run_ours(args):
     barrier()
     ms_serial = k0.elapsed_time(k1)
     n_launch = launches["n"] * groups                              # launches inside the headline region (all groups)
+    cfg = ops.pressure_cg_config()                                 # launch geometry of the headline grid
     ops.pressure_cg, ops.bicgstab_ilu = orig_cg, orig_bicg
     cg_ms = [a.elapsed_time(b) for a, b, _ in cg_events]
     cg_its = np.concatenate([it.cpu().numpy() for _, _, it in cg_events]).astype(np.float64)
@@ -597,7 +604,6 @@ def run_ours(args):
         except Exception:
             return {}
     cg_prof, bicg_prof = prof("cg_dram_traffic.json"), prof("bicg_dram_traffic.json")
-    cfg = ops.pressure_cg_config()
     # ---- dominant kernel: the cluster-resident pressure CG (rank 0's launches) -------------------------------------
     mean_it = float(cg_its.mean())
     cg_avg_ms = float(np.mean(cg_ms))
@@ -654,11 +660,9 @@ def run_ours(args):
         "metric": "piso_cell_updates_per_s_fwd_adjoint", "value": value, "unit": "cell-updates/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "grid": [NY, NX], "batch_per_gpu": BATCH, "visc": 1e-3, "cfl": 0.5,
-                   "bicgstab": "fp32 tol 1e-8", "pressure_cg": "fp64 tol 1e-8 reset 1000",
-                   "l2": "per-step working set (~0.4 GB of solver workspace + state) exceeds the 126 MB L2; rollout "
-                         "state changes every step", "cg_launch": cfg, "same_seeds": bool(args.same_seeds),
-                   "sample_groups": groups, "cuda_graph_per_group": bool(args.graph)},
+        "config": dict(WORKLOAD_CONFIG),
+        "execution": {"cg_launch": cfg, "same_seeds": bool(args.same_seeds), "sample_groups": groups,
+                      "cuda_graph_per_group": bool(args.graph)},
         "single_stream": {"ms_per_step": ms_serial_all / args.steps, "value": cells * args.steps / (ms_serial_all * 1e-3),
                           "note": "the same steps run eagerly with the whole batch on one stream (the per-kernel pass the "
                                   "rooflines are taken from)"},
